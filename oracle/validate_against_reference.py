@@ -1,0 +1,162 @@
+"""TEST INFRASTRUCTURE (build container only): pin oracle/refmath.py to the UNMODIFIED reference.
+
+Runs every case of oracle/cases.py through the reference classes imported in place from /root/reference
+(models.moe / poe / mopoe / dmvae -> objective(batch), with stand-in VAEs and injected noise) and through the
+restatement, and asserts agreement of loss, kld, reconstruction terms and every gradient.  Also checks the
+function-level pieces (product_of_experts, ReconLoss.*, mixture_component_selection bounds, kl formulas).
+
+    PYTHONHASHSEED=0 python -m oracle.validate_against_reference
+"""
+import itertools
+import os
+import sys
+
+import torch
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, _ROOT)
+
+from oracle import cases, ref_inplace, refmath  # noqa: E402
+
+RTOL = 2e-6  # two fp32 CPU evaluations of the same formulas; differences are summation order only
+
+
+def reference_poe_subsets(utils, batch):
+    """The order subsample_input_modalities (utils.py:86-112) actually produced in this process."""
+    subs = []
+    for mi in utils.subsample_input_modalities(batch):
+        subs.append(tuple(i for i, k in enumerate(batch.keys()) if mi[k]["data"] is not None))
+    return subs
+
+
+def run_reference(case):
+    models, objectives, utils = ref_inplace.load()
+    vaes = cases.build_vaes(case)
+    cls = getattr(models, case["model"])
+    model = cls(vaes, case["D"], {"obj": case["obj"], "beta": case["beta"], "K": case["K"]}, None)
+    with torch.no_grad():
+        model._pz_params[1].copy_(case["pz_logits"])
+    if case["obj"] == "iwae":  # N1 shim: tuple with a .cuda() method, arithmetic untouched
+        base_prop = cls.pz_params
+        patched = type(cls.__name__ + "N1", (cls,), {
+            "pz_params": property(lambda self: ref_inplace.PzParams(base_prop.fget(self)))})
+        model.__class__ = patched
+    batch = cases.build_batch(case)
+    subsets = reference_poe_subsets(utils, batch) if case["model"] == "poe" else None
+    with ref_inplace.NoiseInjector([n.clone() for n in case["noise"]]) as inj:
+        out = model.objective(batch)
+        assert not inj.noises, "reference consumed %d fewer noise tensors than planned" % len(inj.noises)
+    out["loss"].backward()
+    leaves = cases.named_leaves(vaes, model._pz_params[1])
+    res = cases.collect(out, leaves)
+    return res, subsets
+
+
+def compare(a, b, name, rtol=RTOL):
+    worst = 0.0
+    for k in sorted(set(a) | set(b)):
+        if k.startswith("_"):
+            continue
+        if k not in a or k not in b:
+            if k == "reconstruction_loss" or k == "kld":
+                continue
+            raise AssertionError("%s: key %s missing on one side" % (name, k))
+        x, y = a[k], b[k]
+        if x is None or y is None:
+            zx = x is None or float(x.abs().max()) == 0.0
+            zy = y is None or float(y.abs().max()) == 0.0
+            assert zx and zy, "%s: %s is None on one side but non-zero on the other" % (name, k)
+            continue
+        assert x.shape == y.shape, "%s: %s shape %s vs %s" % (name, k, tuple(x.shape), tuple(y.shape))
+        denom = max(float(x.abs().max()), 1e-12)
+        err = float((x - y).abs().max()) / denom
+        worst = max(worst, err)
+        assert err <= rtol, "%s: %s differs rel %.3e" % (name, k, err)
+    return worst
+
+
+def check_functions():
+    models, objectives, utils = ref_inplace.load()
+    g = torch.Generator().manual_seed(7)
+    # a1 product_of_experts
+    mu, lv = torch.randn(4, 9, 5, generator=g), torch.rand(4, 9, 5, generator=g)
+    ra = models.mmvae_base.TorchMMVAE.product_of_experts(mu, lv)
+    rb = refmath.product_of_experts(mu, lv)
+    assert torch.equal(ra[0], rb[0]) and torch.equal(ra[1], rb[1])
+    # a13 chunk bounds, bit exact, through the reference method on a bare object
+    mop = models.mopoe.__new__(models.mopoe)
+    n = 0
+    for S in (1, 2, 3, 5, 7, 15, 31, 63):
+        for B in list(range(1, 70)) + [100, 127, 128, 255, 256, 1000, 1024, 4096, 65536, 99991]:
+            mus = torch.arange(B, dtype=torch.float32).reshape(1, B, 1).repeat(S, 1, 1) + \
+                1e6 * torch.arange(S, dtype=torch.float32).reshape(S, 1, 1)
+            w = (1 / float(S)) * torch.ones(S)
+            sel, _ = mop.moe_fusion(mus, mus.clone(), w)
+            ref_map = (sel.reshape(-1) // 1e6).to(torch.int32)
+            assert torch.equal(ref_map, refmath.mopoe_row_to_subset(S, B)), (S, B)
+            n += 1
+    # a19-a22 ReconLoss through recon_loss_fn
+    obj = objectives.MultimodalObjective("elbo", 1.0)
+    import torch.distributions as dist
+    for ltype, lik, shape in [("bce", "normal", (6, 3, 4, 4)), ("mse", "normal", (6, 7)), ("l1", "normal", (6, 7)),
+                              ("category_ce", "normal", (6, 5, 27)), ("category_ce", "normal", (6, 9)),
+                              ("lprob", "normal", (6, 11)), ("lprob", "laplace", (6, 11)),
+                              ("optimal_sigma", "normal", (6, 3, 4))]:
+        for K in (1, 3):
+            x = torch.randn(K * shape[0], *shape[1:], generator=g)
+            if ltype == "bce":
+                x = torch.sigmoid(x)
+                x[0].fill_(0.0)  # exercises the log clamp at -100
+                x[1].fill_(1.0)
+            t = torch.rand(shape, generator=g)
+            x1 = x.clone().requires_grad_(True)
+            x2 = x.clone().requires_grad_(True)
+            obj.set_ltype(ltype)
+            D = dist.Laplace if lik == "laplace" else dist.Normal
+            ra = obj.recon_loss_fn(D(x1, torch.tensor(0.75)), {"data": t, "masks": None}, K=K)
+            rb = refmath.recon_logp(ltype, x2, t, K, lik)
+            assert ra.shape == rb.shape and ra.dtype == rb.dtype, (ltype, ra.shape, rb.shape)
+            assert torch.allclose(ra, rb, rtol=1e-6, atol=0), ltype
+            wgt = torch.randn(ra.shape, generator=g).to(ra.dtype)
+            (ra * wgt).sum().backward()
+            (rb * wgt).sum().backward()
+            assert torch.allclose(x1.grad, x2.grad, rtol=1e-6, atol=1e-9), ltype
+            n += 1
+    # a23 kl closed forms
+    for (d1, f) in [(dist.Normal, refmath.kl_normal_normal), (dist.Laplace, refmath.kl_laplace_normal)]:
+        l, s = torch.randn(5, 4, generator=g), torch.rand(5, 4, generator=g) + 0.1
+        l0, s0 = torch.randn(1, 4, generator=g), torch.rand(1, 4, generator=g) + 0.5
+        assert torch.allclose(utils.kl_divergence(d1(l, s), dist.Normal(l0, s0)), f(l, s, l0, s0), rtol=1e-6)
+        n += 1
+    l, s = torch.randn(5, 4, generator=g), torch.rand(5, 4, generator=g) + 0.1
+    assert torch.allclose(utils.kl_divergence(dist.Laplace(l, s), dist.Laplace(l0, s0)),
+                          refmath.kl_laplace_laplace(l, s, l0, s0), rtol=1e-6)
+    # a25
+    v = torch.randn(6, 5, generator=g)
+    assert torch.equal(utils.log_mean_exp(v), refmath.log_mean_exp(v))
+    # a11 subsets order
+    for M in (2, 3, 4):
+        names = ["mod_%d" % (i + 1) for i in range(M)]
+        mop.vaes = {k: k for k in names}
+        keys = list(models.mopoe.set_subsets(mop).keys())
+        assert keys == ["_".join(names[i] for i in s) for s in refmath.mopoe_subsets(range(M))], keys
+    return n
+
+
+def main():
+    assert ref_inplace.available(), "needs /root/reference"
+    n = check_functions()
+    print("function-level checks ok (%d comparisons)" % n)
+    for case in cases.case_list():
+        ref, subsets = run_reference(case)
+        if subsets is not None:
+            case["poe_subsets"] = subsets
+        orc = cases.run_oracle(case)
+        worst = compare(ref, orc, case["name"])
+        print("%-22s loss=% .6f  worst rel diff vs reference %.2e  (%d tensors)" % (
+            case["name"], float(ref["loss"]), worst, len(ref)))
+    print("ORACLE PINNED: restatement == reference on all cases")
+
+
+if __name__ == "__main__":
+    main()
