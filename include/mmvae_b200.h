@@ -1,0 +1,232 @@
+/*
+ * mmvae_b200 -- C ABI of the B200-native latent + objective hot path of multimodal-vae-comparison.
+ *
+ * Boundary contract:
+ *   - extern "C" only; plain pointers and sizes; no torch types, no exceptions, no allocation, no host sync,
+ *     no global state.  The caller owns every buffer (inputs, outputs, workspaces) and they are DEVICE pointers.
+ *   - every call is stream ordered on `stream` (a cudaStream_t passed as void*); cudaSetDevice is the caller's job.
+ *   - return value: 0 ok; <0 argument error (MMVAE_E_*); >0 a cudaError_t from the launch.
+ *   - row-major contiguous tensors unless a leading dimension (`ld*`, in ELEMENTS) is given.
+ *   - "rows" of a reconstruction are k-major: row = k*B + b uses target row b (reference
+ *     objectives.py:103-125 reshape_for_loss: target.repeat(K,1,..)).
+ *
+ * Each entry point cites the reference code it replaces (paths relative to
+ * /root/reference/multimodal_compare).  The reference has no FFI: these are the functions a maintainer binds
+ * from Python via ctypes (INTEGRATION.md shows the stub), called by the torch.autograd.Functions of the drop-in
+ * model/objective plugins.
+ */
+#ifndef MMVAE_B200_H
+#define MMVAE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMVAE_ABI_VERSION 1
+
+/* the library is built with -fvisibility=hidden: only the entry points below are exported */
+#if defined(__GNUC__)
+#define MMVAE_API __attribute__((visibility("default")))
+#else
+#define MMVAE_API
+#endif
+
+/* error codes (negative) */
+#define MMVAE_E_ARG   (-1) /* null pointer / non-positive size                     */
+#define MMVAE_E_ENUM  (-2) /* unknown dtype / ltype / dist enum                    */
+#define MMVAE_E_LIMIT (-3) /* size beyond a compiled-in limit (M, D, smem)         */
+
+/* element types of big streamed tensors (reconstructions, targets, their gradients) */
+enum { MMVAE_F32 = 0, MMVAE_BF16 = 1 };
+/* posterior / likelihood families (reference vae.py:142-147 dist_map) */
+enum { MMVAE_NORMAL = 0, MMVAE_LAPLACE = 1 };
+/* element-wise likelihood terms (reference objectives.py:389-458 ReconLoss.{bce,lprob,mse,l1}) */
+enum { MMVAE_LT_BCE = 0, MMVAE_LT_LPROB_NORMAL = 1, MMVAE_LT_LPROB_LAPLACE = 2, MMVAE_LT_MSE = 3, MMVAE_LT_L1 = 4 };
+
+#define MMVAE_MAX_MODS 8    /* modalities per model                       */
+#define MMVAE_MAX_COLS 256  /* latent columns per modality (shared+private) */
+
+MMVAE_API int mmvae_version(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Likelihood row reductions: replaces  (obj_fn.recon_loss_fn(px_z, x, K) * llik_scaling).sum(-1)
+ *   reference: objectives.py:30-52 (recon_loss_fn), :103-125 (reshape_for_loss), :389-458 (ReconLoss.*),
+ *   call sites mmvae_models.py:48-49, :54-55, :66-71, :177, :312-313, :448-449, :454.
+ *
+ *   out_rows[r] = lam * sum_p logp(recon[r,p] | target[r % B, p])           r in [0, rows), rows = K*B
+ *     BCE           t*max(log x,-100) + (1-t)*max(log(1-x),-100)      (F.binary_cross_entropy clamps)
+ *     LPROB_NORMAL  Normal(x, scale).log_prob(t), NaN -> 0            (objectives.py:422-423)
+ *     LPROB_LAPLACE Laplace(x, scale).log_prob(t), NaN -> 0
+ *     MSE           -(x-t)^2          L1   -|x-t|
+ *
+ * _fwd   : reads recon + target, writes out_rows.                                   bytes: R + T
+ * _bwd   : grad[r,p] = w_rows[r] * lam * dlogp/dx                                  bytes: 2R + T (+rows)
+ * _fused : one pass producing out_rows AND grad for weights known a priori (every ELBO): w = w_rows[r] if
+ *          w_rows != NULL else w_const.                                            bytes: 2R + T
+ *
+ * workspace: mmvae_loglik_workspace_bytes(rows, P, dtype) bytes (may be 0), used for a deterministic two stage
+ * row sum when a row is split over several CTAs (few rows, long rows).
+ * ------------------------------------------------------------------------------------------------------- */
+MMVAE_API int64_t mmvae_loglik_workspace_bytes(int64_t rows, int64_t P, int dtype_recon);
+
+MMVAE_API int mmvae_loglik_rowreduce_fwd(const void* recon, int64_t ld_recon, int dtype_recon,
+                               const void* target, int64_t ld_target, int dtype_target,
+                               int64_t rows, int64_t B, int64_t P, int ltype, float scale, float lam,
+                               float* out_rows, void* workspace, void* stream);
+
+MMVAE_API int mmvae_loglik_rowreduce_bwd(const void* recon, int64_t ld_recon, int dtype_recon,
+                               const void* target, int64_t ld_target, int dtype_target,
+                               int64_t rows, int64_t B, int64_t P, int ltype, float scale, float lam,
+                               const float* w_rows, void* grad_recon, int64_t ld_grad, void* stream);
+
+MMVAE_API int mmvae_loglik_rowreduce_fused(const void* recon, int64_t ld_recon, int dtype_recon,
+                                 const void* target, int64_t ld_target, int dtype_target,
+                                 int64_t rows, int64_t B, int64_t P, int ltype, float scale, float lam,
+                                 const float* w_rows, float w_const,
+                                 float* out_rows, void* grad_recon, int64_t ld_grad,
+                                 void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * category_ce rows: replaces ReconLoss.category_ce (objectives.py:485-500): nn.CrossEntropyLoss with
+ * probability targets -> the class axis is dim 1.  recon (rows, C, d) (d = 1 for 2-D inputs), target (B, C, d):
+ *   out_rows[r] = lam * sum_j sum_c t[c,j] * (x[c,j] - logsumexp_c x[:,j])
+ *   grad[r,c,j] = w * lam * (t[c,j] - softmax_c(x[:,j])[c] * sum_c' t[c',j])
+ * ld_recon / ld_grad: row stride in elements (>= C*d; a mask crop loc[:, :T] keeps the row stride,
+ * objectives.py:43-45).  mode: 0 fwd, 1 bwd, 2 fused (same meaning as above).
+ * ------------------------------------------------------------------------------------------------------- */
+MMVAE_API int mmvae_catce_rows(int mode, const void* recon, int64_t ld_recon, int dtype_recon,
+                     const void* target, int64_t ld_target, int dtype_target,
+                     int64_t rows, int64_t B, int64_t C, int64_t d, float lam,
+                     const float* w_rows, float w_const,
+                     float* out_rows, void* grad_recon, int64_t ld_grad, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * optimal_sigma (sigma-VAE) rows: replaces ReconLoss.optimal_sigma (objectives.py:502-509) + utils.softclip
+ * (utils.py:66-69).  Three stream-ordered stages so that a multi-GPU caller can all-reduce the scalar between
+ * stage 1 and 2:
+ *   _sumsq : sumsq[0] += sum_all (t - x)^2      (double accumulator, caller zeroes it)
+ *   _fwd   : log_sigma = -6 + softplus(log sqrt(sumsq/n_total) + 6);
+ *            out_rows[r] = -lam * sum_p [ ((t-x)/sigma)^2 + log_sigma + 0.5 log 2pi ]; stats = {log_sigma, dlogsigma/du}
+ *   _bwd   : only log_sigma carries gradient (the squared term is detached):
+ *            grad[i] = -lam * P * (sum_r w_rows[r]) * sigmoid(u+6) * (x_i - t_i) / sumsq
+ * ------------------------------------------------------------------------------------------------------- */
+MMVAE_API int mmvae_osigma_sumsq(const void* recon, int64_t ld_recon, int dtype_recon,
+                       const void* target, int64_t ld_target, int dtype_target,
+                       int64_t rows, int64_t B, int64_t P, double* sumsq, void* stream);
+MMVAE_API int mmvae_osigma_fwd(const void* recon, int64_t ld_recon, int dtype_recon,
+                     const void* target, int64_t ld_target, int dtype_target,
+                     int64_t rows, int64_t B, int64_t P, float lam, const double* sumsq, double n_total,
+                     float* out_rows, float* stats2, void* workspace, void* stream);
+MMVAE_API int mmvae_osigma_bwd(const void* recon, int64_t ld_recon, int dtype_recon,
+                     const void* target, int64_t ld_target, int dtype_target,
+                     int64_t rows, int64_t B, int64_t P, float lam, const double* sumsq, double n_total,
+                     const float* w_rows, float* wsum_scratch, void* grad_recon, int64_t ld_grad, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Latent draws: product-of-experts fusion / direct posteriors, reparameterised sampling and KL rows.
+ * Replaces TorchMMVAE.product_of_experts (mmvae_base.py:203-222), POE.modality_mixing + prior_expert
+ * (mmvae_models.py:210-250), MoPOE.poe_fusion + mixture_component_selection (:385-410), the DMVAE joint
+ * (:478-480), every Normal/Laplace rsample on the path (:99, :201, :366, :481-499) and calc_kld ->
+ * torch.distributions.kl (objectives.py:148-161, utils.py:399-405).
+ *
+ * Encoder outputs: mu, s as (M, B, Dtot) fp32.  A draw j is described by mmvae_draw_desc:
+ *   fused (default): experts = modalities in `mask` (+ the prior expert (0,0) if MMVAE_DRAW_PRIOR) on columns
+ *          [col0, col0+width):  var_e = exp(s_e)+1e-8, T_e = 1/var_e, loc = sum mu_e T_e / sum T_e,
+ *          scale = 1/sum T_e   (the PoE *variance* is the Normal scale -- reference quirk, reproduced)
+ *   MMVAE_DRAW_DIRECT: loc, scale = mu_m, s_m of the single modality in `mask`
+ *   MMVAE_DRAW_ROWMASK: the expert set of row b is row_masks[b] (bit 31 = prior expert) -- MoPoE mixture
+ *          component selection as a row -> subset bitmask map
+ *   z[k,b,c]  = loc + scale * eps[k,b,c]          (Normal)          k < K  (K may be 0: no samples)
+ *             = loc - scale * sign(u) log1p(-|u|) (MMVAE_DRAW_LAPLACE, eps holds u)
+ *   kl[b]     = sum_c KL(q || prior): kl_mode 0 none, 1 vs learnable prior N(mu0, s0), 2 vs N(0,1);
+ *               q is Normal, or Laplace with MMVAE_DRAW_LAPLACE (torch kl.py _kl_laplace_normal)
+ * Offsets are in ELEMENTS into the caller's packed eps / z / par_loc / par_scale / kl buffers; -1 = not wanted.
+ * ------------------------------------------------------------------------------------------------------- */
+#define MMVAE_DRAW_PRIOR   1
+#define MMVAE_DRAW_DIRECT  2
+#define MMVAE_DRAW_LAPLACE 4
+#define MMVAE_DRAW_ROWMASK 8
+
+typedef struct {
+    uint32_t mask;
+    int32_t flags;
+    int32_t kl_mode;
+    int32_t col0, width;
+    int32_t K;
+    int64_t eps_off; /* (K,B,width) noise                      */
+    int64_t z_off;   /* (K,B,width) samples                    */
+    int64_t par_off; /* (B,width) loc and scale outputs, or -1 */
+    int64_t kl_off;  /* (B) KL rows, or -1                     */
+} mmvae_draw_desc;
+
+#define MMVAE_MAX_DRAWS 64
+
+MMVAE_API int mmvae_latent_draws_fwd(const float* mu, const float* s, int M, int64_t B, int Dtot,
+                           const mmvae_draw_desc* descs_host, int n_draws, const uint32_t* row_masks,
+                           const float* mu0, const float* s0, /* (D) learnable prior, may be NULL if unused */
+                           const float* eps, float* z, float* par_loc, float* par_scale, float* kl,
+                           void* stream);
+
+/* backward: dz (packed like z), dkl (packed like kl: per-row upstream grads), dpar_loc / dpar_scale (packed
+ * like par_*; may be NULL) -> dmu, ds (M,B,Dtot) fully written; dprior_ws: (2, grid, Dtot) partials followed by
+ * dmu0 (D), ds0 (D) written by the finalisation kernel; size from mmvae_latent_draws_bwd_ws_floats(). */
+MMVAE_API int64_t mmvae_latent_draws_bwd_ws_floats(int64_t B, int Dtot);
+MMVAE_API int mmvae_latent_draws_bwd(const float* mu, const float* s, int M, int64_t B, int Dtot,
+                           const mmvae_draw_desc* descs_host, int n_draws, const uint32_t* row_masks,
+                           const float* mu0, const float* s0,
+                           const float* eps, const float* dz, const float* dkl,
+                           const float* dpar_loc, const float* dpar_scale,
+                           float* dmu, float* ds, float* dprior_ws, float* dmu0, float* ds0, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * MoE sample + log-densities (fused): replaces MOE.forward's rsample (mmvae_models.py:99), the importance
+ * terms of the ELBO branch (:56-62) and the log p(z) / log-mean q_j(z) terms of MultimodalObjective.iwae /
+ * _m_dreg_looser (objectives.py:342-373).
+ *   z[r,k,b,:]   = rsample of q_r = dist_r(mu_r, s_r) with noise eps[r,k,b,:]
+ *   lq[r,j,k,b]  = sum_d log q_j(z[r,k,b,d])                      (M,M,K,B)
+ *   lpz[r,k,b]   = sum_d log N(z[r,k,b,d]; mu0_d, s0_d)           (M,K,B)
+ * backward: given dz_ext (grad reaching z from the decoders; may be NULL), dlq, dlpz ->
+ *   dmu, ds (M,B,D) and per-CTA partials of dmu0, ds0.  `through_z` = 0 reproduces the ELBO branch where z is
+ *   detached inside the log-densities (:58) -- dlq then only reaches the parameters of q_j.
+ * ------------------------------------------------------------------------------------------------------- */
+MMVAE_API int mmvae_moe_logdens_fwd(const float* mu, const float* s, int M, int64_t B, int D, int K, const int32_t* dists_host,
+                          const float* mu0, const float* s0, const float* eps,
+                          float* z, float* lq, float* lpz, void* stream);
+MMVAE_API int64_t mmvae_moe_logdens_bwd_ws_floats(int64_t B, int D, int K);
+MMVAE_API int mmvae_moe_logdens_bwd(const float* mu, const float* s, int M, int64_t B, int D, int K, const int32_t* dists_host,
+                          const float* mu0, const float* s0, const float* eps,
+                          const float* dz_ext, const float* dlq, const float* dlpz, int through_z,
+                          float* dmu, float* ds, float* dprior_ws, float* dmu0, float* ds0, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Objective combination (forward value + the per-row weights its backward needs, in one launch):
+ *   _iwae : MultimodalObjective.iwae objectives.py:342-359 (N1 shim) + utils.log_mean_exp utils.py:395-396
+ *           lw[r,k,b] = lpz + sum_l lpx[r,l,k,b] - beta * logmeanexp_j lq[r,j,k,b]
+ *           loss_b[b] = -(logsumexp_{r,k} lw - log(M K));   w[r,k,b] = softmax_{r,k}(lw) (= -dloss/dlw)
+ *           dlq[r,j,k,b] = beta * w * softmax_j(lq[r,:,k,b])
+ *   _dreg : _m_dreg_looser + dreg objectives.py:361-387 (parity mode: batch-summed log-weights)
+ *           stage 1: lw_part[r,k] = sum_b (lpz + sum_l lpx - logmeanexp_j lq)   (local batch shard)
+ *           [multi-GPU: all-reduce lw_part between the stages, SURVEY 8e (1)]
+ *           stage 2: wt = softmax_k(lw[r,:]); loss = -(1/M) sum_{r,k} wt*lw;  out wt (M,K)
+ *   _sum  : deterministic single-CTA sum of n floats (ELBO reductions objectives.py:54-67).
+ * ------------------------------------------------------------------------------------------------------- */
+MMVAE_API int mmvae_objective_iwae(const float* lpz, const float* lq, const float* lpx, int M, int L, int K, int64_t B,
+                         float beta, float* lw, float* loss_b, float* w, float* dlq, void* stream);
+/* lw_part: (MMVAE_DREG_MAX_SPLIT + 1) * M * K floats; the first M*K receive the local batch sums, the rest is
+ * scratch for the deterministic two-stage batch reduction.  lq_soft (M,M,K,B) = softmax_j(lq), may be NULL. */
+#define MMVAE_DREG_MAX_SPLIT 64
+MMVAE_API int mmvae_objective_dreg_stage1(const float* lpz, const float* lq, const float* lpx, int M, int L, int K, int64_t B,
+                                float* lw_part, float* lq_soft, void* stream);
+MMVAE_API int mmvae_objective_dreg_stage2(const float* lw, int M, int K, float* wt, float* loss, void* stream);
+MMVAE_API int mmvae_reduce_sum(const float* x, int64_t n, float scale, float* out, void* stream);
+
+/* in-place scale of a gradient buffer by a DEVICE scalar, skipped entirely (early exit) when the scalar == 1:
+ * lets the fused ELBO path keep autograd semantics for loss.backward(gradient=g) at zero cost when g == 1. */
+MMVAE_API int mmvae_scale_inplace(void* buf, int dtype, int64_t n, const float* scalar_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMVAE_B200_H */

