@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- objective fwd+bwd samples/s of the latent + objective hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload at N=1: BASELINE.json configs[1] -- MMVAE (MoE) IWAE K=30 on CdSprites+ level-5 shapes, batch 256, fp32
+(the configuration the metric is quoted on; it fits one GPU).  N>1 is batch sharded, weak scaling (256 samples per
+GPU), one NCCL all-reduce(SUM) of the replicated prior-logit gradient per step; no data-path collective.
+
+A "step" is one objective fwd+bwd on synthetic leaf tensors (SURVEY.md 8d protocol).  Inputs are resident in HBM for
+`value`; `e2e` repeats the measurement with every input in pinned HOST memory, H2D copies and the loss read-back
+inside the timed region.  Per-step working set (~1.6 GB) is far larger than the 126 MB L2, so no explicit flush.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEFAULT_WORKLOAD = "c2_moe_iwae_cdsprites_l5"
+METRIC = "objective fwd+bwd samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default: the workload's batch)")
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="samples per step of the bounded CPU sample")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class KernelTimer:
+    """CUDA events around selected C-ABI launches, on the launching (current) stream."""
+
+    def __init__(self, names):
+        import torch
+        self.torch, self.names, self.ev = torch, set(names), {n: [] for n in names}
+
+    def wrap(self, name, fn):
+        a, b = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn()
+        b.record()
+        self.ev[name].append((a, b))
+        return rc
+
+    def times_ms(self, name):
+        return [a.elapsed_time(b) for a, b in self.ev[name]]
+
+
+def reference_arm(args, rank, world):
+    """The reference's algorithm for this path on the box's host cores: /root/reference (pure Python/torch, nothing
+    to compile) is absent on the GPU box, so this is the oracle port (oracle/refmath.py, pinned to the in-place
+    reference by oracle/validate_against_reference.py) with all host threads, on a bounded sample per step."""
+    if rank != 0:
+        return
+    import torch
+    import mmvae_b200.workloads as W
+    from oracle import leafstep
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg, t = W.make_leaves(args.workload, B=args.cpu_batch, seed=1234)
+    for _ in range(max(args.warmup, 1)):
+        leafstep.run(cfg, t)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        leafstep.run(cfg, t)
+    dt = time.perf_counter() - t0
+    val = args.cpu_batch * args.steps / dt
+    sample = "%d samples/step of %s (same shapes, K=%d), %d steps" % (args.cpu_batch, args.workload, cfg["K"], args.steps)
+    line = {"metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": args.workload, "model": cfg["model"], "objective": cfg["obj"], "K": cfg["K"],
+                       "batch_per_step": args.cpu_batch},
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args):
+    import torch
+    import mmvae_b200.workloads as W
+    from oracle import leafstep
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg, t = W.make_leaves(args.workload, B=args.cpu_batch, seed=1234)
+    leafstep.run(cfg, t)
+    n, t0 = 0, time.perf_counter()
+    while n < 3 or (time.perf_counter() - t0 < 10 and n < 200):
+        leafstep.run(cfg, t)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": args.cpu_batch * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": "%d samples/step of %s (same shapes, K=%d), %d steps, %.1f s" % (
+                args.cpu_batch, args.workload, cfg["K"], n, dt)}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+    import mmvae_b200._lib as L
+    import mmvae_b200.workloads as W
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    L.load()
+    rdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    cfg, t = W.make_leaves(args.workload, B=args.batch, seed=1234 + rank, recon_dtype=rdt)
+    B = cfg["B"]
+    step = W.LeafStep(cfg, t, device=dev, group=group, global_batch=B * world)
+    W_, K_ = max(args.warmup, 3), args.steps
+
+    def sync_grads():
+        # the only replicated parameter on this leaf protocol is the prior logit vector: all-reduce(SUM) its grad
+        if world > 1:
+            dist.all_reduce(step.pz_logits.grad, group=group)
+
+    # launches of our kernels per step, counted on one eager step
+    step.run()
+    torch.cuda.synchronize()
+    c0 = L.launch_count
+    step.run()
+    launches_per_step = L.launch_count - c0
+    runner = step
+    # a collective inside the step (DReG batch sums, optimal_sigma RMS under sharding) keeps the step eager
+    needs_coll = world > 1 and (cfg["obj"] == "dreg" or any(m["ltype"] == "optimal_sigma" for m in cfg["mods"]))
+    if not args.no_graph and not needs_coll:
+        runner = W.GraphedStep(step)
+
+    def timed(nsteps, fn):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(nsteps):
+            fn()
+        b.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    def one():
+        runner.run()
+        sync_grads()
+
+    for _ in range(W_):
+        one()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = timed(K_, one)
+    clocks = sampler.stop() if rank == 0 else None
+    value = B * world * K_ / (ms / 1e3)
+
+    # roofline of the dominant kernel: CUDA events around every launch of it, eager steps, same inputs
+    dom = "mmvae_loglik_rowreduce_bwd" if cfg["obj"] != "elbo" else "mmvae_loglik_rowreduce_fused"
+    kt = KernelTimer([dom, "mmvae_loglik_rowreduce_fwd"])
+    L.timer = kt
+    for _ in range(min(K_, 10)):
+        step.run()
+    torch.cuda.synchronize()
+    L.timer = None
+    import math
+    big = max(range(len(cfg["mods"])), key=lambda i: math.prod(cfg["mods"][i]["data_dim"]))
+    P = int(math.prod(cfg["mods"][big]["data_dim"]))
+    e = 2 if rdt == torch.bfloat16 else 4
+    rows = (cfg["K"] if cfg["model"] == "moe" else 1) * B
+    R, T = rows * P * e, B * P * 4
+    dom_bytes = 2 * R + T + rows * 4
+    tms = kt.times_ms(dom)
+    tms = tms[len(tms) // 5:] if len(tms) >= 5 else tms
+    peak, peak_src = measured_peak()
+    ach = dom_bytes / (statistics.mean(tms) * 1e-3) / 1e9 if tms else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": (ach / peak) if ach else None, "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_launch": dom_bytes, "avg_ms": statistics.mean(tms) if tms else None,
+                "launches_timed": len(tms)}
+    fms = kt.times_ms("mmvae_loglik_rowreduce_fwd")
+    fms = fms[len(fms) // 5:] if len(fms) >= 5 else fms
+    if fms:
+        fb = R + T + rows * 4
+        roofline["fwd_kernel"] = {"achieved": fb / (statistics.mean(fms) * 1e-3) / 1e9, "bytes_per_launch": fb,
+                                  "avg_ms": statistics.mean(fms)}
+    step_bytes = W.algorithmic_bytes(cfg, rdt) * B
+    roofline["step"] = {"algorithmic_bytes": step_bytes, "achieved": step_bytes * K_ / (ms * 1e-3) / 1e9,
+                        "frac": step_bytes * K_ / (ms * 1e-3) / 1e9 / peak}
+
+    # end to end: every input of the step lives in pinned host memory; H2D + loss read-back inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        pairs = [(step.mu, t["mu"]), (step.s, t["s"]), (step.pz_logits, t["pz_logits"])]
+        pairs += list(zip(step.targets, t["targets"])) + list(zip(step.recon, t["recon"]))
+        if cfg["model"] == "moe":
+            pairs += list(zip(step.noise, t["noise"]))
+        else:  # the draws kernel reads one packed noise buffer
+            pairs.append((step.eps_packed, torch.cat([n.reshape(-1) for n in t["noise"]])))
+        pairs = [(d, h.contiguous().pin_memory()) for d, h in pairs]
+        h2d = sum(h.numel() * h.element_size() for _, h in pairs)
+        copy_stream = torch.cuda.Stream()
+
+        def e2e_step():
+            copy_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(copy_stream):
+                for d, h in pairs:
+                    d.data.copy_(h, non_blocking=True)
+            torch.cuda.current_stream().wait_stream(copy_stream)
+            loss = runner.run()
+            sync_grads()
+            return float(loss)  # device -> host read of the step's result
+
+        for _ in range(3):
+            e2e_step()
+        ke = max(3, min(K_, 10))
+        ems = timed(ke, e2e_step)
+        e2e = {"value": B * world * ke / (ems / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 4, "ms_per_step": ems / ke, "steps": ke,
+               "api": "mmvae_b200.workloads.LeafStep / GraphedStep (C-ABI kernels), pinned host inputs"}
+
+    line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K_, "warmup": W_,
+            "ms_per_step": ms / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if rdt == torch.bfloat16 else "f32", "data": "synthetic", "impl": "ours",
+            "config": {"workload": args.workload, "model": cfg["model"], "objective": cfg["obj"], "K": cfg["K"],
+                       "latent_dim": cfg["D"], "batch_per_gpu": B, "global_batch": B * world,
+                       "mods": [{"data_dim": list(m["data_dim"]), "ltype": m["ltype"]} for m in cfg["mods"]],
+                       "parallelism": "batch-sharded x%d, NCCL all-reduce of replicated grads" % world,
+                       "l2": "per-step working set %.2f GB >> 126 MB L2, no flush" % (step_bytes / 1e9),
+                       "launch_mode": "cuda-graph" if runner is not step else "eager"},
+            "roofline": roofline, "gpu_launches": launches_per_step * K_, "launches_per_step": launches_per_step,
+            "clocks": clocks}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -214,12 +214,14 @@ MMVAE_API int mmvae_moe_logdens_bwd(const float* mu, const float* s, int M, int6
  * ------------------------------------------------------------------------------------------------------- */
 MMVAE_API int mmvae_objective_iwae(const float* lpz, const float* lq, const float* lpx, int M, int L, int K, int64_t B,
                          float beta, float* lw, float* loss_b, float* w, float* dlq, void* stream);
-/* lw_part: (MMVAE_DREG_MAX_SPLIT + 1) * M * K floats; the first M*K receive the local batch sums, the rest is
- * scratch for the deterministic two-stage batch reduction.  lq_soft (M,M,K,B) = softmax_j(lq), may be NULL. */
+/* lw_part: (MMVAE_DREG_MAX_SPLIT + 1) * M * K DOUBLES; the first M*K receive the local batch sums, the rest is
+ * scratch for the deterministic two-stage batch reduction.  The sums are carried in fp64: they feed a softmax over
+ * K whose conditioning is set by their absolute error, and the reference holds them in fp64 for lprob likelihoods
+ * (objectives.py:422).  lq_soft (M,M,K,B) = softmax_j(lq), may be NULL. */
 #define MMVAE_DREG_MAX_SPLIT 64
 MMVAE_API int mmvae_objective_dreg_stage1(const float* lpz, const float* lq, const float* lpx, int M, int L, int K, int64_t B,
-                                float* lw_part, float* lq_soft, void* stream);
-MMVAE_API int mmvae_objective_dreg_stage2(const float* lw, int M, int K, float* wt, float* loss, void* stream);
+                                double* lw_part, float* lq_soft, void* stream);
+MMVAE_API int mmvae_objective_dreg_stage2(const double* lw, int M, int K, float* wt, float* loss, void* stream);
 MMVAE_API int mmvae_reduce_sum(const float* x, int64_t n, float scale, float* out, void* stream);
 
 /* in-place scale of a gradient buffer by a DEVICE scalar, skipped entirely (early exit) when the scalar == 1:

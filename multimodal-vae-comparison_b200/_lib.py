@@ -82,10 +82,18 @@ def load():
     return lib
 
 
+# optional per-kernel CUDA-event timer (bench.py roofline leg): object with .names and .wrap(name, fn)
+timer = None
+
+
 def call(name, *args):
     """Invoke an int-returning entry point and turn a non-zero status into a RuntimeError."""
     global launch_count
-    rc = getattr(load(), name)(*args)
+    fn = getattr(load(), name)
+    if timer is not None and name in timer.names:
+        rc = timer.wrap(name, lambda: fn(*args))
+    else:
+        rc = fn(*args)
     if rc != 0:
         kind = {-1: "bad argument", -2: "unknown enum", -3: "size limit"}.get(rc, "cudaError_t %d" % rc)
         raise RuntimeError("mmvae_b200: %s failed: %s" % (name, kind))

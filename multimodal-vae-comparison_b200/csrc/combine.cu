@@ -91,47 +91,58 @@ __global__ void __launch_bounds__(kIwaeWarps * 32) iwae_kernel(const CombParams 
 }
 
 // DReG stage 1: one CTA per ((r,k), batch split); writes partial batch sums and softmax_j(lq) for the backward.
-__global__ void __launch_bounds__(256) dreg_stage1_kernel(const CombParams p, float* __restrict__ part, int nsplit,
+__global__ void __launch_bounds__(256) dreg_stage1_kernel(const CombParams p, double* __restrict__ part, int nsplit,
                                                           float* __restrict__ lq_soft) {
-    __shared__ float red[32];
+    __shared__ double red[32];
     const int q = blockIdx.x, sp = blockIdx.y;
     const int r = q / p.K, k = q - r * p.K;
     const int64_t per = (p.B + nsplit - 1) / nsplit;
     const int64_t b0 = sp * per, b1 = min(p.B, b0 + per);
     float vals[MMVAE_MAX_MODS];
-    float acc = 0.f;
+    // batch sums feed a softmax over K: |lw| grows with B*P while the softmax needs its ABSOLUTE error small, and
+    // the reference carries these sums in fp64 whenever the likelihood is lprob (objectives.py:422) -> double here
+    double acc = 0.0;
     for (int64_t b = b0 + threadIdx.x; b < b1; b += blockDim.x) {
         float mx, se;
-        acc += lw_value(p, r, k, b, 1.0f, vals, mx, se);  // no beta in _m_dreg_looser (objectives.py:371)
+        acc += (double)lw_value(p, r, k, b, 1.0f, vals, mx, se);  // no beta in _m_dreg_looser (objectives.py:371)
         if (lq_soft) {
 #pragma unroll
             for (int j = 0; j < MMVAE_MAX_MODS; ++j)
                 if (j < p.M) lq_soft[(((int64_t)r * p.M + j) * p.K + k) * p.B + b] = expf(vals[j] - mx) / se;
         }
     }
-    const float tot = block_sum(acc, red);
+    const double tot = block_sum(acc, red);
     if (threadIdx.x == 0) part[(size_t)sp * p.M * p.K + q] = tot;
 }
 
+__global__ void dreg_partial_sum_kernel(const double* __restrict__ ws, int parts, int n, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double tot = 0.0;
+    for (int q = 0; q < parts; ++q) tot += ws[(size_t)q * n + i];
+    out[i] = tot;
+}
+
 // DReG stage 2 (single CTA, one warp per modality row): wt = softmax_k(lw[r,:]); loss = -(1/M) sum wt*lw
-__global__ void __launch_bounds__(256) dreg_stage2_kernel(const float* __restrict__ lw, int M, int K,
+__global__ void __launch_bounds__(256) dreg_stage2_kernel(const double* __restrict__ lw, int M, int K,
                                                           float* __restrict__ wt, float* __restrict__ loss) {
-    __shared__ float s_part[8];
+    __shared__ double s_part[8];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float mine = 0.f;
+    double mine = 0.0;
     for (int r = wid; r < M; r += 8) {
-        float mx = -INFINITY;
-        for (int k = lane; k < K; k += 32) mx = fmaxf(mx, lw[r * K + k]);
-        mx = warp_max(mx);
-        float se = 0.f;
-        for (int k = lane; k < K; k += 32) se += expf(lw[r * K + k] - mx);
+        double mx = -INFINITY;
+        for (int k = lane; k < K; k += 32) mx = fmax(mx, lw[r * K + k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        double se = 0.0;
+        for (int k = lane; k < K; k += 32) se += exp(lw[r * K + k] - mx);
         se = warp_sum(se);
-        const float lse = mx + logf(se);
-        float acc = 0.f;
+        const double lse = mx + log(se);
+        double acc = 0.0;
         for (int k = lane; k < K; k += 32) {
-            const float v = lw[r * K + k];
-            const float w = expf(v - lse);
-            wt[r * K + k] = w;
+            const double v = lw[r * K + k];
+            const double w = exp(v - lse);
+            wt[r * K + k] = (float)w;
             acc += w * v;
         }
         mine += warp_sum(acc);
@@ -139,9 +150,9 @@ __global__ void __launch_bounds__(256) dreg_stage2_kernel(const float* __restric
     if (lane == 0) s_part[wid] = mine;
     __syncthreads();
     if (threadIdx.x == 0) {
-        float tot = 0.f;
+        double tot = 0.0;
         for (int w = 0; w < 8; ++w) tot += s_part[w];
-        *loss = -tot / (float)M;
+        *loss = (float)(-tot / (double)M);
     }
 }
 
@@ -191,8 +202,8 @@ extern "C" int mmvae_objective_iwae(const float* lpz, const float* lq, const flo
 
 #define DREG_MAX_SPLIT MMVAE_DREG_MAX_SPLIT
 extern "C" int mmvae_objective_dreg_stage1(const float* lpz, const float* lq, const float* lpx, int M, int L, int K,
-                                           int64_t B, float* lw_part, float* lq_soft, void* stream) {
-    // lw_part: (DREG_MAX_SPLIT + 1, M*K) floats: [0] receives the local batch sums, [1..] is scratch
+                                           int64_t B, double* lw_part, float* lq_soft, void* stream) {
+    // lw_part: (DREG_MAX_SPLIT + 1, M*K) doubles: [0] receives the local batch sums, [1..] is scratch
     CombParams p{};
     int rc = comb_fill(p, lpz, lq, lpx, M, L, K, B);
     if (rc) return rc;
@@ -204,12 +215,12 @@ extern "C" int mmvae_objective_dreg_stage1(const float* lpz, const float* lq, co
     dim3 grid(M * K, nsplit);
     dreg_stage1_kernel<<<grid, 256, 0, st>>>(p, lw_part + (size_t)M * K, nsplit, lq_soft);
     MMVAE_LAUNCH_CHECK();
-    partial_sum_kernel<<<(M * K + 127) / 128, 128, 0, st>>>(lw_part + (size_t)M * K, nsplit, M * K, M * K, 0, lw_part);
+    dreg_partial_sum_kernel<<<(M * K + 127) / 128, 128, 0, st>>>(lw_part + (size_t)M * K, nsplit, M * K, lw_part);
     MMVAE_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int mmvae_objective_dreg_stage2(const float* lw, int M, int K, float* wt, float* loss, void* stream) {
+extern "C" int mmvae_objective_dreg_stage2(const double* lw, int M, int K, float* wt, float* loss, void* stream) {
     if (!lw || !wt || !loss || M <= 0 || K <= 0) return MMVAE_E_ARG;
     dreg_stage2_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(lw, M, K, wt, loss);
     MMVAE_LAUNCH_CHECK();

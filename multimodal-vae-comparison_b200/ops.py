@@ -505,7 +505,7 @@ class _Dreg(torch.autograd.Function):
         f = lambda t: t.detach().float().contiguous()
         lpz_c, lq_c, lpx_c = f(lpz), f(lq), f(lpx)
         dev = lpz.device
-        part = torch.empty(((_lib.DREG_MAX_SPLIT + 1), M * K), dtype=torch.float32, device=dev)
+        part = torch.empty(((_lib.DREG_MAX_SPLIT + 1), M * K), dtype=torch.float64, device=dev)
         lq_soft = torch.empty((M, M, K, B), dtype=torch.float32, device=dev)
         call("mmvae_objective_dreg_stage1", _ptr(lpz_c), _ptr(lq_c), _ptr(lpx_c), M, L, K, B, _ptr(part),
              _ptr(lq_soft), _stream())

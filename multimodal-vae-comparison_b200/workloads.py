@@ -1,0 +1,266 @@
+"""Functional objective steps on leaf tensors -- the measurement protocol of SURVEY.md 8d.
+
+"Objective fwd+bwd" = fusion / sampling / log-densities / KL (segment A), the decoder log-likelihood row reductions
+and the ELBO / IWAE / DReG combination (segment B), and the backward of both, with the dense decoders replaced by
+*leaf* reconstruction tensors so that no dense layer is timed.  Inputs: ``mu_m, s_m`` (B, Dtot), prior logits (1, D),
+``recon_{t<-s}`` (K*B, *data_dim) (all requiring grad), targets (B, *data_dim), pre-generated noise.  Outputs: the
+loss and the gradient w.r.t. every leaf.
+
+Everything here is product code (it only calls ops.py -> the C ABI); the same leaf tensors are fed to the oracle by
+tests/ and by bench.py's cpu_baseline leg.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from . import synthetic as syn
+from .mmvae_models import MOE, mopoe_inmodel_component, mopoe_subsets, poe_subsets
+from .ops import Draw
+
+
+def term_plan(model, M):
+    """(target modality, source tag) of every likelihood term, in evaluation order."""
+    if model == "moe":
+        plan = []
+        for r in range(M):
+            plan.append((r, "self"))
+            if MOE._cross_source(M, r) is not None:
+                plan.append((r, "cross"))
+        return plan
+    if model == "poe":
+        return [(m, "subset%d" % a) for a in range(2 ** M - 1) for m in range(M)]
+    if model == "mopoe":
+        return [(m, "joint") for m in range(M)]
+    if model == "dmvae":
+        plan = []
+        for m in range(M):
+            plan += [(m, "shared"), (m, "joint")] + [(m, "cross%d" % j) for j in range(M) if j != m]
+        return plan
+    raise ValueError(model)
+
+
+def _noise_plan(model, M, K, B, D, pv, dists):
+    """Shapes of the noise tensors in the reference's rsample order."""
+    if model == "poe":
+        return [("normal", (1, B, D)) for _ in range(2 ** M - 1)]
+    if model == "moe":
+        return [(dists[m], (K, B, D)) for m in range(M)]
+    if model == "mopoe":
+        return [("normal", (1, B, D)) for _ in range(M)]
+    plan = [("normal", (1, B, D))]
+    for m in range(M):
+        plan += [("normal", (1, B, D)), ("normal", (1, B, pv))] + [("normal", (1, B, D))] * (M - 1)
+    return plan
+
+
+def make_leaves(name, B=None, seed=1234, recon_dtype=torch.float32):
+    """Synthetic leaf tensors of workload `name` (synthetic.WORKLOADS), generated on the host with a fixed seed.
+    Returns (cfg, dict of CPU tensors): mu, s (M,B,Dtot), pz_logits (1,D), targets [..], recon [..], noise [..]."""
+    cfg = dict(syn.WORKLOADS[name])
+    B = B or cfg["B"]
+    cfg["B"] = B
+    g = syn.gen(seed)
+    M, K, D, pv = len(cfg["mods"]), cfg["K"], cfg["D"], cfg.get("private") or 0
+    post = [syn.make_posterior(g, B, D + pv) for _ in range(M)]
+    t = {"mu": torch.stack([p[0] for p in post]), "s": torch.stack([p[1] for p in post]),
+         "pz_logits": torch.zeros(1, D)}
+    t["targets"] = [syn.make_target(g, m["target"], B, m["data_dim"]) for m in cfg["mods"]]
+    Kr = K if cfg["model"] == "moe" else 1
+    t["recon"] = [syn.make_recon(g, cfg["mods"][tm]["ltype"], Kr * B, cfg["mods"][tm]["data_dim"]).to(recon_dtype)
+                  for tm, _ in term_plan(cfg["model"], M)]
+    t["noise"] = [syn.make_noise(g, kind, shape)
+                  for kind, shape in _noise_plan(cfg["model"], M, K, B, D, pv, [m["dist"] for m in cfg["mods"]])]
+    return cfg, t
+
+
+def algorithmic_bytes(cfg, recon_dtype=torch.float32):
+    """Minimum HBM traffic of one objective fwd+bwd per SAMPLE: per likelihood term 2R+T when the
+    row weights are known a priori (ELBO), 3R+2T otherwise (IWAE / DReG); latent segment 4*K*D*4 per drawn tensor
+    plus the (M, Dtot) parameters read and their gradients written."""
+    e = 2 if recon_dtype == torch.bfloat16 else 4
+    M, K, D, pv = len(cfg["mods"]), cfg["K"], cfg["D"], cfg.get("private") or 0
+    Kr = K if cfg["model"] == "moe" else 1
+    tot = 0
+    for tm, _ in term_plan(cfg["model"], M):
+        P = int(math.prod(cfg["mods"][tm]["data_dim"]))
+        R, T = Kr * P * e, P * 4
+        tot += (2 * R + T) if cfg["obj"] == "elbo" else (3 * R + 2 * T)
+    n_noise = sum(int(math.prod(shape[2:])) * shape[0] for _, shape in
+                  _noise_plan(cfg["model"], M, K, 1, D, pv, [m["dist"] for m in cfg["mods"]]))
+    tot += 4 * n_noise * 4 + 2 * 2 * M * (D + pv) * 4
+    return tot
+
+
+class LeafStep:
+    """One objective fwd+bwd on device-resident leaves through the CUDA path.  ``run()`` returns the loss tensor;
+    gradients land in ``.grad`` of ``self.mu / self.s / self.pz_logits / self.recon[i]``."""
+
+    def __init__(self, cfg, tensors, device="cuda", beta=1.0, group=None, global_batch=None):
+        self.cfg, self.beta, self.group = cfg, beta, group
+        self.model, self.obj = cfg["model"], cfg["obj"]
+        self.M, self.K, self.D, self.pv, self.B = len(cfg["mods"]), cfg["K"], cfg["D"], cfg.get("private") or 0, cfg["B"]
+        self.Bt = global_batch or self.B
+        dev = torch.device(device)
+        self.mu = tensors["mu"].to(dev).requires_grad_(True)
+        self.s = tensors["s"].to(dev).requires_grad_(True)
+        self.pz_logits = tensors["pz_logits"].to(dev).requires_grad_(True)
+        self.targets = [x.to(dev) for x in tensors["targets"]]
+        self.recon = [x.to(dev).requires_grad_(True) for x in tensors["recon"]]
+        self.noise = [x.to(dev) for x in tensors["noise"]]
+        self.plan = term_plan(self.model, self.M)
+        self.codes = [1 if m["dist"] == "laplace" else 0 for m in cfg["mods"]]
+        if self.model == "mopoe":
+            subs = mopoe_subsets(range(self.M))
+            comp = mopoe_inmodel_component(len(subs))
+            bits = sum(1 << i for i in subs[comp]) | ((1 << 31) if len(subs[comp]) == self.M else 0)
+            bits = bits - (1 << 32) if bits >= (1 << 31) else bits
+            self.row_masks = torch.full((self.B,), bits, dtype=torch.int32, device=dev)
+        if self.model != "moe":
+            self.eps_packed = torch.cat([n.reshape(-1) for n in self.noise])
+
+    def leaves(self):
+        return [self.mu, self.s, self.pz_logits] + self.recon
+
+    def zero_grad(self):
+        for t in self.leaves():
+            t.grad = None
+
+    # -- likelihood helpers ---------------------------------------------------------------------------------
+    def _family(self, tm, tag):
+        # MOE wraps its self reconstruction in a Normal whatever the family (reference mmvae_models.py:105-107)
+        return "normal" if (self.model == "moe" and tag == "self") else self.cfg["mods"][tm]["dist"]
+
+    def _rows(self, i):
+        tm, tag = self.plan[i]
+        m = self.cfg["mods"][tm]
+        fam = self._family(tm, tag)
+        if m["ltype"] == "category_ce":
+            return ops.catce_rows(self.recon[i], self.targets[tm], m["lam"])
+        if m["ltype"] == "optimal_sigma":
+            return ops.osigma_rows(self.recon[i], self.targets[tm], m["lam"], self.group)
+        return ops.loglik_rows(self.recon[i], self.targets[tm], m["ltype"], fam, m["lam"])
+
+    def _wsum(self, i, w_const=1.0, w_rows=None):
+        tm, tag = self.plan[i]
+        m = self.cfg["mods"][tm]
+        fam = self._family(tm, tag)
+        if m["ltype"] == "category_ce":
+            return ops.catce_weighted_sum(self.recon[i], self.targets[tm], m["lam"], w_rows=w_rows, w_const=w_const)
+        if m["ltype"] == "optimal_sigma":
+            rows = ops.osigma_rows(self.recon[i], self.targets[tm], m["lam"], self.group)
+            return (torch.dot(rows, w_rows) if w_rows is not None else w_const * rows.sum()), rows.detach()
+        return ops.loglik_weighted_sum(self.recon[i], self.targets[tm], m["ltype"], fam, m["lam"], w_rows=w_rows,
+                                       w_const=w_const)
+
+    def _prior(self):
+        return torch.zeros_like(self.pz_logits), F.softmax(self.pz_logits, dim=1) * self.D
+
+    # -- objectives -----------------------------------------------------------------------------------------
+    def loss(self):
+        return getattr(self, "_" + self.model)()
+
+    def run(self):
+        self.zero_grad()
+        loss = self.loss()
+        loss.backward()
+        return loss
+
+    def _moe(self):
+        M, K, B = self.M, self.K, self.B
+        mu0, s0 = self._prior()
+        eps = torch.stack(self.noise)
+        if self.obj == "elbo":
+            z, lq, _ = ops.moe_logdens(self.mu, self.s, mu0.detach(), s0.detach(), eps, self.codes, False)
+            kls = ops.latent_draws(self.mu, self.s, None, None, None,
+                                   [Draw(mods=(m,), direct=True, laplace=bool(self.codes[m]), kl_mode=2, width=self.D)
+                                    for m in range(M)])
+            total, n_keep, i = 0.0, 0.0, 0
+            for r in range(M):
+                S, _ = self._wsum(i, w_const=-1.0 / M)
+                i += 1
+                total, n_keep = total + S, n_keep + (S != 0).float()
+                src = MOE._cross_source(M, r)
+                if src is None:
+                    continue
+                lwt = lq[src, r, 0] - lq[src, src, 0].detach()
+                S, _ = self._wsum(i, w_rows=-lwt.exp() / M)
+                i += 1
+                total, n_keep = total + S, n_keep + (S != 0).float()
+            kld = torch.stack([k["kl"] for k in kls])
+            return total + (self.beta / M) * n_keep * kld.sum()
+        z, lq, lpz = ops.moe_logdens(self.mu, self.s, mu0, s0, eps, self.codes, True)
+        rows = [self._rows(i) for i in range(len(self.plan))]
+        L = len(rows) // M
+        lpx = torch.stack(rows).view(M, L, K, B)
+        if self.obj == "iwae":
+            return ops.iwae_combine(lpz, lq, lpx, self.beta)[0]
+        return ops.dreg_combine(lpz, lq, lpx, self.group)[0]
+
+    def _poe(self):
+        M, D = self.M, self.D
+        mu0, s0 = self._prior()
+        subsets = poe_subsets(range(M))
+        res = ops.latent_draws(self.mu, self.s, mu0, s0, self.eps_packed,
+                               [Draw(mods=sub, prior=True, kl_mode=1, width=D, K=1) for sub in subsets])
+        total = 0.0
+        for i in range(len(self.plan)):
+            total = total + self._wsum(i, w_const=-1.0)[0]
+        return total + self.beta * torch.stack([r["kl"] for r in res]).sum()
+
+    def _mopoe(self):
+        M, D = self.M, self.D
+        mu0, s0 = self._prior()
+        draws = [Draw(rowmask=True, kl_mode=1 if i == 0 else 0, width=D, K=1) for i in range(M)]
+        draws += [Draw(mods=(i,), direct=True, kl_mode=1, width=D) for i in range(M)]
+        res = ops.latent_draws(self.mu, self.s, mu0, s0, self.eps_packed, draws, self.row_masks)
+        total = 0.0
+        for i in range(len(self.plan)):
+            total = total + self._wsum(i, w_const=-1.0 / self.Bt)[0]
+        kl_all = torch.stack([res[0]["kl"]] + [res[M + i]["kl"] for i in range(M)])
+        return total + self.beta * kl_all.sum() / ((M + 1) * self.Bt)
+
+    def _dmvae(self):
+        M, D, pv = self.M, self.D, self.pv
+        mu0, s0 = self._prior()
+        draws = [Draw(mods=tuple(range(M)), kl_mode=1, width=D, K=1)]
+        idx = []
+        for i in range(M):
+            idx.append(len(draws))
+            draws.append(Draw(mods=(i,), direct=True, kl_mode=1, col0=0, width=D, K=1))
+            draws.append(Draw(mods=(i,), direct=True, kl_mode=2, col0=D, width=pv, K=1))
+            draws += [Draw(mods=(j,), direct=True, col0=0, width=D, K=1) for j in range(M) if j != i]
+        res = ops.latent_draws(self.mu, self.s, mu0, s0, self.eps_packed, draws)
+        total = 0.0
+        for i in range(len(self.plan)):
+            total = total + self._wsum(i, w_const=-1.0)[0]
+        for i in range(M):
+            total = total + self.beta * (res[idx[i]]["kl"].sum() + res[0]["kl"].sum()
+                                         + (M - 1) * res[idx[i] + 1]["kl"].sum())
+        return total
+
+
+class GraphedStep:
+    """CUDA-graph capture of a LeafStep (fwd+bwd): the launch-bound chain of ~30 small kernels replays as one graph
+    launch.  Gradients are written into static buffers (``step.grads``)."""
+
+    def __init__(self, step: LeafStep, warmup=3):
+        self.step = step
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                step.run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        step.zero_grad()
+        with torch.cuda.graph(self.graph):
+            self.loss = step.loss()
+            self.loss.backward()
+        self.grads = [t.grad for t in step.leaves()]
+
+    def run(self):
+        self.graph.replay()
+        return self.loss
