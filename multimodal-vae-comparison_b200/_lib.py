@@ -58,8 +58,8 @@ _lib = None
 launch_count = 0
 _LAUNCHES = {"mmvae_loglik_rowreduce_fwd": 1, "mmvae_loglik_rowreduce_bwd": 1, "mmvae_loglik_rowreduce_fused": 1,
              "mmvae_catce_rows": 1, "mmvae_osigma_sumsq": 1, "mmvae_osigma_fwd": 1, "mmvae_osigma_bwd": 2,
-             "mmvae_latent_draws_fwd": 1, "mmvae_latent_draws_bwd": 3, "mmvae_moe_logdens_fwd": 1,
-             "mmvae_moe_logdens_bwd": 3, "mmvae_objective_iwae": 1, "mmvae_objective_dreg_stage1": 2,
+             "mmvae_latent_draws_fwd": 1, "mmvae_latent_draws_bwd": 2, "mmvae_moe_logdens_fwd": 1,
+             "mmvae_moe_logdens_bwd": 2, "mmvae_objective_iwae": 1, "mmvae_objective_dreg_stage1": 2,
              "mmvae_objective_dreg_stage2": 1, "mmvae_reduce_sum": 1, "mmvae_scale_inplace": 1}
 
 

@@ -1,7 +1,14 @@
 // category_ce rows: cross entropy with probability targets whose class axis is dim 1 (reference
 // objectives.py:485-500; for (rows, T, 27) text the softmax runs over the SEQUENCE axis -- reproduced as is).
-// One CTA per reconstruction row: the (C, d) slab of x and t is staged in shared memory with coalesced loads,
-// each thread then owns a column j and walks the class axis; the row value is a warp-shuffle + smem block sum.
+//
+// Rows are tiny (C*d = 9 ... 6642 elements), so the kernel is organised around staging, not arithmetic:
+//   * a CTA owns R consecutive rows; their (C, d) slabs of x and t are ONE contiguous run in HBM, brought into
+//     shared memory by a single TMA bulk copy each (cp.async.bulk + mbarrier) whenever the run is 16-byte aligned
+//     (R is chosen so that R*C*d*elemsize is a multiple of 16); otherwise by coalesced element loads;
+//   * W warps per row split the class axis (W = 1 for short class axes: then there is no block barrier on the compute
+//     path at all); lanes own columns j, so the smem walk along the class axis is conflict free;
+//   * two passes over the class axis (max, then exp-sum / target sums: one MUFU.EX2 per element), warp-shuffle row
+//     sum; the gradient is written in place over the staged x and leaves through one TMA bulk store.
 #include "common.cuh"
 
 namespace mmvae {
@@ -13,72 +20,184 @@ struct CatceParams {
     const float* w_rows;
     float* out_rows;
     int64_t ldx, ldt, ldg, rows, B;
-    int C, d;
+    int C, d, R, W, tma;
     float lam, w_const;
 };
 
-template <typename TX, typename TT, int MODE>  // 0 fwd, 1 bwd, 2 fused
-__global__ void __launch_bounds__(128) catce_kernel(const CatceParams p) {
-    extern __shared__ float sm[];
-    const int n = p.C * p.d;
-    float* sx = sm;           // n
-    float* st = sm + n;       // n
-    float* s_lse = st + n;    // d
-    float* s_tsum = s_lse + p.d;  // d
-    __shared__ float red[32];
+__host__ __device__ __forceinline__ size_t up16(size_t v) { return (v + 15) & ~(size_t)15; }
 
-    const int64_t row = blockIdx.x;
-    const TX* __restrict__ x = reinterpret_cast<const TX*>(p.x) + row * p.ldx;
-    const TT* __restrict__ t = reinterpret_cast<const TT*>(p.t) + (row % p.B) * p.ldt;
-    for (int e = threadIdx.x; e < n; e += blockDim.x) {
-        sx[e] = Elem<TX>::load1(x + e);
-        st[e] = Elem<TT>::load1(t + e);
-    }
-    __syncthreads();
-    float acc = 0.f;
-    for (int j = threadIdx.x; j < p.d; j += blockDim.x) {
-        float m = -INFINITY;
-        for (int c = 0; c < p.C; ++c) m = fmaxf(m, sx[c * p.d + j]);
-        float se = 0.f, ts = 0.f, txs = 0.f;
-        for (int c = 0; c < p.C; ++c) {
-            const float xv = sx[c * p.d + j], tv = st[c * p.d + j];
-            se += expf(xv - m);
-            ts += tv;
-            txs += tv * xv;
+template <typename TX, typename TT, int MODE>  // 0 fwd, 1 bwd, 2 fused
+__global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const int n = p.C * p.d, R = p.R, W = p.W;
+    TX* sx = reinterpret_cast<TX*>(smraw);
+    size_t off = up16((size_t)R * n * sizeof(TX));
+    TT* st = reinterpret_cast<TT*>(smraw + off);
+    off += up16((size_t)R * n * sizeof(TT));
+    float* s_lse = reinterpret_cast<float*>(smraw + off);  // R*d
+    float* s_ts = s_lse + R * p.d;                          // R*d
+    float* part = s_ts + R * p.d;                           // R*W*d*4 (only touched when W > 1)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smraw + up16(off + (size_t)(2 * R * p.d + 4 * R * W * p.d) * 4));
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rl = warp / W, w = warp - rl * W;  // local row, class slice
+    const int64_t row0 = (int64_t)blockIdx.x * R;
+    const int nrows = (int)min((int64_t)R, p.rows - row0);
+    const TX* __restrict__ xg = reinterpret_cast<const TX*>(p.x);
+    const TT* __restrict__ tg = reinterpret_cast<const TT*>(p.t);
+
+    // ---- stage R rows of x and t ----------------------------------------------------------------------------
+    if (p.tma) {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bx = (uint32_t)((size_t)R * n * sizeof(TX)), bt = (uint32_t)((size_t)R * n * sizeof(TT));
+            mbar_expect_tx(bar, bx + bt);
+            bulk_g2s(sx, xg + row0 * p.ldx, bx, bar);
+            bulk_g2s(st, tg + (row0 % p.B) * p.ldt, bt, bar);
         }
-        const float lse = m + logf(se);
-        s_lse[j] = lse;
-        s_tsum[j] = ts;
-        acc += txs - lse * ts;
-    }
-    if (MODE != 1) {
-        const float tot = block_sum(acc, red);  // contains a __syncthreads -> s_lse / s_tsum visible below
-        if (threadIdx.x == 0) p.out_rows[row] = p.lam * tot;
+        mbar_wait(bar, 0);
     } else {
+        for (int r = 0; r < nrows; ++r) {
+            const TX* xr = xg + (row0 + r) * p.ldx;
+            const TT* tr = tg + ((row0 + r) % p.B) * p.ldt;
+#pragma unroll 8
+            for (int e = threadIdx.x; e < n; e += blockDim.x) {
+                sx[r * n + e] = xr[e];
+                st[r * n + e] = tr[e];
+            }
+        }
         __syncthreads();
     }
+    const bool live = rl < nrows;
+    const TX* rx = sx + (size_t)rl * n;
+    const TT* rt = st + (size_t)rl * n;
+    float acc = 0.f;
+
+    if (W == 1) {  // one warp owns the whole row: no block barrier on the compute path
+        if (live) {
+            for (int j = lane; j < p.d; j += 32) {
+                float m = -INFINITY;
+                for (int c = 0; c < p.C; ++c) m = fmaxf(m, Elem<TX>::load1(rx + c * p.d + j));
+                float se = 0.f, ts = 0.f, txs = 0.f;
+                for (int c = 0; c < p.C; ++c) {
+                    const float xv = Elem<TX>::load1(rx + c * p.d + j), tv = Elem<TT>::load1(rt + c * p.d + j);
+                    se += __expf(xv - m);
+                    ts += tv;
+                    txs = fmaf(tv, xv, txs);
+                }
+                const float lse = m + logf(se);
+                s_lse[rl * p.d + j] = lse;
+                s_ts[rl * p.d + j] = ts;
+                acc += txs - lse * ts;
+            }
+            __syncwarp();
+        }
+    } else {  // W warps split the class axis of a row; merged through shared memory
+        if (live)
+            for (int j = lane; j < p.d; j += 32) {
+                float m = -INFINITY;
+                for (int c = w; c < p.C; c += W) m = fmaxf(m, Elem<TX>::load1(rx + c * p.d + j));
+                part[((size_t)(rl * W + w) * p.d + j) * 4] = m;
+            }
+        __syncthreads();
+        if (live)
+            for (int j = lane; j < p.d; j += 32) {
+                float m = -INFINITY;
+                for (int ww = 0; ww < W; ++ww) m = fmaxf(m, part[((size_t)(rl * W + ww) * p.d + j) * 4]);
+                float se = 0.f, ts = 0.f, txs = 0.f;
+                for (int c = w; c < p.C; c += W) {
+                    const float xv = Elem<TX>::load1(rx + c * p.d + j), tv = Elem<TT>::load1(rt + c * p.d + j);
+                    se += __expf(xv - m);
+                    ts += tv;
+                    txs = fmaf(tv, xv, txs);
+                }
+                float* q = part + ((size_t)(rl * W + w) * p.d + j) * 4;
+                q[1] = se;
+                q[2] = ts;
+                q[3] = txs;
+            }
+        __syncthreads();
+        if (live && w == 0)
+            for (int j = lane; j < p.d; j += 32) {
+                float mm = -INFINITY;  // every slice summed exp(x - mm) against the same global max
+                for (int ww = 0; ww < W; ++ww) mm = fmaxf(mm, part[((size_t)(rl * W + ww) * p.d + j) * 4]);
+                float se = 0.f, ts = 0.f, txs = 0.f;
+                for (int ww = 0; ww < W; ++ww) {
+                    const float* q = part + ((size_t)(rl * W + ww) * p.d + j) * 4;
+                    se += q[1];
+                    ts += q[2];
+                    txs += q[3];
+                }
+                const float lse = mm + logf(se);
+                s_lse[rl * p.d + j] = lse;
+                s_ts[rl * p.d + j] = ts;
+                acc += txs - lse * ts;
+            }
+        __syncthreads();
+    }
+    if (MODE != 1 && live && w == 0) {
+        acc = warp_sum(acc);
+        if (lane == 0) p.out_rows[row0 + rl] = p.lam * acc;
+    }
     if (MODE != 0) {
-        TX* __restrict__ g = reinterpret_cast<TX*>(p.g) + row * p.ldg;
-        const float wl = (p.w_rows ? __ldg(p.w_rows + row) : p.w_const) * p.lam;
-        for (int e = threadIdx.x; e < n; e += blockDim.x) {
-            const int j = e % p.d;
-            const float sftm = expf(sx[e] - s_lse[j]);
-            Elem<TX>::store1(g + e, wl * (st[e] - sftm * s_tsum[j]));
+        TX* gr = reinterpret_cast<TX*>(p.g) + (row0 + rl) * p.ldg;
+        TX* gs = sx + (size_t)rl * n;  // in-place staging of the gradient when it leaves through TMA
+        if (live) {
+            const float wl = (p.w_rows ? __ldg(p.w_rows + row0 + rl) : p.w_const) * p.lam;
+            for (int j = lane; j < p.d; j += 32) {
+                const float lse = s_lse[rl * p.d + j], ts = s_ts[rl * p.d + j];
+                for (int c = w; c < p.C; c += W) {
+                    const int e = c * p.d + j;
+                    const float gv = wl * (Elem<TT>::load1(rt + e) - __expf(Elem<TX>::load1(rx + e) - lse) * ts);
+                    if (p.tma)
+                        Elem<TX>::store1(gs + e, gv);
+                    else
+                        Elem<TX>::store1(gr + e, gv);
+                }
+            }
+        }
+        if (p.tma) {
+            fence_async_smem();  // generic-proxy smem writes -> visible to the async (TMA) proxy
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                bulk_s2g(reinterpret_cast<TX*>(p.g) + row0 * p.ldg, sx, (uint32_t)((size_t)R * n * sizeof(TX)));
+                bulk_wait_read();  // smem must stay alive until the bulk store has read it
+            }
         }
     }
 }
 
+static size_t catce_smem(int R, int W, int n, int d, int sx, int st) {
+    size_t off = up16((size_t)R * n * sx) + up16((size_t)R * n * st);
+    off = up16(off + (size_t)(2 * R * d + 4 * R * W * d) * 4);
+    return off + 16;
+}
+
 template <typename TX, typename TT>
-static int launch_catce(int mode, const CatceParams& p, cudaStream_t st) {
-    const size_t smem = (size_t)(2 * p.C * p.d + 2 * p.d) * sizeof(float);
-    if (smem > 200 * 1024) return MMVAE_E_LIMIT;
-    if (p.rows > 0x7fffffffLL) return MMVAE_E_LIMIT;
+static int launch_catce(int mode, CatceParams p, cudaStream_t st) {
+    const int n = p.C * p.d, sx = (int)sizeof(TX), stt = (int)sizeof(TT);
+    // warps per row: split long class axes; rows per CTA: fill ~8 warps, prefer a TMA-able (16 B multiple) run
+    int W = p.C >= 192 ? 4 : (p.C >= 96 ? 2 : 1);
+    int R = 8 / W;
+    const size_t budget = 100 * 1024;  // keep >= 2 CTAs per SM
+    while (R > 1 && catce_smem(R, W, n, p.d, sx, stt) > budget) R >>= 1;
+    if (catce_smem(R, W, n, p.d, sx, stt) > 200 * 1024) return MMVAE_E_LIMIT;
+    bool dense = p.ldx == n && p.ldt == n && (mode == 0 || p.ldg == n);
+    bool tma = dense && aligned16(p.x) && aligned16(p.t) && (mode == 0 || aligned16(p.g)) && p.rows % R == 0 &&
+               p.B % R == 0 && ((size_t)R * n * sx) % 16 == 0 && ((size_t)R * n * stt) % 16 == 0;
+    p.R = R;
+    p.W = W;
+    p.tma = tma ? 1 : 0;
+    const size_t smem = catce_smem(R, W, n, p.d, sx, stt);
+    const int64_t grid = (p.rows + R - 1) / R;
+    if (grid > 0x7fffffffLL) return MMVAE_E_LIMIT;
     auto k = mode == 0 ? catce_kernel<TX, TT, 0> : (mode == 1 ? catce_kernel<TX, TT, 1> : catce_kernel<TX, TT, 2>);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    k<<<(unsigned)p.rows, 128, smem, st>>>(p);
+    k<<<(unsigned)grid, R * W * 32, smem, st>>>(p);
     MMVAE_LAUNCH_CHECK();
     return 0;
 }

@@ -8,7 +8,6 @@
 
 namespace mmvae {
 
-constexpr int kIwaeWarps = 8;
 
 struct CombParams {
     const float *lpz, *lq, *lpx;
@@ -42,46 +41,51 @@ __device__ __forceinline__ float lw_value(const CombParams& p, int r, int k, int
     return v - beta * lme_j(p, r, k, b, vals, mx, se);
 }
 
-// CTA: 32 consecutive batch rows (lanes) x 8 warps that split the M*K (r,k) pairs.
-__global__ void __launch_bounds__(kIwaeWarps * 32) iwae_kernel(const CombParams p) {
-    __shared__ float s_m[kIwaeWarps][32], s_s[kIwaeWarps][32];
+// CTA: 32 consecutive batch rows (lanes, coalesced along b) x up to 32 warps that split the M*K (r,k) pairs.  The
+// log-weights are parked in shared memory between the logsumexp pass and the weight pass; the (r,k) logsumexp is
+// an online-softmax merge across warps.
+__global__ void __launch_bounds__(1024) iwae_kernel(const CombParams p) {
+    extern __shared__ float sm[];
+    const int n = p.M * p.K;
+    const int nw = blockDim.x >> 5;
+    float* s_lw = sm;               // n x 32
+    float* s_m = s_lw + n * 32;     // nw x 32
+    float* s_s = s_m + nw * 32;     // nw x 32
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t b = (int64_t)blockIdx.x * 32 + lane;
     const bool ok = b < p.B;
-    const int n = p.M * p.K;
     float vals[MMVAE_MAX_MODS];
     float run_m = -INFINITY, run_s = 0.f;
     if (ok) {
-        for (int q = wid; q < n; q += kIwaeWarps) {
+        for (int q = wid; q < n; q += nw) {
             const int r = q / p.K, k = q - r * p.K;
             float mx, se;
             const float lw = lw_value(p, r, k, b, p.beta, vals, mx, se);
             p.lw[((int64_t)r * p.K + k) * p.B + b] = lw;
+            s_lw[q * 32 + lane] = lw;
             const float nm = fmaxf(run_m, lw);
-            run_s = run_s * expf(run_m - nm) + expf(lw - nm);
+            run_s = run_s * __expf(run_m - nm) + __expf(lw - nm);
             run_m = nm;
         }
     }
-    s_m[wid][lane] = run_m;
-    s_s[wid][lane] = run_s;
+    s_m[wid * 32 + lane] = run_m;
+    s_s[wid * 32 + lane] = run_s;
     __syncthreads();
     float tm = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < kIwaeWarps; ++w) tm = fmaxf(tm, s_m[w][lane]);
+    for (int w = 0; w < nw; ++w) tm = fmaxf(tm, s_m[w * 32 + lane]);
     float ts = 0.f;
-#pragma unroll
-    for (int w = 0; w < kIwaeWarps; ++w)
-        if (s_s[w][lane] > 0.f) ts += s_s[w][lane] * expf(s_m[w][lane] - tm);
+    for (int w = 0; w < nw; ++w)
+        if (s_s[w * 32 + lane] > 0.f) ts += s_s[w * 32 + lane] * __expf(s_m[w * 32 + lane] - tm);
     const float lse = tm + logf(ts);
     if (!ok) return;
     if (wid == 0) p.loss_b[b] = -(lse - logf((float)n));
-    for (int q = wid; q < n; q += kIwaeWarps) {
+    for (int q = wid; q < n; q += nw) {
         const int r = q / p.K, k = q - r * p.K;
-        float mx, se;
-        const float lw = lw_value(p, r, k, b, p.beta, vals, mx, se);
-        const float wv = expf(lw - lse);
+        const float wv = expf(s_lw[q * 32 + lane] - lse);
         p.w[((int64_t)r * p.K + k) * p.B + b] = wv;
         if (p.dlq) {
+            float mx, se;
+            lme_j(p, r, k, b, vals, mx, se);
             const float c = p.beta * wv / se;
 #pragma unroll
             for (int j = 0; j < MMVAE_MAX_MODS; ++j)
@@ -195,7 +199,15 @@ extern "C" int mmvae_objective_iwae(const float* lpz, const float* lq, const flo
     if (rc) return rc;
     if (!lw || !loss_b || !w) return MMVAE_E_ARG;
     p.beta = beta; p.lw = lw; p.loss_b = loss_b; p.w = w; p.dlq = dlq;
-    iwae_kernel<<<(unsigned)((B + 31) / 32), kIwaeWarps * 32, 0, (cudaStream_t)stream>>>(p);
+    const int n = M * K;
+    int nw = n < 32 ? n : 32;
+    const size_t smem = (size_t)(n * 32 + 2 * nw * 32) * sizeof(float);
+    if (smem > 200 * 1024) return MMVAE_E_LIMIT;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(iwae_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    iwae_kernel<<<(unsigned)((B + 31) / 32), nw * 32, smem, (cudaStream_t)stream>>>(p);
     MMVAE_LAUNCH_CHECK();
     return 0;
 }

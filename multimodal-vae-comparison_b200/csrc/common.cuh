@@ -104,16 +104,59 @@ struct Elem<__nv_bfloat16> {
     __device__ static __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
 
-// out[0..n) = sum over `parts` partial vectors (ws laid out parts x stride, vector at `offset`), fixed order:
-// second stage of the deterministic batch reductions (learnable-prior gradients).
-static __global__ void partial_sum_kernel(const float* __restrict__ ws, int parts, int n, int stride, int offset,
-                                          float* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float tot = 0.f;
-    for (int q = 0; q < parts; ++q) tot += ws[(size_t)q * stride + offset + i];
-    out[i] = tot;
+// Second stage of the deterministic batch reductions (learnable-prior gradients): ws holds `parts` partial vectors
+// of length n_total (row-major); output element i = sum_q ws[q][i].  One CTA per output element, strided loads,
+// fixed-shape block reduction -> bit-reproducible; out0 receives elements [0, n0), out1 the rest.
+static __global__ void __launch_bounds__(128) partial_sum_kernel(const float* __restrict__ ws, int parts, int n_total,
+                                                                 int n0, float* __restrict__ out0,
+                                                                 float* __restrict__ out1) {
+    __shared__ float red[32];
+    const int i = blockIdx.x;
+    float acc = 0.f;
+    for (int q = threadIdx.x; q < parts; q += blockDim.x) acc += ws[(size_t)q * n_total + i];
+    const float tot = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+        if (i < n0) out0[i] = tot;
+        else out1[i - n0] = tot;
+    }
 }
+
+// ---- TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier ---------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __host__ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

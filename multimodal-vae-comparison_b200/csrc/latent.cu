@@ -302,9 +302,7 @@ extern "C" int mmvae_latent_draws_bwd(const float* mu, const float* s, int M, in
     draws_bwd_kernel<<<grid, kWarps * 32, smem, st>>>(p);
     MMVAE_LAUNCH_CHECK();
     if (dmu0 && ds0) {
-        partial_sum_kernel<<<(Dtot + 127) / 128, 128, 0, st>>>(dprior_ws, (int)grid, Dtot, 2 * Dtot, 0, dmu0);
-        MMVAE_LAUNCH_CHECK();
-        partial_sum_kernel<<<(Dtot + 127) / 128, 128, 0, st>>>(dprior_ws, (int)grid, Dtot, 2 * Dtot, Dtot, ds0);
+        partial_sum_kernel<<<2 * Dtot, 128, 0, st>>>(dprior_ws, (int)grid, 2 * Dtot, Dtot, dmu0, ds0);
         MMVAE_LAUNCH_CHECK();
     }
     return 0;

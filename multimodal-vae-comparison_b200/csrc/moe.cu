@@ -16,7 +16,7 @@
 
 namespace mmvae {
 
-constexpr int kMoeWarps = 4;
+constexpr int kMoeMaxWarps = 16;  // warps per CTA = min(K, 16): the K samples of a row are split over the warps
 constexpr float kLogSqrt2Pi = 0.91893853320467274178f;
 
 struct MoeParams {
@@ -50,7 +50,8 @@ __device__ __forceinline__ void stage_row(const MoeParams& p, int64_t b, float* 
     }
 }
 
-__global__ void __launch_bounds__(kMoeWarps * 32) moe_fwd_kernel(const MoeParams p) {
+__global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_fwd_kernel(const MoeParams p) {
+    const int kMoeWarps = blockDim.x >> 5;
     extern __shared__ float sm[];
     const int MD = p.M * p.D;
     float* smu = sm;
@@ -106,7 +107,8 @@ __global__ void __launch_bounds__(kMoeWarps * 32) moe_fwd_kernel(const MoeParams
     }
 }
 
-__global__ void __launch_bounds__(kMoeWarps * 32) moe_bwd_kernel(const MoeParams p) {
+__global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_bwd_kernel(const MoeParams p) {
+    const int kMoeWarps = blockDim.x >> 5;
     extern __shared__ float sm[];
     const int MD = p.M * p.D;
     float* smu = sm;
@@ -204,6 +206,7 @@ static unsigned moe_grid(int64_t B) {
     const int64_t cap = (int64_t)kNumSMs * 8;
     return (unsigned)(B < cap ? B : cap);
 }
+static int moe_warps(int K) { return K < kMoeMaxWarps ? (K < 1 ? 1 : K) : kMoeMaxWarps; }
 
 static int moe_fill(MoeParams& p, const float* mu, const float* s, int M, int64_t B, int D, int K,
                     const int32_t* dists, const float* mu0, const float* s0, const float* eps) {
@@ -230,7 +233,7 @@ extern "C" int mmvae_moe_logdens_fwd(const float* mu, const float* s, int M, int
     if (!z || !lq || !lpz) return MMVAE_E_ARG;
     p.z = z; p.lq = lq; p.lpz = lpz;
     const size_t smem = (size_t)(4 * M * D + 3 * D) * sizeof(float);
-    moe_fwd_kernel<<<moe_grid(B), kMoeWarps * 32, smem, (cudaStream_t)stream>>>(p);
+    moe_fwd_kernel<<<moe_grid(B), moe_warps(K) * 32, smem, (cudaStream_t)stream>>>(p);
     MMVAE_LAUNCH_CHECK();
     return 0;
 }
@@ -249,7 +252,8 @@ extern "C" int mmvae_moe_logdens_bwd(const float* mu, const float* s, int M, int
     if (rc) return rc;
     if (!dmu || !ds || !dprior_ws) return MMVAE_E_ARG;
     p.dz_ext = dz_ext; p.dlq = dlq; p.dlpz = dlpz; p.through_z = through_z; p.dmu = dmu; p.ds = ds; p.ws = dprior_ws;
-    const size_t smem = (size_t)(4 * M * D + 2 * D + kMoeWarps * (2 * M * D + 2 * D)) * sizeof(float);
+    const int nw = moe_warps(K);
+    const size_t smem = (size_t)(4 * M * D + 2 * D + nw * (2 * M * D + 2 * D)) * sizeof(float);
     if (smem > 200 * 1024) return MMVAE_E_LIMIT;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(moe_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -257,12 +261,10 @@ extern "C" int mmvae_moe_logdens_bwd(const float* mu, const float* s, int M, int
     }
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = moe_grid(B);
-    moe_bwd_kernel<<<grid, kMoeWarps * 32, smem, st>>>(p);
+    moe_bwd_kernel<<<grid, nw * 32, smem, st>>>(p);
     MMVAE_LAUNCH_CHECK();
     if (dmu0 && ds0) {
-        partial_sum_kernel<<<(D + 127) / 128, 128, 0, st>>>(dprior_ws, (int)grid, D, 2 * D, 0, dmu0);
-        MMVAE_LAUNCH_CHECK();
-        partial_sum_kernel<<<(D + 127) / 128, 128, 0, st>>>(dprior_ws, (int)grid, D, 2 * D, D, ds0);
+        partial_sum_kernel<<<2 * D, 128, 0, st>>>(dprior_ws, (int)grid, 2 * D, D, dmu0, ds0);
         MMVAE_LAUNCH_CHECK();
     }
     return 0;

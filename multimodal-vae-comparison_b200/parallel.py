@@ -1,0 +1,95 @@
+"""Batch-sharded data parallelism for the hot path: one process per GPU (torchrun), NCCL over NVLink/NVSwitch.
+
+The path shards naturally over batch rows: fusion, sampling, log-densities, KL and the likelihood row
+reductions are row independent and every ELBO / IWAE loss is a plain sum over b.  So there is NO data-path
+collective; the only communication is
+
+  * one all-reduce(SUM) per step of a single flat bucket holding the gradients of the replicated parameters
+    (encoder / decoder weights and the prior logits ``_pz_params[1]``) -- SUM, not mean: the reference's losses are
+    sums over the batch;
+  * three tiny forward exchanges that batch-GLOBAL statistics need for exact parity:
+      (1) DReG parity mode: the (M,K) batch-summed log-weights are all-reduced between the two combine stages
+          (ops._Dreg, include/mmvae_b200.h mmvae_objective_dreg_stage{1,2});
+      (2) MoPoE: batch means use the global batch size (``model.global_batch``), no communication;
+      (3) optimal_sigma: the scalar sum of squares is all-reduced between its stages (ops._OsigmaRows).
+"""
+from typing import Iterable, List
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_global: int, rank: int, world: int):
+    """Contiguous global-row range [lo, hi) of `rank`: rows [g*B/G, (g+1)*B/G), remainder to the first ranks."""
+    base, rem = divmod(n_global, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(batch: dict, rank: int, world: int) -> dict:
+    """Slice every per-sample tensor of a reference-format batch dict ({"mod_i": {"data","masks","categorical"}})."""
+    out = {}
+    for mod, entry in batch.items():
+        n = None
+        for v in entry.values():
+            if torch.is_tensor(v):
+                n = v.shape[0]
+                break
+        new = dict(entry)
+        if n is not None:
+            lo, hi = shard_range(n, rank, world)
+            for k, v in entry.items():
+                if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == n:
+                    new[k] = v[lo:hi]
+        out[mod] = new
+    return out
+
+
+def attach(model, group=None, global_batch: int = None):
+    """Tell a drop-in model plugin that it sees one shard of a global batch."""
+    model.group = group
+    model.obj_fn.group = group
+    model.global_batch = global_batch
+    return model
+
+
+class GradSync:
+    """All-reduce(SUM) of the gradients of replicated parameters through ONE flat bucket per step.
+
+    NVSwitch gives every GPU full bandwidth to every peer, so the bucket is sized for launch latency: a single
+    collective per step instead of one per parameter."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group=None):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        self.group = group
+        self._flat = None
+
+    def _bucket(self):
+        n = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        if self._flat is None or self._flat.numel() != n or self._flat.device != ref.device:
+            self._flat = torch.empty(n, dtype=torch.float32, device=ref.device)
+        return self._flat
+
+    def __call__(self):
+        if not self.params or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return
+        flat = self._bucket()
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is None:
+                flat[off:off + n].zero_()
+            else:
+                flat[off:off + n].copy_(p.grad.reshape(-1))
+            off += n
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            g = flat[off:off + n].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += n

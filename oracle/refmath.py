@@ -108,8 +108,8 @@ def log_mean_exp(value, dim=0, keepdim=False):
 
 
 def softclip(t, mn):
-    """utils.py:66-69."""
-    return mn + F.softplus((t - mn).float())
+    """utils.py:66-69 (the reference casts to float; kept in the input dtype so fp64 evaluation stays fp64)."""
+    return mn + F.softplus(t - mn)
 
 
 def prior_params(pz_logits_mu, pz_logits):
@@ -195,23 +195,24 @@ def recon_logp(ltype, loc, target, K=1, likelihood="normal", scale=0.75, mask_le
     mask_len: objectives.py:43-45 crops loc[:, :masks.shape[1]]."""
     if mask_len is not None:
         loc = loc[:, :mask_len]
-    target = reshape_target(loc, target.float() if ltype != "lprob" else target, K)
+    # reference: target.float(); the cast follows loc so that the restatement can also be evaluated in fp64
+    target = reshape_target(loc, target.to(loc.dtype), K)
     bs = target.shape[0]
     if ltype == "bce":  # objectives.py:391-406
-        loss = F.binary_cross_entropy(loc, target.float().detach(), reduction="none").reshape(bs, -1)
+        loss = F.binary_cross_entropy(loc, target.detach(), reduction="none").reshape(bs, -1)
     elif ltype == "lprob":  # objectives.py:408-424 (fp64 accumulate, NaN -> 0)
         sc = torch.as_tensor(scale, dtype=loc.dtype, device=loc.device)
         out = log_prob(likelihood, target, loc, sc).view(bs, -1).double().reshape(bs, -1)
         out = torch.where(torch.isnan(out), torch.zeros_like(out), out)
         loss = -out
     elif ltype == "l1":  # objectives.py:426-441
-        loss = F.l1_loss(loc, target.float().detach(), reduction="none").reshape(bs, -1)
+        loss = F.l1_loss(loc, target.detach(), reduction="none").reshape(bs, -1)
     elif ltype == "mse":  # objectives.py:443-458
-        loss = F.mse_loss(loc, target.float().detach(), reduction="none").reshape(bs, -1)
+        loss = F.mse_loss(loc, target.detach(), reduction="none").reshape(bs, -1)
     elif ltype == "category_ce":  # objectives.py:485-500 -- class axis is dim 1
-        loss = F.cross_entropy(loc, target.float().detach(), reduction="none").reshape(bs, -1)
+        loss = F.cross_entropy(loc, target.detach(), reduction="none").reshape(bs, -1)
     elif ltype == "optimal_sigma":  # objectives.py:502-509
-        t = target.float().detach()
+        t = target.detach()
         log_sigma = ((t - loc) ** 2).mean(list(range(loc.dim())), keepdim=True).sqrt().log()
         log_sigma = log_sigma.reshape(())
         log_sigma = softclip(log_sigma, -6)

@@ -1,0 +1,137 @@
+"""CPU: the C-ABI library loads and exports exactly what include/mmvae_b200.h declares; the product package is
+isolated from the oracle; ops refuse CPU tensors (no fallback); host-side integer logic."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "multimodal-vae-comparison_b200")
+HEADER = os.path.join(ROOT, "include", "mmvae_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    import mmvae_b200._lib as L
+    return L
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"MMVAE_API\s+(?:int64_t|int)\s+(mmvae_\w+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 20
+    cdll = ctypes.CDLL(lib.LIB_PATH)
+    for n in names:
+        assert hasattr(cdll, n), "symbol %s declared in the header but not exported" % n
+    assert sorted(lib.SIGNATURES) == names, "ctypes binding and header disagree"
+
+
+def test_only_cabi_symbols_are_exported(lib):
+    out = subprocess.run(["nm", "-D", "--defined-only", lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    assert sorted(exported) == declared_symbols()
+
+
+def test_version_and_argument_errors_without_gpu(lib):
+    L = lib.load()
+    assert L.mmvae_version() == 1
+    # argument validation happens before any launch: callable without a GPU
+    assert L.mmvae_loglik_rowreduce_fwd(None, 0, 0, None, 0, 0, 0, 0, 0, 0, 0.75, 1.0, None, None, None) == -1
+    assert L.mmvae_loglik_workspace_bytes(32, 12288, 0) > 0      # few long rows are split over CTAs
+    assert L.mmvae_loglik_workspace_bytes(7680, 12288, 0) == 0   # one CTA per row: no workspace
+    assert L.mmvae_reduce_sum(None, 0, 1.0, None, None) == -1
+
+
+def test_draw_desc_layout_matches_header(lib):
+    assert ctypes.sizeof(lib.DrawDesc) == 56
+
+
+def test_library_is_sm100a_only(lib):
+    out = subprocess.run(["cuobjdump", "-lelf", lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_ops_refuse_cpu_tensors():
+    import mmvae_b200.ops as ops
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.loglik_rows(torch.rand(4, 8), torch.rand(4, 8), "bce")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.moe_logdens(torch.rand(2, 3, 4), torch.rand(2, 3, 4), torch.zeros(1, 4), torch.ones(1, 4),
+                        torch.rand(2, 1, 3, 4), [0, 0])
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    import mmvae_b200._lib as L
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", os.path.join(PKG, "does_not_exist.so"))
+    with pytest.raises(RuntimeError, match="no fallback"):
+        L.load()
+
+
+def test_product_never_imports_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/."""
+    bad = []
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M) or "refmath" in src or "/root/reference" in src:
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
+
+
+def test_subset_orders_and_chunk_maps(golden):
+    import mmvae_b200.mmvae_models as mm
+    from oracle import refmath
+    assert mm.poe_subsets(range(3)) == refmath.poe_subsets(range(3))
+    assert mm.mopoe_subsets(range(4)) == refmath.mopoe_subsets(range(4))
+    assert mm.mopoe_subsets(["mod_1", "mod_2", "mod_3"])[3] == ("mod_1", "mod_2")
+    for (S, B), ends in golden["chunk_ends"].items():
+        assert list(mm.mopoe_chunk_bounds(S, B)[1]) == ends, (S, B)  # bit exact vs the reference run
+    for S in (1, 3, 7, 15, 31, 63):
+        assert mm.mopoe_inmodel_component(S) == S - 1
+    masks = mm.subset_bitmasks(mm.mopoe_subsets(range(3)), 3)
+    assert masks.tolist()[:6] == [1, 2, 4, 3, 5, 6] and (masks[6].item() & 0xffffffff) == (7 | 1 << 31)
+
+
+def test_registry_and_plugin_surface():
+    import mmvae_b200
+    from oracle import cases
+    assert set(mmvae_b200.MODEL_REGISTRY) == {"moe", "poe", "mopoe", "dmvae"}
+    case = cases.case_list()[0]
+    m = mmvae_b200.poe(cases.build_vaes(case), case["D"], {"obj": "elbo", "beta": 1.0, "K": 1}, None)
+    assert isinstance(m, mmvae_b200.TorchMMVAE) and m.modelName == "poe" and m.K == 1
+    mu0, s0 = m.pz_params
+    assert mu0.shape == (1, case["D"]) and torch.allclose(s0, torch.ones(1, case["D"]))
+    assert {"_pz_params.0", "_pz_params.1"} <= set(m.state_dict())
+    assert m.obj_fn.obj_name == "elbo"
+    with pytest.raises(AssertionError):
+        mmvae_b200.MultimodalObjective("nope")
+    m.obj_fn.set_ltype("bce")
+    with pytest.raises(AssertionError):
+        m.obj_fn.set_ltype("does_not_exist")
+    with pytest.raises(ValueError):  # the reference also needs every modality in objective()
+        m.objective({"mod_1": {"data": None, "masks": None}, "mod_2": {"data": torch.zeros(2, 5, 27), "masks": None}})
+
+
+def test_algorithmic_bytes_match_survey():
+    import mmvae_b200.synthetic as syn
+    import mmvae_b200.workloads as W
+    b = {k: W.algorithmic_bytes(dict(v)) for k, v in syn.WORKLOADS.items()}
+    assert abs(b["c1_poe_elbo_cdsprites_l1"] - 449e3) / 449e3 < 0.01
+    assert abs(b["c2_moe_iwae_cdsprites_l5"] - 9.95e6) / 9.95e6 < 0.01
+    assert abs(b["c3_mopoe_elbo_sprites"] - 1.18e6) / 1.18e6 < 0.01
+    # C5: bf16 reconstructions + gradients (2R) against fp32 targets (T): 3 terms per modality, 8 bytes per feature
+    c5 = W.algorithmic_bytes(dict(syn.WORKLOADS["c5_dmvae_elbo_cub"]), torch.bfloat16)
+    assert abs(c5 - 3 * 8 * (12288 + 6642)) / c5 < 0.01

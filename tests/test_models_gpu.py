@@ -75,7 +75,8 @@ def test_dropin_logged_terms(golden, idx):
     got, out = run_dropin(case)
     if "kld" in ref and ref["kld"].dim() == 0 or case["model"] == "moe":
         assert _rel(torch.as_tensor(out["kld"]).sum(), ref["kld"].sum()) < TOL
-    if "reconstruction_loss" in ref and case["model"] in ("poe", "dmvae", "mopoe"):
+    # (POE's logged list pairs modality m with the m-th SUBSET of a PYTHONHASHSEED dependent order: not comparable)
+    if "reconstruction_loss" in ref and case["model"] in ("dmvae", "mopoe"):
         mine = out["reconstruction_loss"]
         tot = sum(float(torch.as_tensor(m).sum()) for m in mine)
         assert abs(tot - float(ref["reconstruction_loss"].sum())) <= TOL * abs(float(ref["reconstruction_loss"].sum()))

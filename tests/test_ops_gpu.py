@@ -235,9 +235,9 @@ def test_latent_draws_poe_subsets(ops, M, B, D):
     wk = [torch.randn(B, generator=g) for _ in subsets]
 
     def run(dev):
-        mus = [p[0].to(dev).requires_grad_(True) for p in post]
-        ss = [p[1].to(dev).requires_grad_(True) for p in post]
-        lg = logits.to(dev).requires_grad_(True)
+        mus = [p[0].detach().clone().to(dev).requires_grad_(True) for p in post]
+        ss = [p[1].detach().clone().to(dev).requires_grad_(True) for p in post]
+        lg = logits.detach().clone().to(dev).requires_grad_(True)
         mu0 = torch.zeros_like(lg)
         s0 = torch.softmax(lg, 1) * D
         tot = 0
@@ -287,9 +287,9 @@ def test_latent_draws_direct_and_private(ops):
     wk = [torch.randn(B, generator=g) for _ in range(4)]
 
     def run(dev):
-        mus = [p[0].to(dev).requires_grad_(True) for p in post]
-        ss = [p[1].to(dev).requires_grad_(True) for p in post]
-        lg = logits.to(dev).requires_grad_(True)
+        mus = [p[0].detach().clone().to(dev).requires_grad_(True) for p in post]
+        ss = [p[1].detach().clone().to(dev).requires_grad_(True) for p in post]
+        lg = logits.detach().clone().to(dev).requires_grad_(True)
         mu0, s0 = torch.zeros_like(lg), torch.softmax(lg, 1) * D
         if dev == "cpu":
             sh, pr = (mus[0][:, :D], ss[0][:, :D]), (mus[1][:, D:], ss[1][:, D:])
@@ -376,9 +376,9 @@ def test_moe_logdens(ops, M, B, D, K, dists, through_z):
     w_lp = torch.randn(M, K, B, generator=g)
 
     def run(dev):
-        mus = [p[0].to(dev).requires_grad_(True) for p in post]
-        ss = [p[1].to(dev).requires_grad_(True) for p in post]
-        lg = logits.to(dev).requires_grad_(True)
+        mus = [p[0].detach().clone().to(dev).requires_grad_(True) for p in post]
+        ss = [p[1].detach().clone().to(dev).requires_grad_(True) for p in post]
+        lg = logits.detach().clone().to(dev).requires_grad_(True)
         mu0, s0 = torch.zeros_like(lg), torch.softmax(lg, 1) * D
         if dev == "cpu":
             z = torch.stack([refmath.rsample(dists[m], mus[m], ss[m], noise[m]) for m in range(M)])
@@ -413,7 +413,7 @@ def test_iwae_combine(ops, M, L, K, B):
     beta = 1.3
 
     def run(dev):
-        a, b, c = (t.to(dev).requires_grad_(True) for t in (lpz, lq, lpx))
+        a, b, c = (t.detach().clone().to(dev).requires_grad_(True) for t in (lpz, lq, lpx))
         if dev == "cpu":
             lws = [a[r] + c[r].sum(0) - beta * refmath.log_mean_exp(b[r]) for r in range(M)]
             loss = -refmath.log_mean_exp(torch.cat(lws)).sum()
@@ -435,7 +435,7 @@ def test_dreg_combine(ops, M, L, K, B):
     lpx = torch.randn(M, L, K, B, generator=g)
 
     def run(dev):
-        a, b, c = (t.to(dev).requires_grad_(True) for t in (lpz, lq, lpx))
+        a, b, c = (t.detach().clone().to(dev).requires_grad_(True) for t in (lpz, lq, lpx))
         if dev == "cpu":
             lw = torch.stack([a[r].sum(-1) + c[r].sum(0).sum(-1) - refmath.log_mean_exp(b[r]).sum(-1) for r in range(M)])
             with torch.no_grad():
