@@ -78,10 +78,10 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
         if (live) {
             for (int j = lane; j < p.d; j += 32) {
                 float m = -INFINITY;
-                for (int c = 0; c < p.C; ++c) m = fmaxf(m, Elem<TX>::load1(rx + c * p.d + j));
+                for (int c = 0; c < p.C; ++c) m = fmaxf(m, Elem<TX>::get(rx + c * p.d + j));
                 float se = 0.f, ts = 0.f, txs = 0.f;
                 for (int c = 0; c < p.C; ++c) {
-                    const float xv = Elem<TX>::load1(rx + c * p.d + j), tv = Elem<TT>::load1(rt + c * p.d + j);
+                    const float xv = Elem<TX>::get(rx + c * p.d + j), tv = Elem<TT>::get(rt + c * p.d + j);
                     se += __expf(xv - m);
                     ts += tv;
                     txs = fmaf(tv, xv, txs);
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
         if (live)
             for (int j = lane; j < p.d; j += 32) {
                 float m = -INFINITY;
-                for (int c = w; c < p.C; c += W) m = fmaxf(m, Elem<TX>::load1(rx + c * p.d + j));
+                for (int c = w; c < p.C; c += W) m = fmaxf(m, Elem<TX>::get(rx + c * p.d + j));
                 part[((size_t)(rl * W + w) * p.d + j) * 4] = m;
             }
         __syncthreads();
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
                 for (int ww = 0; ww < W; ++ww) m = fmaxf(m, part[((size_t)(rl * W + ww) * p.d + j) * 4]);
                 float se = 0.f, ts = 0.f, txs = 0.f;
                 for (int c = w; c < p.C; c += W) {
-                    const float xv = Elem<TX>::load1(rx + c * p.d + j), tv = Elem<TT>::load1(rt + c * p.d + j);
+                    const float xv = Elem<TX>::get(rx + c * p.d + j), tv = Elem<TT>::get(rt + c * p.d + j);
                     se += __expf(xv - m);
                     ts += tv;
                     txs = fmaf(tv, xv, txs);
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
                 const float lse = s_lse[rl * p.d + j], ts = s_ts[rl * p.d + j];
                 for (int c = w; c < p.C; c += W) {
                     const int e = c * p.d + j;
-                    const float gv = wl * (Elem<TT>::load1(rt + e) - __expf(Elem<TX>::load1(rx + e) - lse) * ts);
+                    const float gv = wl * (Elem<TT>::get(rt + e) - __expf(Elem<TX>::get(rx + e) - lse) * ts);
                     if (p.tma)
                         Elem<TX>::store1(gs + e, gv);
                     else

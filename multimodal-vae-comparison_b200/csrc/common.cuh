@@ -77,7 +77,8 @@ struct Elem<float> {
     __device__ static __forceinline__ uint4 pack(const float* o) {
         return make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]));
     }
-    __device__ static __forceinline__ float load1(const float* p) { return __ldg(p); }
+    __device__ static __forceinline__ float load1(const float* p) { return __ldg(p); }  // GLOBAL memory only
+    __device__ static __forceinline__ float get(const float* p) { return *p; }          // any address space
     __device__ static __forceinline__ void store1(float* p, float v) { *p = v; }
 };
 template <>
@@ -101,6 +102,7 @@ struct Elem<__nv_bfloat16> {
         return make_uint4(w[0], w[1], w[2], w[3]);
     }
     __device__ static __forceinline__ float load1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+    __device__ static __forceinline__ float get(const __nv_bfloat16* p) { return __bfloat162float(*p); }
     __device__ static __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
 

@@ -1,6 +1,7 @@
 """CPU, world_size 2, gloo: the host-side logic of the batch-sharded path -- shard ranges, the flat-bucket gradient
 all-reduce(SUM), and the three forward exchanges of SURVEY 8e (DReG batch sums, MoPoE global batch mean,
 optimal_sigma global RMS) -- reproduce the single-process result of the oracle on the full batch."""
+import math
 import os
 import socket
 
@@ -85,7 +86,7 @@ def _worker(rank, world, port, q):
         ss = ((tt[lo:hi] - x[lo:hi]) ** 2).sum().reshape(1)
         dist.all_reduce(ss)
         log_sigma = refmath.softclip((ss / x.numel()).sqrt().log(), -6)
-        rows = -(((tt[lo:hi] - x[lo:hi]) / log_sigma.exp()) ** 2 + log_sigma + 0.5 * torch.log(torch.tensor(2 * torch.pi))).sum(-1)
+        rows = -(((tt[lo:hi] - x[lo:hi]) / log_sigma.exp()) ** 2 + log_sigma + 0.5 * math.log(2 * math.pi)).sum(-1)
         res["osigma"] = float((rows - full[lo:hi]).abs().max() / full.abs().max())
         if rank == 0:
             q.put(res)
@@ -106,8 +107,8 @@ def test_sharded_equals_full_batch_world2():
         assert p.exitcode == 0
     res = q.get()
     for k, v in res.items():
-        if isinstance(v, tuple):
-            assert max(v) < 1e-9, (k, v)
+        if isinstance(v, tuple):  # (loss, all-reduced replicated grad [fp32 flat bucket], local grads)
+            assert v[0] < 1e-9 and v[1] < 1e-6 and v[2] < 1e-9, (k, v)
         else:
             assert v < 1e-9, (k, v)
 
