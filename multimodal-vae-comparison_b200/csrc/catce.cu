@@ -180,8 +180,12 @@ static int launch_catce(int mode, CatceParams p, cudaStream_t st) {
     // warps per row: split long class axes; rows per CTA: fill ~8 warps, prefer a TMA-able (16 B multiple) run
     int W = p.C >= 192 ? 4 : (p.C >= 96 ? 2 : 1);
     int R = 8 / W;
-    const size_t budget = 100 * 1024;  // keep >= 2 CTAs per SM
-    while (R > 1 && catce_smem(R, W, n, p.d, sx, stt) > budget) R >>= 1;
+    // a CTA's life is TMA latency + a short compute phase: favour many resident CTAs (<= 48 KB each) ...
+    while (R > 1 && catce_smem(R, W, n, p.d, sx, stt) > 48 * 1024) R >>= 1;
+    // ... but keep the staged run a multiple of 16 bytes (TMA-able) when that still leaves 2 CTAs per SM
+    auto tma_ok = [&](int r) { return ((size_t)r * n * sx) % 16 == 0 && ((size_t)r * n * stt) % 16 == 0; };
+    for (int r2 = R; r2 <= 8 && !tma_ok(R); r2 <<= 1)
+        if (tma_ok(r2) && catce_smem(r2, W, n, p.d, sx, stt) <= 110 * 1024 && r2 * W <= 16) R = r2;
     if (catce_smem(R, W, n, p.d, sx, stt) > 200 * 1024) return MMVAE_E_LIMIT;
     bool dense = p.ldx == n && p.ldt == n && (mode == 0 || p.ldg == n);
     bool tma = dense && aligned16(p.x) && aligned16(p.t) && (mode == 0 || aligned16(p.g)) && p.rows % R == 0 &&

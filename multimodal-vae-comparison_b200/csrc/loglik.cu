@@ -16,7 +16,7 @@ constexpr int kThreads = 256;
 template <int MODE>
 struct Tune {
     static constexpr int kUnroll = 4;      // measured: 2 in flight / 32 regs / 8 CTAs per SM was 6% slower for MODE 0
-    static constexpr int kMinBlocks = (MODE == 0) ? 5 : 4;
+    static constexpr int kMinBlocks = 4;
 };
 constexpr int kUnrollMax = 4;
 
@@ -33,6 +33,14 @@ struct LoglikParams {
     int cpr;        // CTAs per row
     float scale, lam, w_const;
 };
+
+// MUFU.LG2 without the compiler's per-call denormal rescue (3 extra instructions per log).  Sub-normal inputs are
+// handled exactly by the caller's vector-level guard (slow path below), everything else is identical.
+__device__ __forceinline__ float lg2_ftz(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 template <int LT>
 struct LogP {
@@ -51,6 +59,12 @@ struct LogP {
             c_const = 0.f;
         }
     }
+    // exact value for a sub-normal reconstruction 0 < x < 2^-126 (lg2.approx.ftz would flush it to log 0)
+    __device__ __noinline__ static float bce_value_subnormal(float x, float t) {
+        const float l1 = fmaxf(__log2f(1.0f - x), -144.26950408889634f);
+        const float l0 = fmaxf(__log2f(x), -144.26950408889634f);
+        return fmaf(t, l0 - l1, l1);
+    }
     // value of log p(t | x) and its derivative w.r.t. x
     template <bool NEED_V, bool NEED_D>
     __device__ __forceinline__ void eval(float x, float t, float& v, float& d) const {
@@ -62,8 +76,9 @@ struct LogP {
             // evaluated in log2 units (the row sum is rescaled by ln 2 once, see kValueScale) and blended with one
             // FFMA: 2 MUFU.LG2 + FADD + 2 FMNMX + FADD + FFMA per element
             if (NEED_V) {
-                const float l1 = fmaxf(__log2f(1.0f - x), -144.26950408889634f);  // -100 / ln 2
-                const float l0 = fmaxf(__log2f(x), -144.26950408889634f);
+                // 1-x is never sub-normal (0 or >= 2^-24); a sub-normal x (0 < x < 2^-126) takes the exact path
+                const float l1 = fmaxf(lg2_ftz(1.0f - x), -144.26950408889634f);  // -100 / ln 2
+                const float l0 = fmaxf(lg2_ftz(x), -144.26950408889634f);
                 v = fmaf(t, l0 - l1, l1);
             }
             if (NEED_D) d = __fdividef(t - x, fmaxf((1.0f - x) * x, 1e-12f));
@@ -127,8 +142,9 @@ __global__ void __launch_bounds__(kThreads, Tune<MODE>::kMinBlocks) loglik_kerne
 
     const int64_t row = blockIdx.x / p.cpr;
     const int chunk_id = blockIdx.x - row * p.cpr;
-    const int64_t c0 = (int64_t)chunk_id * p.chunk;
-    const int64_t c1 = min(p.P, c0 + p.chunk);
+    // 32-bit offsets inside a row (P < 2^31 is checked on the host): halves the address arithmetic
+    const int c0 = chunk_id * (int)p.chunk;
+    const int c1 = min((int)p.P, c0 + (int)p.chunk);
 
     const TX* __restrict__ x = reinterpret_cast<const TX*>(p.x) + row * p.ldx;
     const TT* __restrict__ t = reinterpret_cast<const TT*>(p.t) + (row % p.B) * p.ldt;
@@ -139,38 +155,57 @@ __global__ void __launch_bounds__(kThreads, Tune<MODE>::kMinBlocks) loglik_kerne
     if (NEED_D) wl = (p.w_rows ? __ldg(p.w_rows + row) : p.w_const) * p.lam;
 
     float acc = 0.f;
-    constexpr int64_t kStep = (int64_t)kThreads * V;
-    for (int64_t base = c0 + (int64_t)threadIdx.x * V; base < c1; base += kStep * kUnroll) {
+    constexpr int kStep = kThreads * V;
+
+    auto process = [&](const float* xv, const float* tv, int i) {
+        float gv[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            float v = 0.f, d = 0.f;
+            f.template eval<NEED_V, NEED_D>(xv[e], tv[e], v, d);
+            if (NEED_V) acc += v;
+            if (NEED_D) gv[e] = wl * d;
+        }
+        if (LT == MMVAE_LT_BCE && NEED_V) {
+            // vector-level guard for sub-normal reconstructions (never taken for decoder outputs, which the
+            // reference clamps to [1e-6, 1-1e-6]): redo those elements exactly
+            float mn = xv[0];
+#pragma unroll
+            for (int e = 1; e < V; ++e) mn = fminf(mn, xv[e]);
+            if (__builtin_expect(mn < 1.17549435e-38f, 0)) {
+                for (int e = 0; e < V; ++e)
+                    if (xv[e] > 0.f && xv[e] < 1.17549435e-38f) {
+                        float v = 0.f, d = 0.f;
+                        f.template eval<true, false>(xv[e], tv[e], v, d);
+                        acc += LogP<LT>::bce_value_subnormal(xv[e], tv[e]) - v;
+                    }
+            }
+        }
+        if (NEED_D) {
+            if (V == 1)
+                Elem<TX>::store1(g + i, gv[0]);
+            else
+                stg_stream(g + i, Elem<TX>::pack(gv));
+        }
+    };
+
+    int base = c0 + (int)threadIdx.x * V;
+    // main body: kUnroll vectors per tensor in flight, no per-vector bounds predicates
+    for (; base + (kUnroll - 1) * kStep < c1; base += kStep * kUnroll) {
         float xv[kUnroll][V], tv[kUnroll][V];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-            const int64_t i = base + u * kStep;
-            if (i < c1) {
-                load_vec<TX, V>(x + i, xv[u], true);
-                load_vec<TT, V>(t + i, tv[u], false);
-            }
+            load_vec<TX, V>(x + base + u * kStep, xv[u], true);
+            load_vec<TT, V>(t + base + u * kStep, tv[u], false);
         }
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const int64_t i = base + u * kStep;
-            if (i < c1) {
-                float gv[V];
-#pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    float v = 0.f, d = 0.f;
-                    f.template eval<NEED_V, NEED_D>(xv[u][e], tv[u][e], v, d);
-                    if (NEED_V) acc += v;
-                    if (NEED_D) gv[e] = wl * d;
-                }
-                if (NEED_D) {
-                    if (V == 1) {
-                        Elem<TX>::store1(g + i, gv[0]);
-                    } else {
-                        stg_stream(g + i, Elem<TX>::pack(gv));
-                    }
-                }
-            }
-        }
+        for (int u = 0; u < kUnroll; ++u) process(xv[u], tv[u], base + u * kStep);
+    }
+    for (; base < c1; base += kStep) {  // tail
+        float xv[V], tv[V];
+        load_vec<TX, V>(x + base, xv, true);
+        load_vec<TT, V>(t + base, tv, false);
+        process(xv, tv, base);
     }
     if (NEED_V) {
         const float tot = block_sum(acc, red) * LogP<LT>::kValueScale;
@@ -239,6 +274,7 @@ static int launch2(const LoglikParams& p, int ltype, bool vect, cudaStream_t st)
 template <int MODE>
 static int launch(LoglikParams p, int dtx, int dtt, int ltype, cudaStream_t st) {
     if (!p.x || !p.t || p.rows <= 0 || p.B <= 0 || p.P <= 0) return MMVAE_E_ARG;
+    if (p.P >= (1LL << 30)) return MMVAE_E_LIMIT;
     if (MODE != MODE_BWD && !p.out_rows) return MMVAE_E_ARG;
     if (MODE != MODE_FWD && !p.g) return MMVAE_E_ARG;
     if (MODE == MODE_BWD && !p.w_rows) return MMVAE_E_ARG;
