@@ -185,7 +185,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     group = None
+    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)  # capture warm-up runs on a side stream
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     L.load()
@@ -303,7 +306,7 @@ def main():
             torch.cuda.current_stream().wait_stream(copy_stream)
             loss = runner.run()
             sync_grads()
-            return float(loss)  # device -> host read of the step's result
+            return float(loss.detach())  # device -> host read of the step's result
 
         for _ in range(3):
             e2e_step()

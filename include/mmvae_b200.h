@@ -95,12 +95,14 @@ MMVAE_API int mmvae_loglik_rowreduce_fused(const void* recon, int64_t ld_recon, 
  *   grad[r,c,j] = w * lam * (t[c,j] - softmax_c(x[:,j])[c] * sum_c' t[c',j])
  * ld_recon / ld_grad: row stride in elements (>= C*d; a mask crop loc[:, :T] keeps the row stride,
  * objectives.py:43-45).  mode: 0 fwd, 1 bwd, 2 fused (same meaning as above).
+ * stats: optional (rows, 2, d) floats: the forward stores logsumexp_c and sum_c t per column, the backward then
+ * runs as a single streaming pass (no reductions); NULL = recompute in the backward.
  * ------------------------------------------------------------------------------------------------------- */
 MMVAE_API int mmvae_catce_rows(int mode, const void* recon, int64_t ld_recon, int dtype_recon,
                      const void* target, int64_t ld_target, int dtype_target,
                      int64_t rows, int64_t B, int64_t C, int64_t d, float lam,
                      const float* w_rows, float w_const,
-                     float* out_rows, void* grad_recon, int64_t ld_grad, void* stream);
+                     float* out_rows, void* grad_recon, int64_t ld_grad, float* stats, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * optimal_sigma (sigma-VAE) rows: replaces ReconLoss.optimal_sigma (objectives.py:502-509) + utils.softclip

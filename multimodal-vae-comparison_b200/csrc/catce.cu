@@ -19,6 +19,7 @@ struct CatceParams {
     void* g;
     const float* w_rows;
     float* out_rows;
+    float* stats;  // (rows, 2, d): logsumexp and target sum per column; written by fwd, read by bwd (may be NULL)
     int64_t ldx, ldt, ldg, rows, B;
     int C, d, R, W, tma;
     float lam, w_const;
@@ -56,7 +57,10 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
             bulk_g2s(sx, xg + row0 * p.ldx, bx, bar);
             bulk_g2s(st, tg + (row0 % p.B) * p.ldt, bt, bar);
         }
-        mbar_wait(bar, 0);
+        // ONE warp polls the mbarrier; the others park on the CTA barrier (a spinning try_wait loop in every warp
+        // burned 3x more issue slots than the arithmetic of the whole kernel -- ncu r1: 18.7 M warp instructions)
+        if (warp == 0) mbar_wait(bar, 0);
+        __syncthreads();
     } else {
         for (int r = 0; r < nrows; ++r) {
             const TX* xr = xg + (row0 + r) * p.ldx;
@@ -74,14 +78,51 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
     const TT* rt = st + (size_t)rl * n;
     float acc = 0.f;
 
+    if (MODE == 1 && p.stats) {
+        // backward with the column statistics cached by the forward: one streaming pass, no reductions.
+        // (class-row, column) walk: warps stride over the R*C class rows, lanes over the columns.
+        for (int i = threadIdx.x; i < nrows * 2 * p.d; i += blockDim.x) s_lse[i] = __ldg(p.stats + row0 * 2 * p.d + i);
+        __syncthreads();
+        const int nwarps = blockDim.x >> 5;
+        for (int r = 0; r < nrows; ++r) {
+            const float wl = __ldg(p.w_rows + row0 + r) * p.lam;
+            const float* sl = s_lse + r * 2 * p.d;
+            TX* gr = reinterpret_cast<TX*>(p.g) + (row0 + r) * p.ldg;
+            for (int j = lane; j < p.d; j += 32) {
+                const float lse = sl[j], ts = sl[p.d + j];
+                for (int c = warp; c < p.C; c += nwarps) {
+                    const int e = r * n + c * p.d + j;
+                    const float gv = wl * (Elem<TT>::get(st + e) - __expf(Elem<TX>::get(sx + e) - lse) * ts);
+                    if (p.tma)
+                        Elem<TX>::store1(sx + e, gv);
+                    else
+                        Elem<TX>::store1(gr + c * p.d + j, gv);
+                }
+            }
+        }
+        if (p.tma) {
+            fence_async_smem();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                bulk_s2g(reinterpret_cast<TX*>(p.g) + row0 * p.ldg, sx, (uint32_t)((size_t)R * n * sizeof(TX)));
+                bulk_wait_read();
+            }
+        }
+        return;
+    }
+
     if (W == 1) {  // one warp owns the whole row: no block barrier on the compute path
         if (live) {
             for (int j = lane; j < p.d; j += 32) {
                 float m = -INFINITY;
-                for (int c = 0; c < p.C; ++c) m = fmaxf(m, Elem<TX>::get(rx + c * p.d + j));
+                const TX* px = rx + j;
+                const TT* pt = rt + j;
+#pragma unroll 5
+                for (int c = 0; c < p.C; ++c) m = fmaxf(m, Elem<TX>::get(px + c * p.d));
                 float se = 0.f, ts = 0.f, txs = 0.f;
+#pragma unroll 5
                 for (int c = 0; c < p.C; ++c) {
-                    const float xv = Elem<TX>::get(rx + c * p.d + j), tv = Elem<TT>::get(rt + c * p.d + j);
+                    const float xv = Elem<TX>::get(px + c * p.d), tv = Elem<TT>::get(pt + c * p.d);
                     se += __expf(xv - m);
                     ts += tv;
                     txs = fmaf(tv, xv, txs);
@@ -139,6 +180,11 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
     if (MODE != 1 && live && w == 0) {
         acc = warp_sum(acc);
         if (lane == 0) p.out_rows[row0 + rl] = p.lam * acc;
+        if (p.stats)
+            for (int j = lane; j < p.d; j += 32) {
+                p.stats[(row0 + rl) * 2 * p.d + j] = s_lse[rl * p.d + j];
+                p.stats[(row0 + rl) * 2 * p.d + p.d + j] = s_ts[rl * p.d + j];
+            }
     }
     if (MODE != 0) {
         TX* gr = reinterpret_cast<TX*>(p.g) + (row0 + rl) * p.ldg;
@@ -178,14 +224,18 @@ template <typename TX, typename TT>
 static int launch_catce(int mode, CatceParams p, cudaStream_t st) {
     const int n = p.C * p.d, sx = (int)sizeof(TX), stt = (int)sizeof(TT);
     // warps per row: split long class axes; rows per CTA: fill ~8 warps, prefer a TMA-able (16 B multiple) run
-    int W = p.C >= 192 ? 4 : (p.C >= 96 ? 2 : 1);
-    int R = 8 / W;
+    const bool fast_bwd = (mode == 1 && p.stats != nullptr);
+    // warps per row split the class axis (short dependency chains); the cached-statistics backward has no per-row
+    // reduction and simply strides all warps over the staged class rows
+    // (measured r1, C = 45: W = 1 -> 17 us, W = 4 -> 27 us: the merge costs more than the shorter chains save)
+    int W = fast_bwd ? 1 : (p.C >= 192 ? 8 : (p.C >= 96 ? 4 : 1));
+    int R = fast_bwd ? 4 : (W == 1 ? 8 : 16 / W);
     // a CTA's life is TMA latency + a short compute phase: favour many resident CTAs (<= 48 KB each) ...
     while (R > 1 && catce_smem(R, W, n, p.d, sx, stt) > 48 * 1024) R >>= 1;
     // ... but keep the staged run a multiple of 16 bytes (TMA-able) when that still leaves 2 CTAs per SM
     auto tma_ok = [&](int r) { return ((size_t)r * n * sx) % 16 == 0 && ((size_t)r * n * stt) % 16 == 0; };
     for (int r2 = R; r2 <= 8 && !tma_ok(R); r2 <<= 1)
-        if (tma_ok(r2) && catce_smem(r2, W, n, p.d, sx, stt) <= 110 * 1024 && r2 * W <= 16) R = r2;
+        if (tma_ok(r2) && catce_smem(r2, W, n, p.d, sx, stt) <= 110 * 1024 && (fast_bwd || r2 * W <= 16)) R = r2;
     if (catce_smem(R, W, n, p.d, sx, stt) > 200 * 1024) return MMVAE_E_LIMIT;
     bool dense = p.ldx == n && p.ldt == n && (mode == 0 || p.ldg == n);
     bool tma = dense && aligned16(p.x) && aligned16(p.t) && (mode == 0 || aligned16(p.g)) && p.rows % R == 0 &&
@@ -201,7 +251,8 @@ static int launch_catce(int mode, CatceParams p, cudaStream_t st) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    k<<<(unsigned)grid, R * W * 32, smem, st>>>(p);
+    const int threads = fast_bwd ? 256 : R * W * 32;
+    k<<<(unsigned)grid, threads, smem, st>>>(p);
     MMVAE_LAUNCH_CHECK();
     return 0;
 }
@@ -213,7 +264,7 @@ using namespace mmvae;
 extern "C" int mmvae_catce_rows(int mode, const void* recon, int64_t ld_recon, int dtype_recon, const void* target,
                                 int64_t ld_target, int dtype_target, int64_t rows, int64_t B, int64_t C, int64_t d,
                                 float lam, const float* w_rows, float w_const, float* out_rows, void* grad_recon,
-                                int64_t ld_grad, void* stream) {
+                                int64_t ld_grad, float* stats, void* stream) {
     if (!recon || !target || rows <= 0 || B <= 0 || C <= 0 || d <= 0) return MMVAE_E_ARG;
     if (mode < 0 || mode > 2) return MMVAE_E_ENUM;
     if (mode != 1 && !out_rows) return MMVAE_E_ARG;
@@ -224,7 +275,7 @@ extern "C" int mmvae_catce_rows(int mode, const void* recon, int64_t ld_recon, i
     CatceParams p{};
     p.x = recon; p.t = target; p.g = grad_recon; p.w_rows = w_rows; p.out_rows = out_rows;
     p.ldx = ld_recon; p.ldt = ld_target; p.ldg = ld_grad; p.rows = rows; p.B = B; p.C = (int)C; p.d = (int)d;
-    p.lam = lam; p.w_const = w_const;
+    p.lam = lam; p.w_const = w_const; p.stats = stats;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype_recon == MMVAE_F32 && dtype_target == MMVAE_F32) return launch_catce<float, float>(mode, p, st);
     if (dtype_recon == MMVAE_BF16 && dtype_target == MMVAE_F32) return launch_catce<__nv_bfloat16, float>(mode, p, st);

@@ -181,20 +181,21 @@ class _CatceRows(torch.autograd.Function):
         _need_cuda(recon, target)
         x, t, rows, B, C, d, ldx, ldt = _catce_geom(recon.detach(), target.detach())
         out = torch.empty(rows, dtype=torch.float32, device=recon.device)
+        stats = torch.empty((rows, 2, d), dtype=torch.float32, device=recon.device)  # cached column statistics
         call("mmvae_catce_rows", 0, _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, C, d, lam, _P(0), 0.0,
-             _ptr(out), _P(0), 0, _stream())
-        ctx.save_for_backward(x, t)
+             _ptr(out), _P(0), 0, _ptr(stats), _stream())
+        ctx.save_for_backward(x, t, stats)
         ctx.meta = (rows, B, C, d, ldx, ldt, lam, recon.shape)
         return out
 
     @staticmethod
     def backward(ctx, g_rows):
-        x, t = ctx.saved_tensors
+        x, t, stats = ctx.saved_tensors
         rows, B, C, d, ldx, ldt, lam, shape = ctx.meta
         w = g_rows.detach().to(torch.float32).contiguous()
         g = torch.empty((rows, C * d), dtype=x.dtype, device=x.device)
         call("mmvae_catce_rows", 1, _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, C, d, lam, _ptr(w), 0.0,
-             _P(0), _ptr(g), C * d, _stream())
+             _P(0), _ptr(g), C * d, _ptr(stats), _stream())
         return g.view(shape), None, None
 
 
@@ -207,7 +208,7 @@ class _CatceWeightedSum(torch.autograd.Function):
         g = torch.empty((rows, C * d), dtype=x.dtype, device=x.device)
         w = None if w_rows is None else w_rows.detach().to(torch.float32).contiguous()
         call("mmvae_catce_rows", 2, _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, C, d, lam, _ptr(w),
-             float(w_const), _ptr(out), _ptr(g), C * d, _stream())
+             float(w_const), _ptr(out), _ptr(g), C * d, _P(0), _stream())
         S = torch.empty((), dtype=torch.float32, device=recon.device)
         if w is None:
             call("mmvae_reduce_sum", _ptr(out), rows, float(w_const), _ptr(S), _stream())
