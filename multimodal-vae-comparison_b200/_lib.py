@@ -91,7 +91,7 @@ def call(name, *args):
     global launch_count
     fn = getattr(load(), name)
     if timer is not None and name in timer.names:
-        rc = timer.wrap(name, lambda: fn(*args))
+        rc = timer.wrap(name, lambda: fn(*args), args)
     else:
         rc = fn(*args)
     if rc != 0:

@@ -30,7 +30,9 @@ struct LoglikParams {
     int64_t ldx, ldt, ldg;
     int64_t rows, B, P;
     int64_t chunk;  // elements of a row handled by one CTA (multiple of the vector width)
-    int cpr;        // CTAs per row
+    int cpr;        // CTAs per row (long, few rows) ...
+    int tpr;        // ... or threads per row (32..256, power of two): short rows share a CTA, 256/tpr rows each
+    int tile;       // batch rows per L2 tile: CTAs sweep all K samples of `tile` targets before moving on
     float scale, lam, w_const;
 };
 
@@ -132,19 +134,38 @@ __device__ __forceinline__ void load_vec(const T* p, float* o, bool stream) {
     }
 }
 
-template <typename TX, typename TT, int LT, int MODE, bool VECT>
+template <typename TX, typename TT, int LT, int MODE, bool VECT, bool SHORT>
 __global__ void __launch_bounds__(kThreads, Tune<MODE>::kMinBlocks) loglik_kernel(const LoglikParams p) {
+    const int tpr = SHORT ? p.tpr : kThreads;  // compile-time 256 for long rows: keeps the hot variant lean
     constexpr int V = VECT ? Elem<TX>::kPer16B : 1;
     constexpr int kUnroll = (sizeof(TX) == 2) ? 2 : Tune<MODE>::kUnroll;  // bf16 vectors carry 8 elements
     constexpr bool NEED_V = (MODE != MODE_BWD);
     constexpr bool NEED_D = (MODE != MODE_FWD);
     __shared__ float red[32];
 
-    const int64_t row = blockIdx.x / p.cpr;
-    const int chunk_id = blockIdx.x - row * p.cpr;
-    // 32-bit offsets inside a row (P < 2^31 is checked on the host): halves the address arithmetic
+    // short rows: tpr threads per row, 256/tpr rows per CTA (cpr == 1); long rows: cpr CTAs per row (tpr == 256)
+    const int rpc = kThreads / tpr;
+    const int sub = threadIdx.x / tpr, tin = threadIdx.x - sub * tpr;
+    // Logical index -> row.  Rows are k-major (row = k*B + b) and the K rows of a sample share one target row; walking
+    // rows in memory order re-reads a target larger than L2 from DRAM K times.  So the launch walks b-tiles of
+    // `tile` targets (sized to stay L2 resident) and, inside a tile, all K samples: li -> (tile, k, b in tile).
+    const int64_t li = (int64_t)(blockIdx.x / p.cpr) * rpc + sub;
+    const bool row_ok = li < p.rows;
+    int64_t row_raw = row_ok ? li : p.rows - 1;
+    if (p.tile < p.B) {
+        const int64_t K = p.rows / p.B;
+        const int64_t bt = row_raw / ((int64_t)p.tile * K);
+        const int64_t b0 = bt * p.tile;
+        const int64_t tb = min((int64_t)p.tile, p.B - b0);  // the last tile may be short
+        const int64_t rem = row_raw - b0 * K;
+        const int64_t k = rem / tb;
+        row_raw = k * p.B + b0 + (rem - k * tb);
+    }
+    const int64_t row = row_raw;
+    const int chunk_id = blockIdx.x % p.cpr;
+    // 32-bit offsets inside a row (P < 2^30 is checked on the host): halves the address arithmetic
     const int c0 = chunk_id * (int)p.chunk;
-    const int c1 = min((int)p.P, c0 + (int)p.chunk);
+    const int c1 = row_ok ? min((int)p.P, c0 + (int)p.chunk) : c0;
 
     const TX* __restrict__ x = reinterpret_cast<const TX*>(p.x) + row * p.ldx;
     const TT* __restrict__ t = reinterpret_cast<const TT*>(p.t) + (row % p.B) * p.ldt;
@@ -155,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, Tune<MODE>::kMinBlocks) loglik_kerne
     if (NEED_D) wl = (p.w_rows ? __ldg(p.w_rows + row) : p.w_const) * p.lam;
 
     float acc = 0.f;
-    constexpr int kStep = kThreads * V;
+    const int kStep = tpr * V;
 
     auto process = [&](const float* xv, const float* tv, int i) {
         float gv[V];
@@ -189,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, Tune<MODE>::kMinBlocks) loglik_kerne
         }
     };
 
-    int base = c0 + (int)threadIdx.x * V;
+    int base = c0 + tin * V;
     // main body: kUnroll vectors per tensor in flight, no per-vector bounds predicates
     for (; base + (kUnroll - 1) * kStep < c1; base += kStep * kUnroll) {
         float xv[kUnroll][V], tv[kUnroll][V];
@@ -208,8 +229,20 @@ __global__ void __launch_bounds__(kThreads, Tune<MODE>::kMinBlocks) loglik_kerne
         process(xv, tv, base);
     }
     if (NEED_V) {
-        const float tot = block_sum(acc, red) * LogP<LT>::kValueScale;
-        if (threadIdx.x == 0) {
+        // reduce over the tpr threads of a row: warp shuffles, then (tpr > 32) the row's warps through smem
+        float tot = warp_sum(acc);
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (tpr > 32) {
+            if (lane == 0) red[wid] = tot;
+            __syncthreads();
+            const int wpr = tpr >> 5;  // warps per row
+            if (tin < 32) {
+                float v = tin < wpr ? red[sub * wpr + tin] : 0.f;
+                tot = warp_sum(v);
+            }
+        }
+        tot *= LogP<LT>::kValueScale;
+        if (tin == 0 && row_ok) {
             if (p.cpr == 1)
                 p.out_rows[row] = p.lam * tot;
             else
@@ -226,6 +259,15 @@ __global__ void loglik_finalize_kernel(const float* __restrict__ ws, float* __re
     float s = 0.f;
     for (int c = 0; c < cpr; ++c) s += ws[r * cpr + c];
     out[r] = lam * s;
+}
+
+static int plan_tpr(int64_t P, int V, int cpr) {
+    if (cpr > 1) return kThreads;
+    // aim at >= kUnrollMax vectors per thread so the unrolled main loop is entered
+    int64_t want = P / ((int64_t)V * kUnrollMax);
+    int tpr = 32;
+    while (tpr * 2 <= want && tpr < kThreads) tpr <<= 1;
+    return tpr;
 }
 
 static void plan(int64_t rows, int64_t P, int V, int64_t* chunk, int* cpr) {
@@ -245,12 +287,16 @@ static void plan(int64_t rows, int64_t P, int V, int64_t* chunk, int* cpr) {
 
 template <typename TX, typename TT, int LT, int MODE>
 static int launch3(const LoglikParams& p, bool vect, cudaStream_t st) {
-    const int64_t grid = p.rows * p.cpr;
+    const int rpc = kThreads / p.tpr;
+    const int64_t grid = p.cpr > 1 ? p.rows * p.cpr : (p.rows + rpc - 1) / rpc;
     if (grid > 0x7fffffffLL) return MMVAE_E_LIMIT;
-    if (vect)
-        loglik_kernel<TX, TT, LT, MODE, true><<<(unsigned)grid, kThreads, 0, st>>>(p);
+    const bool shortrows = p.tpr != kThreads;
+    if (vect && !shortrows)
+        loglik_kernel<TX, TT, LT, MODE, true, false><<<(unsigned)grid, kThreads, 0, st>>>(p);
+    else if (vect)
+        loglik_kernel<TX, TT, LT, MODE, true, true><<<(unsigned)grid, kThreads, 0, st>>>(p);
     else
-        loglik_kernel<TX, TT, LT, MODE, false><<<(unsigned)grid, kThreads, 0, st>>>(p);
+        loglik_kernel<TX, TT, LT, MODE, false, true><<<(unsigned)grid, kThreads, 0, st>>>(p);
     MMVAE_LAUNCH_CHECK();
     if (MODE != MODE_BWD && p.cpr > 1) {
         loglik_finalize_kernel<<<(unsigned)((p.rows + 255) / 256), 256, 0, st>>>(p.ws, p.out_rows, p.rows, p.cpr, p.lam);
@@ -285,6 +331,11 @@ static int launch(LoglikParams p, int dtx, int dtt, int ltype, cudaStream_t st) 
                 (p.ldt * stt) % 16 == 0;
     if (MODE != MODE_FWD) vect = vect && aligned16(p.g) && (p.ldg * sx) % 16 == 0;
     plan(p.rows, p.P, vect ? V : 1, &p.chunk, &p.cpr);
+    p.tpr = plan_tpr(p.P, vect ? V : 1, p.cpr);
+    {   // L2 tiling of the target: keep a tile of targets (<= 16 MB) resident while its K sample rows stream by
+        const int64_t tile_rows = (16LL << 20) / (p.P * stt);
+        p.tile = (p.rows > p.B && tile_rows < p.B) ? (int)(tile_rows < 1 ? 1 : tile_rows) : (int)(p.B > 0x7fffffff ? 0x7fffffff : p.B);
+    }
     if (MODE != MODE_BWD && p.cpr > 1 && !p.ws) return MMVAE_E_ARG;
     if (dtx == MMVAE_F32 && dtt == MMVAE_F32) return launch2<float, float, MODE>(p, ltype, vect, st);
     if (dtx == MMVAE_BF16 && dtt == MMVAE_BF16) return launch2<__nv_bfloat16, __nv_bfloat16, MODE>(p, ltype, vect, st);

@@ -119,6 +119,9 @@ class LeafStep:
             self.row_masks = torch.full((self.B,), bits, dtype=torch.int32, device=dev)
         if self.model != "moe":
             self.eps_packed = torch.cat([n.reshape(-1) for n in self.noise])
+        else:
+            self.eps_stacked = torch.stack(self.noise)  # (M,K,B,D), what mmvae_moe_logdens_* consume
+        self._mu0 = torch.zeros(1, self.D, device=dev)
 
     def leaves(self):
         return [self.mu, self.s, self.pz_logits] + self.recon
@@ -155,7 +158,7 @@ class LeafStep:
                                        w_const=w_const)
 
     def _prior(self):
-        return torch.zeros_like(self.pz_logits), F.softmax(self.pz_logits, dim=1) * self.D
+        return self._mu0, F.softmax(self.pz_logits, dim=1) * self.D
 
     # -- objectives -----------------------------------------------------------------------------------------
     def loss(self):
@@ -170,7 +173,7 @@ class LeafStep:
     def _moe(self):
         M, K, B = self.M, self.K, self.B
         mu0, s0 = self._prior()
-        eps = torch.stack(self.noise)
+        eps = self.eps_stacked
         if self.obj == "elbo":
             z, lq, _ = ops.moe_logdens(self.mu, self.s, mu0.detach(), s0.detach(), eps, self.codes, False)
             kls = ops.latent_draws(self.mu, self.s, None, None, None,

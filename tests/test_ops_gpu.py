@@ -454,3 +454,20 @@ def test_dreg_combine(ops, M, L, K, B):
 def test_ops_refuse_cpu_tensors(ops):
     with pytest.raises(RuntimeError):
         ops.loglik_rows(torch.rand(4, 8), torch.rand(4, 8), "bce")
+
+
+def test_loglik_l2_tiled_row_order(ops):
+    """Targets larger than the L2 tile switch the launch to a (b-tile, k, b) row order: same numbers, any K."""
+    g = torch.Generator().manual_seed(16)
+    K, B, P = 3, 5000, 1024  # B*P*4 = 20 MB > 16 MB tile -> tiled order with a short last tile
+    x = torch.sigmoid(torch.randn(K * B, P, generator=g))
+    t = torch.rand(B, P, generator=g)
+    w = torch.randn(K * B, generator=g)
+    xo = x.clone().requires_grad_(True)
+    ref = refmath.lpx_rows("bce", xo, t, 1.0, K)
+    (ref * w).sum().backward()
+    xc = x.cuda().requires_grad_(True)
+    out = ops.loglik_rows(xc, t.cuda(), "bce")
+    (out * w.cuda()).sum().backward()
+    assert rel(out, ref) < FP32_TOL
+    assert rel(xc.grad, xo.grad) < FP32_TOL
