@@ -222,11 +222,20 @@ __global__ void __launch_bounds__(kThreads, Tune<MODE>::kMinBlocks) loglik_kerne
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) process(xv[u], tv[u], base + u * kStep);
     }
-    for (; base < c1; base += kStep) {  // tail
-        float xv[V], tv[V];
-        load_vec<TX, V>(x + base, xv, true);
-        load_vec<TT, V>(t + base, tv, false);
-        process(xv, tv, base);
+    if (base < c1) {
+        // epilogue: the remaining (< kUnroll) vectors, all loads issued before the first use (a serial tail with
+        // one load in flight per iteration cost short rows ~35% of their bandwidth)
+        float xv[kUnroll][V], tv[kUnroll][V];
+#pragma unroll
+        for (int u = 0; u < kUnroll - 1; ++u) {
+            if (base + u * kStep < c1) {
+                load_vec<TX, V>(x + base + u * kStep, xv[u], true);
+                load_vec<TT, V>(t + base + u * kStep, tv[u], false);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll - 1; ++u)
+            if (base + u * kStep < c1) process(xv[u], tv[u], base + u * kStep);
     }
     if (NEED_V) {
         // reduce over the tpr threads of a row: warp shuffles, then (tpr > 32) the row's warps through smem
@@ -263,7 +272,8 @@ __global__ void loglik_finalize_kernel(const float* __restrict__ ws, float* __re
 
 static int plan_tpr(int64_t P, int V, int cpr) {
     if (cpr > 1) return kThreads;
-    // aim at >= kUnrollMax vectors per thread so the unrolled main loop is entered
+    // aim at >= kUnrollMax vectors per thread so the unrolled main loop is entered (measured r1, P = 3072:
+    // 128 threads/row -> 4.7 TB/s fwd, 256 threads/row with a single round trip -> 3.6 TB/s)
     int64_t want = P / ((int64_t)V * kUnrollMax);
     int tpr = 32;
     while (tpr * 2 <= want && tpr < kThreads) tpr <<= 1;

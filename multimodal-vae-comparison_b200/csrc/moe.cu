@@ -50,7 +50,10 @@ __device__ __forceinline__ void stage_row(const MoeParams& p, int64_t b, float* 
     }
 }
 
+// MT: compile-time modality count (0 = generic, loops predicated up to MMVAE_MAX_MODS)
+template <int MT>
 __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_fwd_kernel(const MoeParams p) {
+    constexpr int MM = MT ? MT : MMVAE_MAX_MODS;
     const int kMoeWarps = blockDim.x >> 5;
     extern __shared__ float sm[];
     const int MD = p.M * p.D;
@@ -77,15 +80,15 @@ __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_fwd_kernel(const MoePar
                 const bool lap = p.dist[r] == MMVAE_LAPLACE;
                 float lq[MMVAE_MAX_MODS];
 #pragma unroll
-                for (int j = 0; j < MMVAE_MAX_MODS; ++j) lq[j] = 0.f;
+                for (int j = 0; j < MM; ++j) lq[j] = 0.f;
                 float lp = 0.f;
                 const int64_t base = (((int64_t)r * p.K + k) * p.B + b) * p.D;
                 for (int c = lane; c < p.D; c += 32) {
                     const float zz = smu[r * p.D + c] + eff_noise(__ldg(p.eps + base + c), lap) * ssig[r * p.D + c];
                     p.z[base + c] = zz;
 #pragma unroll
-                    for (int j = 0; j < MMVAE_MAX_MODS; ++j) {
-                        if (j < p.M) {
+                    for (int j = 0; j < MM; ++j) {
+                        if (MT || j < p.M) {
                             const float u = (zz - smu[j * p.D + c]) * sinv[j * p.D + c];
                             lq[j] += (p.dist[j] == MMVAE_LAPLACE ? -fabsf(u) : -0.5f * u * u) + scst[j * p.D + c];
                         }
@@ -94,8 +97,8 @@ __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_fwd_kernel(const MoePar
                     lp += -0.5f * u0 * u0 + pcst[c];
                 }
 #pragma unroll
-                for (int j = 0; j < MMVAE_MAX_MODS; ++j) {
-                    if (j < p.M) {
+                for (int j = 0; j < MM; ++j) {
+                    if (MT || j < p.M) {
                         const float v = warp_sum(lq[j]);
                         if (lane == 0) p.lq[(((int64_t)r * p.M + j) * p.K + k) * p.B + b] = v;
                     }
@@ -107,7 +110,9 @@ __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_fwd_kernel(const MoePar
     }
 }
 
+template <int MT>
 __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_bwd_kernel(const MoeParams p) {
+    constexpr int MM = MT ? MT : MMVAE_MAX_MODS;
     const int kMoeWarps = blockDim.x >> 5;
     extern __shared__ float sm[];
     const int MD = p.M * p.D;
@@ -139,8 +144,8 @@ __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_bwd_kernel(const MoePar
                 const bool lap = p.dist[r] == MMVAE_LAPLACE;
                 float cj[MMVAE_MAX_MODS];
 #pragma unroll
-                for (int j = 0; j < MMVAE_MAX_MODS; ++j)
-                    cj[j] = (j < p.M && p.dlq) ? __ldg(p.dlq + (((int64_t)r * p.M + j) * p.K + k) * p.B + b) : 0.f;
+                for (int j = 0; j < MM; ++j)
+                    cj[j] = ((MT || j < p.M) && p.dlq) ? __ldg(p.dlq + (((int64_t)r * p.M + j) * p.K + k) * p.B + b) : 0.f;
                 const float cp = p.dlpz ? __ldg(p.dlpz + ((int64_t)r * p.K + k) * p.B + b) : 0.f;
                 const int64_t base = (((int64_t)r * p.K + k) * p.B + b) * p.D;
                 for (int c = lane; c < p.D; c += 32) {
@@ -149,8 +154,8 @@ __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_bwd_kernel(const MoePar
                     float dzt = p.dz_ext ? __ldg(p.dz_ext + base + c) : 0.f;
                     float dz_ld = 0.f;  // d(sum_j c_j log q_j + c_p log p)/dz
 #pragma unroll
-                    for (int j = 0; j < MMVAE_MAX_MODS; ++j) {
-                        if (j < p.M) {
+                    for (int j = 0; j < MM; ++j) {
+                        if (MT || j < p.M) {
                             const float inv = sinv[j * p.D + c];
                             const float df = zz - smu[j * p.D + c];
                             float dmu_j, ds_j;
@@ -202,6 +207,223 @@ __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_bwd_kernel(const MoePar
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Register-resident variants (MT modalities, NC columns per lane, MT*NC <= 8): every per-column constant of the row
+// (mu, sigma, 1/sigma, log normaliser of each posterior, the prior) and -- in the backward -- every gradient
+// accumulator lives in registers for the whole (k, r) loop; shared memory is touched once per row, for the fixed-order
+// cross-warp combine.  r1 ncu on C4 (D=64, K=50): the smem-staged kernels executed 35 M / 44 M warp instructions
+// (~175 per column, constants re-read and accumulators read-modify-written in smem inside the loop).
+// ---------------------------------------------------------------------------------------------------------
+template <int MT, int NC>
+__global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_fwd_reg_kernel(const MoeParams p) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    bool lap[MT];
+#pragma unroll
+    for (int j = 0; j < MT; ++j) lap[j] = p.dist[j] == MMVAE_LAPLACE;
+    float pmu[NC], pinv[NC], pcst[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const int c = lane + 32 * i;
+        const float sg = c < p.D ? __ldg(p.s0 + c) : 1.f;
+        pmu[i] = c < p.D ? __ldg(p.mu0 + c) : 0.f;
+        pinv[i] = 1.0f / sg;
+        pcst[i] = -logf(sg) - kLogSqrt2Pi;
+    }
+    for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
+        float rmu[MT][NC], rsig[MT][NC], rinv[MT][NC], rcst[MT][NC];
+#pragma unroll
+        for (int j = 0; j < MT; ++j)
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const int c = lane + 32 * i;
+                const int64_t o = ((int64_t)j * p.B + b) * p.D + c;
+                const float sg = c < p.D ? __ldg(p.s + o) : 1.f;
+                rmu[j][i] = c < p.D ? __ldg(p.mu + o) : 0.f;
+                rsig[j][i] = sg;
+                rinv[j][i] = 1.0f / sg;
+                rcst[j][i] = lap[j] ? -logf(2.0f * sg) : -logf(sg) - kLogSqrt2Pi;
+            }
+        for (int k = wid; k < p.K; k += nw) {
+            float e[MT][NC];
+#pragma unroll
+            for (int r = 0; r < MT; ++r)
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    const int c = lane + 32 * i;
+                    e[r][i] = c < p.D ? __ldg(p.eps + (((int64_t)r * p.K + k) * p.B + b) * p.D + c) : 0.f;
+                }
+#pragma unroll
+            for (int r = 0; r < MT; ++r) {
+                const int64_t base = (((int64_t)r * p.K + k) * p.B + b) * p.D;
+                float lq[MT], lp = 0.f;
+#pragma unroll
+                for (int j = 0; j < MT; ++j) lq[j] = 0.f;
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    const int c = lane + 32 * i;
+                    if (c < p.D) {
+                        const float zz = rmu[r][i] + eff_noise(e[r][i], lap[r]) * rsig[r][i];
+                        p.z[base + c] = zz;
+#pragma unroll
+                        for (int j = 0; j < MT; ++j) {
+                            const float u = (zz - rmu[j][i]) * rinv[j][i];
+                            lq[j] += (lap[j] ? -fabsf(u) : -0.5f * u * u) + rcst[j][i];
+                        }
+                        const float u0 = (zz - pmu[i]) * pinv[i];
+                        lp += -0.5f * u0 * u0 + pcst[i];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < MT; ++j) {
+                    const float v = warp_sum(lq[j]);
+                    if (lane == 0) p.lq[(((int64_t)r * MT + j) * p.K + k) * p.B + b] = v;
+                }
+                lp = warp_sum(lp);
+                if (lane == 0) p.lpz[((int64_t)r * p.K + k) * p.B + b] = lp;
+            }
+        }
+    }
+}
+
+template <int MT, int NC>
+__global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_bwd_reg_kernel(const MoeParams p) {
+    extern __shared__ float sm[];  // nw x (2*MT*NC + 2*NC) x 32 : per-warp register dumps for the combine
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    constexpr int kAcc = 2 * MT * NC, kPri = 2 * NC, kPer = (kAcc + kPri) * 32;
+    bool lap[MT];
+#pragma unroll
+    for (int j = 0; j < MT; ++j) lap[j] = p.dist[j] == MMVAE_LAPLACE;
+    float pmu[NC], pinv[NC], q_mu[NC], q_s[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const int c = lane + 32 * i;
+        pmu[i] = c < p.D ? __ldg(p.mu0 + c) : 0.f;
+        pinv[i] = 1.0f / (c < p.D ? __ldg(p.s0 + c) : 1.f);
+        q_mu[i] = 0.f;
+        q_s[i] = 0.f;
+    }
+    for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
+        float rmu[MT][NC], rsig[MT][NC], rinv[MT][NC], a_mu[MT][NC], a_s[MT][NC];
+#pragma unroll
+        for (int j = 0; j < MT; ++j)
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const int c = lane + 32 * i;
+                const int64_t o = ((int64_t)j * p.B + b) * p.D + c;
+                const float sg = c < p.D ? __ldg(p.s + o) : 1.f;
+                rmu[j][i] = c < p.D ? __ldg(p.mu + o) : 0.f;
+                rsig[j][i] = sg;
+                rinv[j][i] = 1.0f / sg;
+                a_mu[j][i] = 0.f;
+                a_s[j][i] = 0.f;
+            }
+        for (int k = wid; k < p.K; k += nw) {
+            float e[MT][NC], dzx[MT][NC], cj[MT][MT], cp[MT];
+#pragma unroll
+            for (int r = 0; r < MT; ++r) {
+#pragma unroll
+                for (int j = 0; j < MT; ++j)
+                    cj[r][j] = p.dlq ? __ldg(p.dlq + (((int64_t)r * MT + j) * p.K + k) * p.B + b) : 0.f;
+                cp[r] = p.dlpz ? __ldg(p.dlpz + ((int64_t)r * p.K + k) * p.B + b) : 0.f;
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    const int c = lane + 32 * i;
+                    const int64_t o = (((int64_t)r * p.K + k) * p.B + b) * p.D + c;
+                    e[r][i] = c < p.D ? __ldg(p.eps + o) : 0.f;
+                    dzx[r][i] = (c < p.D && p.dz_ext) ? __ldg(p.dz_ext + o) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < MT; ++r)
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    if (lane + 32 * i < p.D) {
+                        const float ef = eff_noise(e[r][i], lap[r]);
+                        const float zz = rmu[r][i] + ef * rsig[r][i];
+                        float dzt = dzx[r][i], dz_ld = 0.f;
+#pragma unroll
+                        for (int j = 0; j < MT; ++j) {
+                            const float inv = rinv[j][i], df = zz - rmu[j][i];
+                            float dmu_j, ds_j;
+                            if (lap[j]) {
+                                const float sg = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
+                                dmu_j = sg * inv;
+                                ds_j = fabsf(df) * inv * inv - inv;
+                            } else {
+                                dmu_j = df * inv * inv;
+                                ds_j = df * df * inv * inv * inv - inv;
+                            }
+                            a_mu[j][i] += cj[r][j] * dmu_j;
+                            a_s[j][i] += cj[r][j] * ds_j;
+                            dz_ld -= cj[r][j] * dmu_j;
+                        }
+                        {
+                            const float inv = pinv[i], df = zz - pmu[i], dm0 = df * inv * inv;
+                            q_mu[i] += cp[r] * dm0;
+                            q_s[i] += cp[r] * (df * df * inv * inv * inv - inv);
+                            dz_ld -= cp[r] * dm0;
+                        }
+                        if (p.through_z) dzt += dz_ld;
+                        a_mu[r][i] += dzt;
+                        a_s[r][i] += dzt * ef;
+                    }
+                }
+        }
+        // fixed-order cross-warp combine through shared memory (deterministic, no atomics)
+        __syncthreads();
+        float* mine = sm + (size_t)wid * kPer;
+#pragma unroll
+        for (int j = 0; j < MT; ++j)
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                mine[((j * NC + i) * 2 + 0) * 32 + lane] = a_mu[j][i];
+                mine[((j * NC + i) * 2 + 1) * 32 + lane] = a_s[j][i];
+            }
+        __syncthreads();
+        for (int t = threadIdx.x; t < kAcc * 32; t += blockDim.x) {
+            float tot = 0.f;
+            for (int w = 0; w < nw; ++w) tot += sm[(size_t)w * kPer + t];
+            const int ln = t & 31, q = t >> 5, which = q & 1, ji = q >> 1, j = ji / NC, i = ji - j * NC;
+            const int c = ln + 32 * i;
+            if (c < p.D) {
+                const int64_t o = ((int64_t)j * p.B + b) * p.D + c;
+                if (which == 0) p.dmu[o] = tot;
+                else p.ds[o] = tot;
+            }
+        }
+    }
+    __syncthreads();
+    float* mine = sm + (size_t)wid * kPer + kAcc * 32;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        mine[(i * 2 + 0) * 32 + lane] = q_mu[i];
+        mine[(i * 2 + 1) * 32 + lane] = q_s[i];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < kPri * 32; t += blockDim.x) {
+        float tot = 0.f;
+        for (int w = 0; w < nw; ++w) tot += sm[(size_t)w * kPer + kAcc * 32 + t];
+        const int ln = t & 31, q = t >> 5, which = q & 1, i = q >> 1;
+        const int c = ln + 32 * i;
+        if (c < p.D) p.ws[(size_t)blockIdx.x * 2 * p.D + which * p.D + c] = tot;
+    }
+}
+
+typedef void (*moe_kernel_t)(const MoeParams);
+template <bool FWD>
+static moe_kernel_t pick_reg_kernel(int M, int D, int* nc_out) {
+    const int nc = D <= 32 ? 1 : (D <= 64 ? 2 : (D <= 128 ? 4 : 8));
+    *nc_out = nc;
+#define MOE_PICK(MT_, NC_) \
+    if (M == MT_ && nc == NC_) return FWD ? (moe_kernel_t)moe_fwd_reg_kernel<MT_, NC_> : (moe_kernel_t)moe_bwd_reg_kernel<MT_, NC_>;
+    MOE_PICK(1, 1) MOE_PICK(1, 2) MOE_PICK(1, 4) MOE_PICK(1, 8)
+    MOE_PICK(2, 1) MOE_PICK(2, 2) MOE_PICK(2, 4)
+    MOE_PICK(3, 1) MOE_PICK(3, 2)
+    MOE_PICK(4, 1) MOE_PICK(4, 2)
+#undef MOE_PICK
+    return nullptr;
+}
+
 static unsigned moe_grid(int64_t B) {
     const int64_t cap = (int64_t)kNumSMs * 8;
     return (unsigned)(B < cap ? B : cap);
@@ -233,7 +455,15 @@ extern "C" int mmvae_moe_logdens_fwd(const float* mu, const float* s, int M, int
     if (!z || !lq || !lpz) return MMVAE_E_ARG;
     p.z = z; p.lq = lq; p.lpz = lpz;
     const size_t smem = (size_t)(4 * M * D + 3 * D) * sizeof(float);
-    moe_fwd_kernel<<<moe_grid(B), moe_warps(K) * 32, smem, (cudaStream_t)stream>>>(p);
+    int nc = 0;
+    if (moe_kernel_t kr = pick_reg_kernel<true>(M, D, &nc)) {
+        kr<<<moe_grid(B), moe_warps(K) * 32, 0, (cudaStream_t)stream>>>(p);
+        MMVAE_LAUNCH_CHECK();
+        return 0;
+    }
+    auto kf = M == 1 ? moe_fwd_kernel<1> : M == 2 ? moe_fwd_kernel<2> : M == 3 ? moe_fwd_kernel<3>
+                                                                              : M == 4 ? moe_fwd_kernel<4> : moe_fwd_kernel<0>;
+    kf<<<moe_grid(B), moe_warps(K) * 32, smem, (cudaStream_t)stream>>>(p);
     MMVAE_LAUNCH_CHECK();
     return 0;
 }
@@ -255,13 +485,31 @@ extern "C" int mmvae_moe_logdens_bwd(const float* mu, const float* s, int M, int
     const int nw = moe_warps(K);
     const size_t smem = (size_t)(4 * M * D + 2 * D + nw * (2 * M * D + 2 * D)) * sizeof(float);
     if (smem > 200 * 1024) return MMVAE_E_LIMIT;
+    auto kb = M == 1 ? moe_bwd_kernel<1> : M == 2 ? moe_bwd_kernel<2> : M == 3 ? moe_bwd_kernel<3>
+                                                                              : M == 4 ? moe_bwd_kernel<4> : moe_bwd_kernel<0>;
+    int nc = 0;
+    if (moe_kernel_t kr = pick_reg_kernel<false>(M, D, &nc)) {
+        const size_t smem_r = (size_t)nw * (2 * M * nc + 2 * nc) * 32 * sizeof(float);
+        if (smem_r > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute((const void*)kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
+            if (e != cudaSuccess) return (int)e;
+        }
+        const unsigned grid_r = moe_grid(B);
+        kr<<<grid_r, nw * 32, smem_r, (cudaStream_t)stream>>>(p);
+        MMVAE_LAUNCH_CHECK();
+        if (dmu0 && ds0) {
+            partial_sum_kernel<<<2 * D, 128, 0, (cudaStream_t)stream>>>(dprior_ws, (int)grid_r, 2 * D, D, dmu0, ds0);
+            MMVAE_LAUNCH_CHECK();
+        }
+        return 0;
+    }
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(moe_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = moe_grid(B);
-    moe_bwd_kernel<<<grid, nw * 32, smem, st>>>(p);
+    kb<<<grid, nw * 32, smem, st>>>(p);
     MMVAE_LAUNCH_CHECK();
     if (dmu0 && ds0) {
         partial_sum_kernel<<<2 * D, 128, 0, st>>>(dprior_ws, (int)grid, 2 * D, D, dmu0, ds0);
