@@ -43,7 +43,10 @@ enum { MMVAE_F32 = 0, MMVAE_BF16 = 1 };
 /* posterior / likelihood families (reference vae.py:142-147 dist_map) */
 enum { MMVAE_NORMAL = 0, MMVAE_LAPLACE = 1 };
 /* element-wise likelihood terms (reference objectives.py:389-458 ReconLoss.{bce,lprob,mse,l1}) */
-enum { MMVAE_LT_BCE = 0, MMVAE_LT_LPROB_NORMAL = 1, MMVAE_LT_LPROB_LAPLACE = 2, MMVAE_LT_MSE = 3, MMVAE_LT_L1 = 4 };
+enum { MMVAE_LT_BCE = 0, MMVAE_LT_LPROB_NORMAL = 1, MMVAE_LT_LPROB_LAPLACE = 2, MMVAE_LT_MSE = 3, MMVAE_LT_L1 = 4,
+       /* BCE on decoder LOGITS with the reference decoder tail fused in (decoders.py:96-97):
+          x = clamp(sigmoid(y), 1e-6, 1-1e-6); saves one read+write of the (K*B, P) reconstruction per direction */
+       MMVAE_LT_BCE_LOGITS = 5 };
 
 #define MMVAE_MAX_MODS 8    /* modalities per model                       */
 #define MMVAE_MAX_COLS 256  /* latent columns per modality (shared+private) */
@@ -60,6 +63,7 @@ MMVAE_API int mmvae_version(void);
  *     LPROB_NORMAL  Normal(x, scale).log_prob(t), NaN -> 0            (objectives.py:422-423)
  *     LPROB_LAPLACE Laplace(x, scale).log_prob(t), NaN -> 0
  *     MSE           -(x-t)^2          L1   -|x-t|
+ *     BCE_LOGITS    BCE of clamp(sigmoid(recon), 1e-6, 1-1e-6): recon holds logits, gradient is w.r.t. the logits
  *
  * _fwd   : reads recon + target, writes out_rows.                                   bytes: R + T
  * _bwd   : grad[r,p] = w_rows[r] * lam * dlogp/dx                                  bytes: 2R + T (+rows)

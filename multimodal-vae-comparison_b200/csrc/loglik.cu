@@ -47,7 +47,8 @@ __device__ __forceinline__ float lg2_ftz(float x) {
 template <int LT>
 struct LogP {
     // the accumulated values are multiplied by this once per row (BCE accumulates in log2 units)
-    static constexpr float kValueScale = (LT == MMVAE_LT_BCE) ? 0.69314718055994530942f : 1.0f;
+    static constexpr float kValueScale =
+        (LT == MMVAE_LT_BCE || LT == MMVAE_LT_BCE_LOGITS) ? 0.69314718055994530942f : 1.0f;
     float c_inv, c_const;  // family specific constants
     __device__ __forceinline__ explicit LogP(float scale) {
         if (LT == MMVAE_LT_LPROB_NORMAL) {
@@ -84,6 +85,29 @@ struct LogP {
                 v = fmaf(t, l0 - l1, l1);
             }
             if (NEED_D) d = __fdividef(t - x, fmaxf((1.0f - x) * x, 1e-12f));
+        } else if (LT == MMVAE_LT_BCE_LOGITS) {
+            // x holds the decoder logit y.  s = sigmoid(y), xc = clamp(s, lo, hi) with lo = fp32(1e-6), hi = fp32(1-1e-6)
+            // (reference decoders.py:96-97), value = t log xc + (1-t) log(1-xc).  log is monotonic, so the clamp moves
+            // onto the logs: log2 s = -log2(1+e) - max(-y,0) log2(e), log2(1-s) = -log2(1+e) - max(y,0) log2(e),
+            // e = exp(-|y|): one EX2 + one LG2 per element instead of a sigmoid pass plus two logs.
+            const float kL2E = 1.44269504088896340736f;
+            const float e = exp2f(-fabsf(x) * kL2E);
+            if (NEED_V) {
+                const float l1pe = lg2_ftz(1.0f + e);
+                const float yl = x * kL2E;
+                // bounds: log2(lo), log2(hi) for xc and log2(1-hi), log2(1-lo) for 1-xc, all with fp32 operands
+                // lo = fp32(1e-6) = 9.99999997e-07, hi = fp32(1-1e-6) = 0.999998987, 1-hi = 1.0132789e-06, 1-lo = hi
+                const float l0 = fminf(fmaxf(-l1pe - fmaxf(-yl, 0.f), -19.93156857296663f), -1.4618532729665813e-06f);
+                const float l1 = fminf(fmaxf(-l1pe - fmaxf(yl, 0.f), -19.91253715874966f), -1.4618532729665813e-06f);
+                v = fmaf(t, l0 - l1, l1);
+            }
+            if (NEED_D) {
+                const float r = __fdividef(1.0f, 1.0f + e);
+                const float sg = x >= 0.f ? r : e * r;
+                // clamp passes the gradient only inside [lo, hi]; there x(1-x) >= 1e-6 >> 1e-12, so
+                // (t-x)/max((1-x)x,1e-12) * s(1-s) = t - s
+                d = (sg >= 9.99999997e-07f && sg <= 0.999998987f) ? (t - sg) : 0.f;
+            }
         } else if (LT == MMVAE_LT_LPROB_NORMAL) {
             const float df = t - x;
             const float lp = -df * df * c_inv + c_const;
@@ -187,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, Tune<MODE>::kMinBlocks) loglik_kerne
             if (NEED_V) acc += v;
             if (NEED_D) gv[e] = wl * d;
         }
-        if (LT == MMVAE_LT_BCE && NEED_V) {
+        if (LT == MMVAE_LT_BCE && NEED_V) {  // (not needed for BCE_LOGITS: 1+e is never sub-normal)
             // vector-level guard for sub-normal reconstructions (never taken for decoder outputs, which the
             // reference clamps to [1e-6, 1-1e-6]): redo those elements exactly
             float mn = xv[0];
@@ -323,6 +347,7 @@ static int launch2(const LoglikParams& p, int ltype, bool vect, cudaStream_t st)
         case MMVAE_LT_LPROB_LAPLACE: return launch3<TX, TT, MMVAE_LT_LPROB_LAPLACE, MODE>(p, vect, st);
         case MMVAE_LT_MSE: return launch3<TX, TT, MMVAE_LT_MSE, MODE>(p, vect, st);
         case MMVAE_LT_L1: return launch3<TX, TT, MMVAE_LT_L1, MODE>(p, vect, st);
+        case MMVAE_LT_BCE_LOGITS: return launch3<TX, TT, MMVAE_LT_BCE_LOGITS, MODE>(p, vect, st);
         default: return MMVAE_E_ENUM;
     }
 }

@@ -10,7 +10,7 @@ import torch
 
 from . import ops
 
-ELEMENTWISE = ("bce", "lprob", "mse", "l1")
+ELEMENTWISE = ("bce", "lprob", "mse", "l1", "bce_logits")
 
 
 class ReconLoss:
@@ -31,6 +31,12 @@ class ReconLoss:
     @staticmethod
     def bce(loc, target, lam=1.0, likelihood="normal"):
         return ReconLoss._rows("bce", loc, target, lam, likelihood)
+
+    @staticmethod
+    def bce_logits(loc, target, lam=1.0, likelihood="normal"):
+        """Not in the reference: ``bce`` for decoders that hand over LOGITS, with the reference decoder tail
+        ``sigmoid(.).clamp(1e-6, 1-1e-6)`` (decoders.py:96-97) fused into the kernel."""
+        return ReconLoss._rows("bce_logits", loc, target, lam, likelihood)
 
     @staticmethod
     def lprob(loc, target, lam=1.0, likelihood="normal"):

@@ -60,7 +60,7 @@ def _rows2d(t: torch.Tensor, rows: int):
     return t2, t2.shape[1], t2.stride(0)
 
 
-LTYPES = {"bce": _lib.LT_BCE, "mse": _lib.LT_MSE, "l1": _lib.LT_L1}
+LTYPES = {"bce": _lib.LT_BCE, "mse": _lib.LT_MSE, "l1": _lib.LT_L1, "bce_logits": _lib.LT_BCE_LOGITS}
 
 
 def ltype_code(ltype: str, likelihood: str) -> int:

@@ -198,7 +198,10 @@ def recon_logp(ltype, loc, target, K=1, likelihood="normal", scale=0.75, mask_le
     # reference: target.float(); the cast follows loc so that the restatement can also be evaluated in fp64
     target = reshape_target(loc, target.to(loc.dtype), K)
     bs = target.shape[0]
-    if ltype == "bce":  # objectives.py:391-406
+    if ltype == "bce_logits":  # decoder tail decoders.py:96-97 (sigmoid + clamp(eta, 1-eta)) followed by bce
+        xs = torch.sigmoid(loc).clamp(1e-6, 1 - 1e-6)
+        loss = F.binary_cross_entropy(xs, target.detach(), reduction="none").reshape(bs, -1)
+    elif ltype == "bce":  # objectives.py:391-406
         loss = F.binary_cross_entropy(loc, target.detach(), reduction="none").reshape(bs, -1)
     elif ltype == "lprob":  # objectives.py:408-424 (fp64 accumulate, NaN -> 0)
         sc = torch.as_tensor(scale, dtype=loc.dtype, device=loc.device)

@@ -471,3 +471,32 @@ def test_loglik_l2_tiled_row_order(ops):
     (out * w.cuda()).sum().backward()
     assert rel(out, ref) < FP32_TOL
     assert rel(xc.grad, xo.grad) < FP32_TOL
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+def test_bce_logits_fused_decoder_tail(ops, dtype, tol):
+    """bce_logits == bce(clamp(sigmoid(y), 1e-6, 1-1e-6)) including the clamp's gradient mask (decoders.py:96-97)."""
+    g = torch.Generator().manual_seed(17)
+    K, B, shape = 2, 5, (3, 16, 16)
+    y = (torch.randn(K * B, *shape, generator=g) * 4)
+    y.view(-1)[:8] = torch.tensor([-30.0, 30.0, -13.9, 13.9, -13.7, 13.7, 0.0, -0.0])  # both sides of the clamp
+    y = y.to(dtype)
+    t = torch.rand(B, *shape, generator=g)
+    w = torch.randn(K * B, generator=g)
+    # The reference formulation log(1 - sigmoid(y)) cancels catastrophically in fp32 for saturated logits (up to 1e-4
+    # absolute per element); the fused kernel evaluates log(1-s) directly.  So the check is against the oracle in
+    # fp64, and the fp32 oracle must itself be within its own error band of the kernel.
+    yo = y.double().requires_grad_(True)
+    ref = refmath.lpx_rows("bce_logits", yo, t.double(), 0.8, K)
+    (ref * w.double()).sum().backward()
+    ref32 = refmath.lpx_rows("bce_logits", y.float(), t, 0.8, K)
+    yc = y.cuda().requires_grad_(True)
+    out = ops.loglik_rows(yc, t.cuda(), "bce_logits", "normal", 0.8)
+    (out * w.cuda()).sum().backward()
+    assert rel(out, ref) < (1e-5 if dtype == torch.float32 else 1e-4)
+    assert rel(out, ref32) < 1e-4 and rel(out, ref) <= rel(ref32, ref) + 1e-6  # at least as close to the truth
+    assert rel(yc.grad, yo.grad) < tol
+    yc2 = y.cuda().requires_grad_(True)
+    S, _ = ops.loglik_weighted_sum(yc2, t.cuda(), "bce_logits", "normal", 0.8, w_rows=w.cuda())
+    S.backward()
+    assert rel(yc2.grad, yo.grad) < tol
