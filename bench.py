@@ -180,7 +180,7 @@ def cpu_baseline(args):
                 args.cpu_batch, args.workload, cfg["K"], n, dt)}
 
 
-def plugin_e2e(cfg, B, dev, steps):
+def plugin_e2e(cfg, B, dev, steps, fused_tail=False):
     import math
     import torch
     import mmvae_b200
@@ -192,7 +192,7 @@ def plugin_e2e(cfg, B, dev, steps):
         name = "mod_%d" % (i + 1)
         dz = cfg["D"] + (pv or 0)
         enc = syn.LinearEncoder(m["data_dim"], dz)
-        dec = syn.LinearDecoder(dz, m["data_dim"], squash=(m["ltype"] == "bce"))
+        dec = syn.LinearDecoder(dz, m["data_dim"], squash=(m["ltype"] == "bce"), returns_logits=fused_tail)
         vaes[name] = syn.StubVAE(enc, dec, cfg["D"], m["ltype"], private_latents=pv, llik_scaling=m["lam"],
                                  prior_dist=m["dist"], id_name=name)
         host[name] = syn.make_target(g, m["target"], B, m["data_dim"]).pin_memory()
@@ -220,7 +220,8 @@ def plugin_e2e(cfg, B, dev, steps):
     return {"value": B * steps / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms / steps, "steps": steps,
             "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()), "d2h_bytes_per_step": 4,
             "api": "mmvae_b200.%s(vaes, ...).objective(batch) + backward, linear stand-in encoders/decoders (torch), "
-                   "eager launches" % cfg["model"]}
+                   "eager launches%s" % (cfg["model"], "; decoder tail sigmoid+clamp fused into the likelihood kernel "
+                                         "(bce_logits)" if fused_tail else "")}
 
 
 def main():
@@ -370,6 +371,8 @@ def main():
     if not args.no_e2e and world == 1:
         try:
             e2e_plugin = plugin_e2e(cfg, B, dev, max(3, min(K_, 10)))
+            if any(m["ltype"] == "bce" for m in cfg["mods"]):
+                e2e_plugin["fused_decoder_tail"] = plugin_e2e(cfg, B, dev, max(3, min(K_, 10)), fused_tail=True)
         except Exception as ex:  # never let the extra leg hide the main numbers
             e2e_plugin = {"error": repr(ex)[:200]}
 

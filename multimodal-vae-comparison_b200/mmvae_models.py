@@ -89,6 +89,15 @@ def _first(t):
     return t[0] if isinstance(t, (tuple, list)) else t
 
 
+def _ltype(vae):
+    """Likelihood the kernels evaluate for this VAE.  A decoder that declares ``returns_logits = True`` hands over
+    pre-sigmoid logits; its ``bce`` is then evaluated by the fused ``bce_logits`` kernel, which folds the reference
+    decoder tail sigmoid(.).clamp(1e-6, 1-1e-6) (decoders.py:96-97) into the row reduction."""
+    if vae.ltype == "bce" and getattr(vae.dec, "returns_logits", False):
+        return "bce_logits"
+    return vae.ltype
+
+
 # ----------------------------------------------------------------------------------------------------------
 class MOE(TorchMMVAE):
     """MMVAE, mixture of experts (reference mmvae_models.py:10-131)."""
@@ -134,7 +143,7 @@ class MOE(TorchMMVAE):
                 loc = _first(vae.dec({"latents": z[r], "masks": data[name]["masks"]}))
                 # self reconstruction: always a Normal likelihood (dist.Normal(*px_z), :105-107)
                 S_self, rows_self = self.obj_fn.lpx_weighted_sum(loc, data[name], vae.llik_scaling, w_const=-1.0 / M,
-                                                                 family="normal")
+                                                                 ltype=_ltype(vae), family="normal")
                 total = total + S_self
                 n_keep = n_keep + (S_self != 0).float()
                 rows_log.append(rows_self)
@@ -145,7 +154,7 @@ class MOE(TorchMMVAE):
                 lwt = lq[src, r, 0] - lq[src, src, 0].detach()  # sum_d log q_r(z_s) - log q_s(z_s)   (:56-59)
                 iw = lwt.exp()
                 S_cross, rows_cross = self.obj_fn.lpx_weighted_sum(loc, data[name], vae.llik_scaling,
-                                                                   w_rows=-iw / M, family=_family(vae))
+                                                                   w_rows=-iw / M, ltype=_ltype(vae), family=_family(vae))
                 total = total + S_cross
                 n_keep = n_keep + (S_cross != 0).float()  # rows summing to exactly 0 are dropped (:73)
                 rows_log.append(iw.detach() * rows_cross)
@@ -159,11 +168,11 @@ class MOE(TorchMMVAE):
             vae = self.vaes[name]
             self.obj_fn.set_ltype(vae.ltype)
             terms = [self.obj_fn.lpx_rows(_first(vae.dec({"latents": z[r], "masks": data[name]["masks"]})), data[name],
-                                          vae.llik_scaling, family="normal")]
+                                          vae.llik_scaling, ltype=_ltype(vae), family="normal")]
             src = self._cross_source(M, r)
             if src is not None:
                 terms.append(self.obj_fn.lpx_rows(_first(vae.dec({"latents": z[src], "masks": data[name]["masks"]})),
-                                                  data[name], vae.llik_scaling, family=_family(vae)))
+                                                  data[name], vae.llik_scaling, ltype=_ltype(vae), family=_family(vae)))
             lpx.append(torch.stack(terms))
         lpx = torch.stack(lpx).view(M, -1, K, B)
         return self.obj_fn.calculate_loss({"lpz": lpz, "lq": lq, "lpx_z": lpx})
@@ -233,7 +242,7 @@ class POE(TorchMMVAE):
                 masks = mods[name]["masks"] if i in sub else None
                 loc = _first(vae.dec({"latents": z, "masks": masks}))
                 S, rows = self.obj_fn.lpx_weighted_sum(loc, mods[name], vae.llik_scaling, w_const=-1.0,
-                                                       family=_family(vae))
+                                                       ltype=_ltype(vae), family=_family(vae))
                 total = total + S
                 if i == a:  # logging quirk: "mod == 'mod_{m+1}'" with m the subset index (:179-180)
                     rec_log[i] = -ops.reduce_sum(rows) / vae.llik_scaling
@@ -338,7 +347,7 @@ class MoPOE(TorchMMVAE):
             self.obj_fn.set_ltype(vae.ltype)
             loc = _first(vae.dec({"latents": res[i]["z"], "masks": mods[name]["masks"]}))
             S, rows = self.obj_fn.lpx_weighted_sum(loc, mods[name], vae.llik_scaling, w_const=-1.0 / Bt,
-                                                   family=_family(vae))
+                                                   ltype=_ltype(vae), family=_family(vae))
             total = total + S
             ind.append(-rows / vae.llik_scaling)
         kl_all = torch.stack([res[0]["kl"]] + [res[M + i]["kl"] for i in range(M)])  # joint + unimodal, (M+1,B)
@@ -446,7 +455,7 @@ class DMVAE(TorchMMVAE):
 
             def term(z_a):
                 loc = _first(vae.dec({"latents": torch.cat([z_a, z_pr], -1), "masks": masks}))
-                return self.obj_fn.lpx_weighted_sum(loc, mods[name], lam, w_const=-1.0, family=fam)
+                return self.obj_fn.lpx_weighted_sum(loc, mods[name], lam, w_const=-1.0, ltype=_ltype(vae), family=fam)
 
             S1, rows1 = term(z_sh)
             S2, _ = term(z_joint)

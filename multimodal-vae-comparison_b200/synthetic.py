@@ -49,16 +49,18 @@ class LinearDecoder(nn.Module):
     """latents (K,B,Dz) -> Linear -> optional sigmoid+clamp (reference decoders.py:96-98) -> rows K*B
     (the CNN/FNN k-major convention).  Returns (mean, 0.75) like every reference decoder."""
 
-    def __init__(self, in_dim, data_dim, squash):
+    def __init__(self, in_dim, data_dim, squash, returns_logits=False):
         super().__init__()
         self.data_dim = tuple(data_dim)
         self.lin = nn.Linear(in_dim, int(math.prod(self.data_dim)))
         self.squash = squash
+        # True: hand the pre-sigmoid logits to the likelihood kernel, which applies the tail itself (bce_logits)
+        self.returns_logits = bool(returns_logits and squash)
 
     def forward(self, z):
         z = z["latents"]
         d = self.lin(z)
-        if self.squash:
+        if self.squash and not self.returns_logits:
             d = torch.sigmoid(d).clamp(ETA, 1 - ETA)
         return d.reshape(-1, *self.data_dim), torch.tensor(0.75, device=d.device)
 

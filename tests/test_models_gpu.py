@@ -107,3 +107,30 @@ def test_state_dict_keys_match_reference_layout():
     keys = set(model.state_dict().keys())
     assert {"_pz_params.0", "_pz_params.1"} <= keys
     assert any(k.startswith("vaes.mod_1.") for k in keys)
+
+
+def test_fused_decoder_tail_matches_torch_tail():
+    """A decoder that returns logits (returns_logits=True) + the bce_logits kernel gives the same objective and
+    gradients as the torch tail sigmoid+clamp followed by bce (fp64-accurate comparison: tolerance 2e-5)."""
+    import mmvae_b200
+    for case in cases.case_list():
+        if case["name"] not in ("poe_elbo_m2", "moe_iwae_m2", "dmvae_elbo_m2"):
+            continue
+        outs = []
+        for fused in (False, True):
+            vaes = cases.build_vaes(case, "cuda")
+            for v in vaes.values():
+                if v.dec.squash:
+                    v.dec.returns_logits = fused
+            model = mmvae_b200.MODEL_REGISTRY[case["model"]](
+                vaes, case["D"], {"obj": case["obj"], "beta": case["beta"], "K": case["K"]}, None).cuda()
+            src, _ = _noise_queue(case)
+            model.noise_source = src
+            out = model.objective(cases.build_batch(case, "cuda"))
+            out["loss"].backward()
+            outs.append(cases.collect(out, cases.named_leaves(vaes, model._pz_params[1])))
+        for k, x in outs[0].items():
+            y = outs[1][k]
+            if x is None or y is None or k == "reconstruction_loss":
+                continue
+            assert _rel(y, x) < 2e-5, (case["name"], k, _rel(y, x))
