@@ -50,14 +50,18 @@ def make_case(name, seed, model, obj, B, D, mods, K=1, beta=1.0, private=None, p
         privs.append(pv)
         dz = D + pv
         mu, s = syn.make_posterior(g, B, dz)
-        P = int(math.prod(spec["data_dim"]))
+        # dec_dim: what the decoder emits; with padding masks the target (and the mask) is shorter along dim 1 and
+        # recon_loss_fn crops the decoder output (objectives.py:43-45)
+        dec_dim = tuple(spec.get("dec_dim", spec["data_dim"]))
+        P = int(math.prod(dec_dim))
         squash = spec["ltype"] in ("bce",)
         W = torch.randn(P, dz, generator=g) * (0.5 / math.sqrt(dz))
         b = torch.randn(P, generator=g) * 0.1
         target = syn.make_target(g, spec.get("target", "uniform"), B, spec["data_dim"])
-        case["mods"].append(dict(data_dim=tuple(spec["data_dim"]), ltype=spec["ltype"], dist=spec.get("dist", "normal"),
+        mask_len = spec["data_dim"][0] if "dec_dim" in spec else None
+        case["mods"].append(dict(data_dim=dec_dim, ltype=spec["ltype"], dist=spec.get("dist", "normal"),
                                  lam=float(spec.get("lam", 1.0)), mu=mu, s=s, W=W, b=b, target=target,
-                                 squash=squash, mask_len=spec.get("mask_len")))
+                                 squash=squash, mask_len=mask_len))
     case["pz_logits"] = torch.randn(1, D, generator=g) * pz_logits_std
     plan = noise_plan(model, M, K, B, D, privs, [m["dist"] for m in case["mods"]])
     case["noise"] = [syn.make_noise(g, kind, shape) for kind, shape in plan]
@@ -100,7 +104,10 @@ class KeepK(torch.nn.Module):
 
 def build_batch(case, device="cpu"):
     """Batch dict format of reference dataloader.py:85-120."""
-    return {"mod_%d" % (i + 1): {"data": m["target"].to(device), "masks": None, "categorical": False}
+    return {"mod_%d" % (i + 1): {"data": m["target"].to(device),
+                                 "masks": None if m.get("mask_len") is None else
+                                 torch.ones(m["target"].shape[0], m["mask_len"], dtype=torch.bool, device=device),
+                                 "categorical": False}
             for i, m in enumerate(case["mods"])}
 
 
@@ -168,6 +175,7 @@ OSG = dict(data_dim=(3, 4, 4), ltype="optimal_sigma", target="uniform")
 LAP_A = dict(data_dim=(1, 7, 7), ltype="lprob", target="uniform", dist="laplace", lam=1.0)
 LAP_B = dict(data_dim=(3, 6, 6), ltype="lprob", target="uniform", dist="laplace", lam=49.0 / 108.0)
 NRM_A = dict(data_dim=(1, 7, 7), ltype="lprob", target="uniform", dist="normal", lam=1.0)
+TXT_MASKED = dict(data_dim=(5, 27), dec_dim=(8, 27), ltype="category_ce", target="onehot")  # decoder pads to T=8
 
 
 def case_list():
@@ -186,4 +194,7 @@ def case_list():
     c.append(make_case("mopoe_elbo_osigma", 303, "mopoe", "elbo", B=9, D=5, mods=[OSG, MSE, L1]))
     c.append(make_case("dmvae_elbo_m2", 401, "dmvae", "elbo", B=6, D=4, private=3, mods=[IMG, TXT]))
     c.append(make_case("dmvae_elbo_m3", 402, "dmvae", "elbo", B=5, D=4, private=2, mods=[IMG, ACT, ATT], beta=1.3))
+    c.append(make_case("poe_elbo_masks", 501, "poe", "elbo", B=6, D=4, mods=[IMG, TXT_MASKED]))
+    c.append(make_case("moe_iwae_masks", 502, "moe", "iwae", B=4, D=4, K=3, mods=[IMG, TXT_MASKED]))
+    c.append(make_case("mopoe_elbo_masks", 503, "mopoe", "elbo", B=7, D=6, mods=[TXT_MASKED, IMG, ACT]))
     return c

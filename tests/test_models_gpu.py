@@ -47,7 +47,7 @@ def run_dropin(case, device="cuda"):
     return cases.collect(out, cases.named_leaves(vaes, model._pz_params[1])), out
 
 
-@pytest.mark.parametrize("idx", range(14))
+@pytest.mark.parametrize("idx", range(17))
 def test_dropin_matches_reference_golden(golden, idx):
     entry = golden["cases"][idx]
     case, ref = entry["case"], entry["reference"]
@@ -134,3 +134,69 @@ def test_fused_decoder_tail_matches_torch_tail():
             if x is None or y is None or k == "reconstruction_loss":
                 continue
             assert _rel(y, x) < 2e-5, (case["name"], k, _rel(y, x))
+
+
+def test_forward_with_missing_modality_uses_present_experts():
+    """forward() at evaluation time with a missing modality ("data": None, reference mmvae_base.py:150-158): the PoE
+    joint is the product of the PRESENT experts and the prior; MoPoE falls back to the available subsets."""
+    import mmvae_b200
+    from oracle import refmath
+    case = [c for c in cases.case_list() if c["name"] == "poe_elbo_m3"][0]
+    batch = cases.build_batch(case, "cuda")
+    batch["mod_2"] = {"data": None, "masks": None, "categorical": False}
+    mods = [dict(mu=m["mu"], s=m["s"]) for m in case["mods"]]
+    B, D = case["B"], case["D"]
+    # POE
+    model = mmvae_b200.poe(cases.build_vaes(case, "cuda"), D, {"obj": "elbo", "beta": 1.0, "K": 1}, None).cuda()
+    out = model.forward(batch, K=2)
+    joint = out.mods["mod_1"].joint_dist
+    mu_ref, var_ref = refmath.poe_mixing(mods, {0, 2}, B, D)
+    assert _rel(joint.loc, mu_ref) < TOL and _rel(joint.scale, var_ref) < TOL
+    assert out.mods["mod_2"].decoder_dist.loc.shape[0] == 2 * B  # the missing modality is still reconstructed
+    assert out.mods["mod_1"].latent_samples["latents"].shape == (2, B, D)
+    # MoPoE: subsets without mod_2 -> (mod_1), (mod_3), (mod_1, mod_3); the joint is the last available one, no prior
+    model = mmvae_b200.mopoe(cases.build_vaes(case, "cuda"), D, {"obj": "elbo", "beta": 1.0, "K": 1}, None).cuda()
+    lat = model.modality_mixing(batch)
+    assert list(lat["subsets"].keys()) == ["mod_1", "mod_3", "mod_1_mod_3"]
+    mu_ref, var_ref = refmath.product_of_experts(torch.stack([mods[0]["mu"], mods[2]["mu"]]),
+                                                 torch.stack([mods[0]["s"], mods[2]["s"]]))
+    assert _rel(lat["joint"][0], mu_ref) < TOL and _rel(lat["joint"][1], var_ref) < TOL
+    # MOE: missing modality is decoded from the first present one's samples
+    model = mmvae_b200.moe(cases.build_vaes(case, "cuda"), D, {"obj": "elbo", "beta": 1.0, "K": 1}, None).cuda()
+    out = model.forward(batch, K=3)
+    assert out.mods["mod_2"].encoder_dist is None
+    assert torch.equal(out.mods["mod_2"].latent_samples["latents"], out.mods["mod_1"].latent_samples["latents"])
+
+
+def test_limits_raise_instead_of_falling_back():
+    import mmvae_b200.ops as ops
+    mu = torch.zeros(2, 4, 300, device="cuda")
+    with pytest.raises(RuntimeError, match="size limit"):
+        ops.latent_draws(mu, torch.ones_like(mu), None, None, None, [ops.Draw(mods=(0, 1), width=300, want_params=True)])
+    with pytest.raises(RuntimeError, match="size limit"):
+        ops.moe_logdens(mu, torch.ones_like(mu), torch.zeros(1, 300, device="cuda"), torch.ones(1, 300, device="cuda"),
+                        torch.zeros(2, 1, 4, 300, device="cuda"), [0, 0])
+    with pytest.raises(RuntimeError):
+        ops.loglik_rows(torch.rand(4, 8, device="cuda", dtype=torch.float64), torch.rand(4, 8, device="cuda"), "bce")
+
+
+def test_bf16_encoder_outputs_are_accepted():
+    """Config 5 runs under bf16 autocast: encoder outputs arrive in bf16, kernels accumulate in fp32, gradients return
+    in the producer's dtype."""
+    import mmvae_b200
+    case = [c for c in cases.case_list() if c["name"] == "dmvae_elbo_m2"][0]
+    ref, _ = run_dropin(case)
+    vaes = cases.build_vaes(case, "cuda")
+    for v in vaes.values():
+        v.enc.mu.data = v.enc.mu.data.to(torch.bfloat16)
+        v.enc.s.data = v.enc.s.data.to(torch.bfloat16)
+    model = mmvae_b200.dmvae(vaes, case["D"], {"obj": "elbo", "beta": case["beta"], "K": 1}, None).cuda()
+    with torch.no_grad():
+        model._pz_params[1].copy_(case["pz_logits"])
+    src, _ = _noise_queue(case)
+    model.noise_source = src
+    out = model.objective(cases.build_batch(case, "cuda"))
+    out["loss"].backward()
+    assert vaes["mod_1"].enc.mu.grad.dtype == torch.bfloat16
+    assert _rel(out["loss"], ref["loss"]) < 2e-2
+    assert _rel(vaes["mod_1"].enc.mu.grad, ref["grad.mod_1.mu"]) < 3e-2
