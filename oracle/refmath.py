@@ -199,7 +199,10 @@ def recon_logp(ltype, loc, target, K=1, likelihood="normal", scale=0.75, mask_le
     target = reshape_target(loc, target.to(loc.dtype), K)
     bs = target.shape[0]
     if ltype == "bce_logits":  # decoder tail decoders.py:96-97 (sigmoid + clamp(eta, 1-eta)) followed by bce
-        xs = torch.sigmoid(loc).clamp(1e-6, 1 - 1e-6)
+        # clamp bounds as the fp32 reference sees them (fp32(1e-6), fp32(1-1e-6)), also when evaluated in fp64
+        lo = float(torch.tensor(1e-6, dtype=torch.float32))
+        hi = float(torch.tensor(1 - 1e-6, dtype=torch.float32))
+        xs = torch.sigmoid(loc).clamp(lo, hi)
         loss = F.binary_cross_entropy(xs, target.detach(), reduction="none").reshape(bs, -1)
     elif ltype == "bce":  # objectives.py:391-406
         loss = F.binary_cross_entropy(loc, target.detach(), reduction="none").reshape(bs, -1)

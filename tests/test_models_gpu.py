@@ -20,8 +20,8 @@ def _noise_queue(case):
     import mmvae_b200.mmvae_models as mm
     noise = list(case["noise"])
     if case["model"] == "poe":  # the golden file records the subset order the reference run used
-        ref_order = [tuple(s) for s in case["poe_subsets"]]
         mine = mm.poe_subsets(range(len(case["mods"])))
+        ref_order = [tuple(s) for s in case.get("poe_subsets", mine)]
         noise = [noise[ref_order.index(tuple(s))] for s in mine]
     q = [n.clone() for n in noise]
 
