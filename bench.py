@@ -113,6 +113,15 @@ class KernelTimer:
         b.record()
         # loglik entry points: (recon, ld, dtype, target, ld, dtype, rows, B, P, ...) -> algorithmic bytes
         nb = None
+        if name.startswith("mmvae_moe_logdens") and len(args) > 10:
+            # (mu, s, M, B, D, K, dists, mu0, s0, eps, ...): fwd reads eps + writes z; bwd reads eps (+ dz_ext)
+            M, B, D, K = args[2], args[3], args[4], args[5]
+            big, rows = M * K * B * D * 4, (M * M + M) * K * B * 4
+            if name.endswith("_fwd"):
+                nb = 2 * big + rows + 2 * M * B * D * 4
+            else:
+                has_dz = bool(getattr(args[10], "value", args[10]))
+                nb = big * (2 if has_dz else 1) + rows + 4 * M * B * D * 4
         if name.startswith("mmvae_loglik_rowreduce") and len(args) > 8:
             ex, et, rows, B, P = (2 if args[2] else 4), (2 if args[5] else 4), args[6], args[7], args[8]
             R, T = rows * P * ex, B * P * et
@@ -304,7 +313,9 @@ def main():
 
     # roofline of the dominant kernel: CUDA events around every launch of it, eager steps, same inputs
     dom = "mmvae_loglik_rowreduce_bwd" if cfg["obj"] != "elbo" else "mmvae_loglik_rowreduce_fused"
-    kt = KernelTimer([dom, "mmvae_loglik_rowreduce_fwd"])
+    if cfg.get("latent_only"):
+        dom = "mmvae_moe_logdens_fwd"
+    kt = KernelTimer([dom, "mmvae_loglik_rowreduce_fwd", "mmvae_moe_logdens_bwd"])
     L.timer = kt
     for _ in range(min(K_, 10)):
         step.run()
@@ -330,6 +341,11 @@ def main():
     if fms:
         roofline["fwd_kernel"] = {"achieved": fb / (statistics.mean(fms) * 1e-3) / 1e9, "bytes_per_launch": fb,
                                   "avg_ms": statistics.mean(fms)}
+    bms, bb = kt.biggest("mmvae_moe_logdens_bwd")
+    bms = bms[len(bms) // 5:] if len(bms) >= 5 else bms
+    if bms and cfg.get("latent_only"):
+        roofline["moe_bwd_kernel"] = {"achieved": bb / (statistics.mean(bms) * 1e-3) / 1e9, "bytes_per_launch": bb,
+                                      "avg_ms": statistics.mean(bms)}
     step_bytes = W.algorithmic_bytes(cfg, rdt) * B
     roofline["step"] = {"algorithmic_bytes": step_bytes, "achieved": step_bytes * K_ / (ms * 1e-3) / 1e9,
                         "frac": step_bytes * K_ / (ms * 1e-3) / 1e9 / peak}

@@ -179,6 +179,11 @@ WORKLOADS = {
     "c4_moe_dreg_mnistsvhn": dict(model="moe", obj="dreg", K=50, D=64, B=1024, mods=[
         dict(data_dim=(1, 28, 28), ltype="lprob", target="uniform", dist="laplace", lam=1.0),
         dict(data_dim=(3, 32, 32), ltype="lprob", target="uniform", dist="laplace", lam=784.0 / 3072.0)]),
+    # C4 latent + combine only: same latent path, the four likelihood row vectors are synthetic (K*B,)
+    # leaves, so that batches up to 64k fit one GPU; bytes/sample = 4*K*D*4 per drawn tensor + row scalars
+    "c4_moe_dreg_latent_only": dict(model="moe", obj="dreg", K=50, D=64, B=16384, latent_only=True, mods=[
+        dict(data_dim=(1, 28, 28), ltype="lprob", target="uniform", dist="laplace", lam=1.0),
+        dict(data_dim=(3, 32, 32), ltype="lprob", target="uniform", dist="laplace", lam=784.0 / 3072.0)]),
     # C5: DMVAE ELBO, CUB shapes (bf16 in the bench)
     "c5_dmvae_elbo_cub": dict(model="dmvae", obj="elbo", K=1, D=16, private=10, B=256, mods=[
         dict(data_dim=(3, 64, 64), ltype="bce", target="uniform", dist="normal", lam=1.0),

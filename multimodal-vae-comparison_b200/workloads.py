@@ -68,8 +68,12 @@ def make_leaves(name, B=None, seed=1234, recon_dtype=torch.float32):
          "pz_logits": torch.zeros(1, D)}
     t["targets"] = [syn.make_target(g, m["target"], B, m["data_dim"]) for m in cfg["mods"]]
     Kr = K if cfg["model"] == "moe" else 1
-    t["recon"] = [syn.make_recon(g, cfg["mods"][tm]["ltype"], Kr * B, cfg["mods"][tm]["data_dim"]).to(recon_dtype)
-                  for tm, _ in term_plan(cfg["model"], M)]
+    if cfg.get("latent_only"):
+        # synthetic likelihood ROWS (one value per decoder row) instead of reconstructions
+        t["recon"] = [-(torch.rand(Kr * B, generator=g) * 50 + 500) for _ in term_plan(cfg["model"], M)]
+    else:
+        t["recon"] = [syn.make_recon(g, cfg["mods"][tm]["ltype"], Kr * B, cfg["mods"][tm]["data_dim"]).to(recon_dtype)
+                      for tm, _ in term_plan(cfg["model"], M)]
     t["noise"] = [syn.make_noise(g, kind, shape)
                   for kind, shape in _noise_plan(cfg["model"], M, K, B, D, pv, [m["dist"] for m in cfg["mods"]])]
     return cfg, t
@@ -84,6 +88,9 @@ def algorithmic_bytes(cfg, recon_dtype=torch.float32):
     Kr = K if cfg["model"] == "moe" else 1
     tot = 0
     for tm, _ in term_plan(cfg["model"], M):
+        if cfg.get("latent_only"):
+            tot += 2 * Kr * 4  # the row value read, its gradient written
+            continue
         P = int(math.prod(cfg["mods"][tm]["data_dim"]))
         R, T = Kr * P * e, P * 4
         tot += (2 * R + T) if cfg["obj"] == "elbo" else (3 * R + 2 * T)
@@ -136,6 +143,8 @@ class LeafStep:
         return "normal" if (self.model == "moe" and tag == "self") else self.cfg["mods"][tm]["dist"]
 
     def _rows(self, i):
+        if self.cfg.get("latent_only"):
+            return self.recon[i]  # already a (K*B,) row vector leaf
         tm, tag = self.plan[i]
         m = self.cfg["mods"][tm]
         fam = self._family(tm, tag)

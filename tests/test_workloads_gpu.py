@@ -15,7 +15,8 @@ def _rel(a, b):
 
 
 CASES = [("c1_poe_elbo_cdsprites_l1", 8, 1e-5), ("c2_moe_iwae_cdsprites_l5", 4, 1e-5),
-         ("c3_mopoe_elbo_sprites", 4, 1e-5), ("c4_moe_dreg_mnistsvhn", 6, 2e-5), ("c5_dmvae_elbo_cub", 6, 1e-5)]
+         ("c3_mopoe_elbo_sprites", 4, 1e-5), ("c4_moe_dreg_mnistsvhn", 6, 2e-5), ("c5_dmvae_elbo_cub", 6, 1e-5),
+         ("c4_moe_dreg_latent_only", 37, 2e-5)]
 
 
 @pytest.mark.parametrize("name,B,tol", CASES)
