@@ -253,8 +253,9 @@ def main():
     group = None
     torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)  # capture warm-up runs on a side stream
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
+        # NCCL prints its version banner on stdout at VERSION and WARN level: send its log to a file so that stdout
+        # carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/mmvae_b200_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     L.load()

@@ -171,3 +171,75 @@ class MultimodalObjective(BaseObjective):
         hook is attached to a tensor that is not on the loss path, so no DReG re-weighting of dz takes place)."""
         loss, lw = ops.dreg_combine(data["lpz"], data["lq"], data["lpx_z"], self.group)
         return {"loss": loss, "kld": torch.tensor(0), "reconstruction_loss": data["lpx_z"], "lw": lw}
+
+
+class UnimodalObjective(BaseObjective):
+    """Reference objectives.py:204-302 (unimodal VAEs).  Only ``elbo`` is executable in the reference: ``iwae`` reads
+    a key that ``calculate_loss`` never sets (``_pz_params``, :283) and ``dreg`` calls ``log_prob`` on the prior CLASS
+    (:296) -- both raise there, and raise here."""
+
+    def __init__(self, obj: str, beta=1):
+        super().__init__()
+        self.beta = beta
+        self.objective = None
+        self.obj_name = obj
+
+    def calculate_loss(self, px_z, target, qz_x, prior_dist, pz_params, zs, K=1):
+        assert hasattr(self, self.obj_name), "Objective {} is not implemented in unimodal scenario".format(self.obj_name)
+        self.objective = getattr(self, self.obj_name)
+        data = {"px_z": px_z, "target": target, "qz_x": qz_x, "prior_dist": prior_dist, "zs": zs, "K": K,
+                "pz_params": pz_params}
+        output = self.objective(data)
+        assert isinstance(output, dict), "Objective function must return a dictionary"
+        return output
+
+    def elbo(self, data, kld_rows=None):
+        """objectives.py:233-247 + BaseObjective.elbo :54-67: -(lpx_z.sum(-1) - beta*kld.sum()).sum() -- the scalar KL
+        total is broadcast against every decoder row, i.e. counted `rows` times (reproduced).  One fused
+        value+gradient pass for the likelihood, one latent kernel for the KL rows."""
+        import torch.distributions as dist
+        px_z, qz_x = data["px_z"], data["qz_x"]
+        S, rows = self.lpx_weighted_sum(px_z, data["target"], 1.0, w_const=-1.0)
+        if kld_rows is None:
+            mu0, s0 = data["pz_params"][0], data["pz_params"][1]
+            res = ops.latent_draws(qz_x.loc.unsqueeze(0), qz_x.scale.unsqueeze(0), mu0, s0, None,
+                                   [ops.Draw(mods=(0,), direct=True, laplace=isinstance(qz_x, dist.Laplace), kl_mode=1,
+                                             width=qz_x.loc.shape[-1])])
+            kld_rows = res[0]["kl"]
+        loss = S + rows.numel() * self.beta * kld_rows.sum()
+        return {"loss": loss, "kld": kld_rows, "reconstruction_loss": rows}
+
+    def iwae(self, data):
+        raise NotImplementedError("UnimodalObjective.iwae raises in the reference (KeyError '_pz_params', objectives.py:283)")
+
+    def dreg(self, data):
+        raise NotImplementedError("UnimodalObjective.dreg raises in the reference (log_prob on the prior class, "
+                                  "objectives.py:296)")
+
+
+def unimodal_objective(vae, data, beta=1.0, K=1, noise=None):
+    """VAE.forward + VAE.objective of the reference (vae.py:99-119, :264-281) for a per-modality VAE object with the
+    reference attribute surface (enc, dec, qz_x, px_z, ltype): sampling and the KL rows come from ONE latent kernel
+    launch, the likelihood is the fused value+gradient pass.  `noise`: optional (K,B,D) tensor (eps, or u for Laplace)."""
+    import torch.distributions as dist
+    x = data["mod_1"] if "mod_1" in data else data
+    mu, s = vae.enc(x)
+    lap = vae.qz_x is dist.Laplace
+    Kb, (B, D) = K, mu.shape
+    if noise is None:
+        if lap:
+            noise = torch.empty((Kb, B, D), device=mu.device).uniform_(torch.finfo(torch.float32).eps - 1, 1)
+        else:
+            noise = torch.randn((Kb, B, D), device=mu.device)
+    res = ops.latent_draws(mu.float().unsqueeze(0), s.float().unsqueeze(0), None, None, noise.reshape(-1),
+                           [ops.Draw(mods=(0,), direct=True, laplace=lap, kl_mode=2, width=D, K=Kb)])[0]
+    masks = None if x.get("masks") is None else x["masks"].repeat(Kb, 1)
+    dec_out = vae.dec({"latents": res["z"].reshape(1, -1, D), "masks": masks})
+    loc = dec_out[0] if isinstance(dec_out, (tuple, list)) else dec_out
+    obj = UnimodalObjective("elbo", beta)
+    obj.set_ltype("bce_logits" if (vae.ltype == "bce" and getattr(vae.dec, "returns_logits", False)) else vae.ltype)
+    px_z = (dist.Laplace if vae.px_z is dist.Laplace else dist.Normal)(loc, torch.tensor(0.75, device=loc.device),
+                                                                       validate_args=False)
+    out = obj.elbo({"px_z": px_z, "target": x, "qz_x": None}, kld_rows=res["kl"])
+    out["z"] = res["z"]
+    return out

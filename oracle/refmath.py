@@ -484,3 +484,19 @@ def dmvae_objective(mods, pz_logits, noise, beta=1.0, K=1):
     ind_r = [-(l).sum() / mods[i]["lam"] for i, l in enumerate(ind)]
     return {"loss": torch.stack(losses).sum(), "reconstruction_loss": ind_r,
             "kld": torch.stack(klds).mean(0).sum(), "joint": (mu_j, var_j), "z": zs}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Unimodal VAE: VAE.forward vae.py:99-119 + VAE.objective :264-281 + UnimodalObjective.elbo
+# objectives.py:233-247.  The fixed VAE-level prior is N(0, 1) (_pz_params = zeros, ones, vae.py:159-162).
+# ----------------------------------------------------------------------------------------------------------
+def unimodal_elbo(mu, s, dist_name, noise, dec, target, ltype, beta=1.0, K=1, mask_len=None):
+    """loss = -(lpx_z.sum(-1) - beta * kld.sum()).sum(): the scalar KL total is broadcast against EVERY decoder row
+    (objectives.py:67), i.e. it is counted rows = K*B times -- reproduced.  Note VAE.objective calls
+    calculate_loss without K (defaults to 1) while forward() used K=1 as well."""
+    z = rsample(dist_name, mu, s, noise)  # (K,B,D)
+    loc = dec(z.reshape(1, -1, z.shape[-1]))  # vae.py:112
+    lpx_z = recon_logp(ltype, loc, target, K, dist_name, mask_len=mask_len)
+    kld = kl_to_normal(dist_name, mu, s, torch.zeros_like(mu[:1]), torch.ones_like(mu[:1]))
+    loss = elbo(lpx_z, kld, beta)
+    return {"loss": loss, "kld": kld, "reconstruction_loss": lpx_z, "z": z}

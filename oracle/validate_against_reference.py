@@ -143,8 +143,69 @@ def check_functions():
     return n
 
 
+def unimodal_cases():
+    g = torch.Generator().manual_seed(77)
+    out = []
+    for name, ltype, distn, shape, K, beta in [("uni_elbo_bce", "bce", "normal", (3, 8, 8), 1, 1.0),
+                                               ("uni_elbo_laplace", "lprob", "laplace", (1, 7, 7), 1, 2.0),
+                                               ("uni_elbo_ce", "category_ce", "normal", (5, 27), 1, 0.5)]:
+        B, D = 6, 5
+        import mmvae_b200.synthetic as syn
+        mu, s = syn.make_posterior(g, B, D)
+        P = 1
+        for x in shape:
+            P *= x
+        W = torch.randn(P, D, generator=g) * 0.3
+        b = torch.randn(P, generator=g) * 0.1
+        target = syn.make_target(g, "onehot" if ltype == "category_ce" else "uniform", B, shape)
+        noise = syn.make_noise(g, distn, (K, B, D))
+        out.append(dict(name=name, ltype=ltype, dist=distn, shape=shape, K=K, beta=beta, mu=mu, s=s, W=W, b=b,
+                        target=target, noise=noise))
+    return out
+
+
+def run_reference_unimodal(c):
+    """Reference UnimodalObjective.elbo through calculate_loss with the distributions VAE.forward builds."""
+    import torch.distributions as dist
+    models, objectives, utils = ref_inplace.load()
+    Dcls = dist.Laplace if c["dist"] == "laplace" else dist.Normal
+    mu, s, W, b = (c[k].clone().requires_grad_(True) for k in ("mu", "s", "W", "b"))
+    obj = objectives.UnimodalObjective("elbo", c["beta"])
+    obj.set_ltype(c["ltype"])
+    with ref_inplace.NoiseInjector([c["noise"].clone()]):
+        qz_x = Dcls(mu, s)
+        zs = qz_x.rsample(torch.Size([c["K"]]))
+    lin = zs.reshape(1, -1, zs.shape[-1]) @ W.t() + b
+    if c["ltype"] == "bce":
+        lin = torch.sigmoid(lin).clamp(1e-6, 1 - 1e-6)
+    loc = lin.reshape(-1, *c["shape"])
+    px_z = Dcls(loc, torch.tensor(0.75))
+    pz_params = (torch.zeros(1, mu.shape[1]), torch.ones(1, mu.shape[1]))
+    out = obj.calculate_loss(px_z, {"data": c["target"], "masks": None}, qz_x, dist.Normal, pz_params, zs, K=c["K"])
+    out["loss"].backward()
+    return {"loss": out["loss"].detach().double(), "kld": out["kld"].detach().double(),
+            "grad.mu": mu.grad.double(), "grad.s": s.grad.double(), "grad.W": W.grad.double(), "grad.b": b.grad.double()}
+
+
+def run_oracle_unimodal(c, dtype=torch.float32):
+    mu, s, W, b = (c[k].to(dtype).clone().requires_grad_(True) for k in ("mu", "s", "W", "b"))
+
+    def dec(z):
+        lin = z @ W.t() + b
+        if c["ltype"] == "bce":
+            lin = torch.sigmoid(lin).clamp(1e-6, 1 - 1e-6)
+        return lin.reshape(-1, *c["shape"])
+    out = refmath.unimodal_elbo(mu, s, c["dist"], c["noise"].to(dtype), dec, c["target"].to(dtype), c["ltype"], c["beta"], c["K"])
+    out["loss"].backward()
+    return {"loss": out["loss"].detach().double(), "kld": out["kld"].detach().double(),
+            "grad.mu": mu.grad.double(), "grad.s": s.grad.double(), "grad.W": W.grad.double(), "grad.b": b.grad.double()}
+
+
 def main():
     assert ref_inplace.available(), "needs /root/reference"
+    for c in unimodal_cases():
+        worst = compare(run_reference_unimodal(c), run_oracle_unimodal(c), c["name"])
+        print("%-22s unimodal worst rel diff vs reference %.2e" % (c["name"], worst))
     n = check_functions()
     print("function-level checks ok (%d comparisons)" % n)
     for case in cases.case_list():

@@ -200,3 +200,53 @@ def test_bf16_encoder_outputs_are_accepted():
     assert vaes["mod_1"].enc.mu.grad.dtype == torch.bfloat16
     assert _rel(out["loss"], ref["loss"]) < 2e-2
     assert _rel(vaes["mod_1"].enc.mu.grad, ref["grad.mod_1.mu"]) < 3e-2
+
+
+def test_unimodal_elbo_matches_reference_golden(golden):
+    """VAE.forward + UnimodalObjective.elbo on the same kernels (M = 1), against the frozen outputs
+    of the reference's own UnimodalObjective."""
+    import torch.distributions as dist
+    import torch.nn as nn
+    import mmvae_b200
+    import mmvae_b200.synthetic as syn
+    for entry in golden["unimodal"]:
+        c, ref = entry["case"], entry["reference"]
+        mu = c["mu"].cuda().requires_grad_(True)
+        s = c["s"].cuda().requires_grad_(True)
+        W = c["W"].cuda().requires_grad_(True)
+        b = c["b"].cuda().requires_grad_(True)
+
+        class Dec(nn.Module):
+            def forward(self, z):
+                lin = z["latents"] @ W.t() + b
+                if c["ltype"] == "bce":
+                    lin = torch.sigmoid(lin).clamp(1e-6, 1 - 1e-6)
+                return lin.reshape(-1, *c["shape"]), torch.tensor(0.75, device=lin.device)
+
+        class Enc(nn.Module):
+            data_dim = c["shape"]
+
+            def forward(self, x):
+                return mu, s
+        vae = syn.StubVAE(Enc(), Dec(), mu.shape[1], c["ltype"], prior_dist=c["dist"])
+        out = mmvae_b200.unimodal_objective(vae, {"mod_1": {"data": c["target"].cuda(), "masks": None}}, beta=c["beta"],
+                                            K=c["K"], noise=c["noise"].cuda())
+        out["loss"].backward()
+        assert _rel(out["loss"], ref["loss"]) < TOL, c["name"]
+        assert _rel(out["kld"], ref["kld"].sum(-1)) < TOL
+        for k, t in (("mu", mu), ("s", s), ("W", W), ("b", b)):
+            assert _rel(t.grad, ref["grad." + k]) < TOL, (c["name"], k)
+        # API-compatible entry: calculate_loss on torch.distributions objects
+        Dcls = dist.Laplace if c["dist"] == "laplace" else dist.Normal
+        obj = mmvae_b200.UnimodalObjective("elbo", c["beta"])
+        obj.set_ltype(c["ltype"])
+        mu2, s2 = c["mu"].cuda().requires_grad_(True), c["s"].cuda().requires_grad_(True)
+        qz = Dcls(mu2, s2)
+        z = out["z"].detach()
+        loc = Dec()({"latents": z.reshape(1, -1, z.shape[-1])})[0]
+        o2 = obj.calculate_loss(Dcls(loc, torch.tensor(0.75, device="cuda")), {"data": c["target"].cuda(), "masks": None}, qz,
+                                dist.Normal, (torch.zeros(1, mu.shape[1], device="cuda"), torch.ones(1, mu.shape[1], device="cuda")),
+                                z, K=c["K"])
+        assert _rel(o2["loss"], ref["loss"]) < TOL
+        with pytest.raises(NotImplementedError):
+            mmvae_b200.UnimodalObjective("iwae").calculate_loss(None, None, None, None, None, None)

@@ -46,3 +46,10 @@ def test_chunk_maps_bit_exact(golden):
         assert en == ends, (S, B)
         rm = refmath.mopoe_row_to_subset(S, B)
         assert [int((rm <= k).sum()) for k in range(S)] == ends
+
+
+def test_unimodal_restatement_matches_reference(golden):
+    from oracle.validate_against_reference import run_oracle_unimodal
+    assert len(golden["unimodal"]) == 3
+    for entry in golden["unimodal"]:
+        _cmp(entry["reference"], run_oracle_unimodal(entry["case"]), entry["case"]["name"])
