@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default: the workload's batch)")
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--overlap", action="store_true", help="run small kernels on a side stream (measured slower on C2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=8, help="samples per step of the bounded CPU sample")
@@ -263,6 +264,7 @@ def main():
     cfg, t = W.make_leaves(args.workload, B=args.batch, seed=1234 + rank, recon_dtype=rdt)
     B = cfg["B"]
     step = W.LeafStep(cfg, t, device=dev, group=group, global_batch=B * world)
+    step.overlap = args.overlap
     W_, K_ = max(args.warmup, 3), args.steps
 
     def sync_grads():
@@ -401,7 +403,8 @@ def main():
                        "mods": [{"data_dim": list(m["data_dim"]), "ltype": m["ltype"]} for m in cfg["mods"]],
                        "parallelism": "batch-sharded x%d, NCCL all-reduce of replicated grads" % world,
                        "l2": "per-step working set %.2f GB >> 126 MB L2, no flush" % (step_bytes / 1e9),
-                       "launch_mode": "cuda-graph" if runner is not step else "eager"},
+                       "launch_mode": "cuda-graph" if runner is not step else "eager",
+                       "streams": "side stream overlaps small kernels" if step.overlap else "single stream"},
             "roofline": roofline, "gpu_launches": launches_per_step * K_, "launches_per_step": launches_per_step,
             "clocks": clocks}
     if e2e is not None:

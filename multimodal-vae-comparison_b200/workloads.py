@@ -129,6 +129,15 @@ class LeafStep:
         else:
             self.eps_stacked = torch.stack(self.noise)  # (M,K,B,D), what mmvae_moe_logdens_* consume
         self._mu0 = torch.zeros(1, self.D, device=dev)
+        # Optional (off by default): run the latency-bound small kernels (latent kernels, short-row likelihood terms) on
+        # a side stream concurrently with the bandwidth-bound long-row terms (fork/join inside the captured graph;
+        # autograd replays each backward node on the stream of its forward).  Measured r1 on C2: 0.554 ms/step with
+        # the overlap vs 0.498 ms without -- the small kernels take SM slots from the streaming kernels -- so the
+        # single-stream order is the default.
+        self.side = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        nbytes = [r.numel() * r.element_size() for r in self.recon]
+        self.small = [nb < 0.25 * max(nbytes) for nb in nbytes]
+        self.overlap = False
 
     def leaves(self):
         return [self.mu, self.s, self.pz_logits] + self.recon
@@ -202,8 +211,24 @@ class LeafStep:
                 total, n_keep = total + S, n_keep + (S != 0).float()
             kld = torch.stack([k["kl"] for k in kls])
             return total + (self.beta / M) * n_keep * kld.sum()
-        z, lq, lpz = ops.moe_logdens(self.mu, self.s, mu0, s0, eps, self.codes, True)
-        rows = [self._rows(i) for i in range(len(self.plan))]
+        if self.overlap and self.side is not None and any(self.small) and not all(self.small):
+            cur = torch.cuda.current_stream()
+            self.side.wait_stream(cur)
+            rows = [None] * len(self.plan)
+            with torch.cuda.stream(self.side):
+                z, lq, lpz = ops.moe_logdens(self.mu, self.s, mu0, s0, eps, self.codes, True)
+                for i in range(len(self.plan)):
+                    if self.small[i]:
+                        rows[i] = self._rows(i)
+            for i in range(len(self.plan)):
+                if not self.small[i]:
+                    rows[i] = self._rows(i)
+            cur.wait_stream(self.side)
+            for t in [lq, lpz] + [rows[i] for i in range(len(self.plan)) if self.small[i]]:
+                t.record_stream(cur)
+        else:
+            z, lq, lpz = ops.moe_logdens(self.mu, self.s, mu0, s0, eps, self.codes, True)
+            rows = [self._rows(i) for i in range(len(self.plan))]
         L = len(rows) // M
         lpx = torch.stack(rows).view(M, L, K, B)
         if self.obj == "iwae":
