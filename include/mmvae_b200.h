@@ -220,6 +220,19 @@ MMVAE_API int mmvae_moe_logdens_bwd(const float* mu, const float* s, int M, int6
  * ------------------------------------------------------------------------------------------------------- */
 MMVAE_API int mmvae_objective_iwae(const float* lpz, const float* lq, const float* lpx, int M, int L, int K, int64_t B,
                          float beta, float* lw, float* loss_b, float* w, float* dlq, void* stream);
+/* same, the M*L likelihood row vectors (K*B each) addressed through a HOST array of device pointers
+ * (index r*L + l) instead of one stacked (M,L,K,B) tensor: no concatenation copy.  lpx may be NULL then. */
+MMVAE_API int mmvae_objective_iwae_ptrs(const float* lpz, const float* lq, const float* lpx,
+                              const float* const* lpx_ptrs_host, int M, int L, int K, int64_t B, float beta,
+                              float* lw, float* loss_b, float* w, float* dlq, void* stream);
+/* IWAE backward in one launch: dlpz_out = -g*w (n_w floats; also the gradient of each likelihood row vector of the
+ * same modality), dlq_inout *= g (n_dlq floats); g_dev: device scalar (upstream gradient of the loss). */
+MMVAE_API int mmvae_objective_iwae_bwd(const float* g_dev, const float* w, float* dlq_inout, float* dlpz_out,
+                             int64_t n_w, int64_t n_dlq, void* stream);
+/* learnable prior scale s0 = softmax(logits)*D (reference mmvae_models.py:28-30 pz_params) and its backward
+ * dlogits = D p (ds0 - <ds0, p>); replaces four tiny eager kernels per step. */
+MMVAE_API int mmvae_prior_scale_fwd(const float* logits, int D, float* s0, void* stream);
+MMVAE_API int mmvae_prior_scale_bwd(const float* s0, const float* ds0, int D, float* dlogits, void* stream);
 /* lw_part: (MMVAE_DREG_MAX_SPLIT + 1) * M * K DOUBLES; the first M*K receive the local batch sums, the rest is
  * scratch for the deterministic two-stage batch reduction.  The sums are carried in fp64: they feed a softmax over
  * K whose conditioning is set by their absolute error, and the reference holds them in fp64 for lprob likelihoods

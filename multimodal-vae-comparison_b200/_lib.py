@@ -47,6 +47,11 @@ SIGNATURES = {
     "mmvae_moe_logdens_bwd": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_i, ctypes.POINTER(ctypes.c_int32), c_p, c_p, c_p,
                                     c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     "mmvae_objective_iwae": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i64, c_f, c_p, c_p, c_p, c_p, c_p]),
+    "mmvae_objective_iwae_ptrs": (c_i, [c_p, c_p, c_p, ctypes.POINTER(c_p), c_i, c_i, c_i, c_i64, c_f, c_p, c_p, c_p,
+                                        c_p, c_p]),
+    "mmvae_objective_iwae_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_p]),
+    "mmvae_prior_scale_fwd": (c_i, [c_p, c_i, c_p, c_p]),
+    "mmvae_prior_scale_bwd": (c_i, [c_p, c_p, c_i, c_p, c_p]),
     "mmvae_objective_dreg_stage1": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i64, c_p, c_p, c_p]),
     "mmvae_objective_dreg_stage2": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p]),
     "mmvae_reduce_sum": (c_i, [c_p, c_i64, c_f, c_p, c_p]),

@@ -9,8 +9,11 @@
 namespace mmvae {
 
 
+constexpr int kMaxTerms = 32;  // M*L likelihood row vectors addressed through a pointer table
+
 struct CombParams {
-    const float *lpz, *lq, *lpx;
+    const float *lpz, *lq;
+    const float* lpx_ptr[kMaxTerms];  // [r*L + l] -> (K*B) rows of likelihood term l of modality r
     float *lw, *loss_b, *w, *dlq;
     int64_t B;
     int M, L, K;
@@ -37,7 +40,7 @@ __device__ __forceinline__ float lme_j(const CombParams& p, int r, int k, int64_
 __device__ __forceinline__ float lw_value(const CombParams& p, int r, int k, int64_t b, float beta, float* vals,
                                           float& mx, float& se) {
     float v = __ldg(p.lpz + ((int64_t)r * p.K + k) * p.B + b);
-    for (int l = 0; l < p.L; ++l) v += __ldg(p.lpx + (((int64_t)r * p.L + l) * p.K + k) * p.B + b);
+    for (int l = 0; l < p.L; ++l) v += __ldg(p.lpx_ptr[r * p.L + l] + (int64_t)k * p.B + b);
     return v - beta * lme_j(p, r, k, b, vals, mx, se);
 }
 
@@ -169,6 +172,60 @@ __global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restric
     if (threadIdx.x == 0) *out = scale * tot;
 }
 
+// IWAE backward in one launch: dlpz = -g * w (also the gradient of every likelihood row vector of that modality),
+// dlq *= g.  g is the upstream gradient of the loss, a device scalar.
+__global__ void __launch_bounds__(256) iwae_bwd_kernel(const float* __restrict__ g, const float* __restrict__ w,
+                                                       float* __restrict__ dlq, float* __restrict__ dlpz, int64_t n_w,
+                                                       int64_t n_dlq) {
+    const float gv = __ldg(g);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_w; i += stride) dlpz[i] = -gv * w[i];
+    if (gv != 1.0f)
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_dlq; i += stride) dlq[i] *= gv;
+}
+
+// Learnable prior scale s0 = softmax(logits) * D (reference mmvae_models.py:28-30) and its backward
+// dlogits_i = D * p_i * (ds0_i - sum_d ds0_d p_d); D <= 1024, one CTA.
+__global__ void __launch_bounds__(256) prior_scale_fwd_kernel(const float* __restrict__ logits, int D,
+                                                              float* __restrict__ s0) {
+    __shared__ float red[32];
+    __shared__ float bc;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) mx = fmaxf(mx, logits[i]);
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = -INFINITY;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+        bc = m;
+    }
+    __syncthreads();
+    mx = bc;
+    float se = 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) se += expf(logits[i] - mx);
+    __syncthreads();
+    se = block_sum(se, red);
+    if (threadIdx.x == 0) bc = se;
+    __syncthreads();
+    se = bc;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) s0[i] = expf(logits[i] - mx) / se * (float)D;
+}
+
+__global__ void __launch_bounds__(256) prior_scale_bwd_kernel(const float* __restrict__ s0,
+                                                              const float* __restrict__ ds0, int D,
+                                                              float* __restrict__ dlogits) {
+    __shared__ float red[32];
+    __shared__ float bc;
+    float dot = 0.f;  // sum_d ds0_d * p_d with p = s0 / D
+    for (int i = threadIdx.x; i < D; i += blockDim.x) dot += ds0[i] * s0[i];
+    dot = block_sum(dot, red);
+    if (threadIdx.x == 0) bc = dot / (float)D;
+    __syncthreads();
+    dot = bc;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) dlogits[i] = s0[i] * (ds0[i] - dot);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) scale_kernel(T* __restrict__ buf, int64_t n, const float* __restrict__ scalar) {
     const float sc = __ldg(scalar);
@@ -183,19 +240,29 @@ using namespace mmvae;
 
 extern "C" int mmvae_version(void) { return MMVAE_ABI_VERSION; }
 
-static int comb_fill(CombParams& p, const float* lpz, const float* lq, const float* lpx, int M, int L, int K,
-                     int64_t B) {
-    if (!lpz || !lq || (L > 0 && !lpx) || M <= 0 || L < 0 || K <= 0 || B <= 0) return MMVAE_E_ARG;
-    if (M > MMVAE_MAX_MODS) return MMVAE_E_LIMIT;
-    p.lpz = lpz; p.lq = lq; p.lpx = lpx; p.M = M; p.L = L; p.K = K; p.B = B;
+static int comb_fill(CombParams& p, const float* lpz, const float* lq, const float* lpx, const float* const* ptrs,
+                     int M, int L, int K, int64_t B) {
+    if (!lpz || !lq || (L > 0 && !lpx && !ptrs) || M <= 0 || L < 0 || K <= 0 || B <= 0) return MMVAE_E_ARG;
+    if (M > MMVAE_MAX_MODS || M * L > kMaxTerms) return MMVAE_E_LIMIT;
+    p.lpz = lpz; p.lq = lq; p.M = M; p.L = L; p.K = K; p.B = B;
+    for (int i = 0; i < M * L; ++i) {
+        p.lpx_ptr[i] = ptrs ? ptrs[i] : lpx + (int64_t)i * K * B;
+        if (!p.lpx_ptr[i]) return MMVAE_E_ARG;
+    }
     return 0;
 }
 
 extern "C" int mmvae_objective_iwae(const float* lpz, const float* lq, const float* lpx, int M, int L, int K,
                                     int64_t B, float beta, float* lw, float* loss_b, float* w, float* dlq,
                                     void* stream) {
+    return mmvae_objective_iwae_ptrs(lpz, lq, lpx, nullptr, M, L, K, B, beta, lw, loss_b, w, dlq, stream);
+}
+
+extern "C" int mmvae_objective_iwae_ptrs(const float* lpz, const float* lq, const float* lpx,
+                                         const float* const* lpx_ptrs_host, int M, int L, int K, int64_t B, float beta,
+                                         float* lw, float* loss_b, float* w, float* dlq, void* stream) {
     CombParams p{};
-    int rc = comb_fill(p, lpz, lq, lpx, M, L, K, B);
+    int rc = comb_fill(p, lpz, lq, lpx, lpx_ptrs_host, M, L, K, B);
     if (rc) return rc;
     if (!lw || !loss_b || !w) return MMVAE_E_ARG;
     p.beta = beta; p.lw = lw; p.loss_b = loss_b; p.w = w; p.dlq = dlq;
@@ -217,7 +284,7 @@ extern "C" int mmvae_objective_dreg_stage1(const float* lpz, const float* lq, co
                                            int64_t B, double* lw_part, float* lq_soft, void* stream) {
     // lw_part: (DREG_MAX_SPLIT + 1, M*K) doubles: [0] receives the local batch sums, [1..] is scratch
     CombParams p{};
-    int rc = comb_fill(p, lpz, lq, lpx, M, L, K, B);
+    int rc = comb_fill(p, lpz, lq, lpx, nullptr, M, L, K, B);
     if (rc) return rc;
     if (!lw_part) return MMVAE_E_ARG;
     int nsplit = (int)((B + 2047) / 2048);
@@ -257,6 +324,31 @@ extern "C" int mmvae_scale_inplace(void* buf, int dtype, int64_t n, const float*
         scale_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)buf, n, scalar_dev);
     else
         return MMVAE_E_ENUM;
+    MMVAE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mmvae_objective_iwae_bwd(const float* g_dev, const float* w, float* dlq_inout, float* dlpz_out,
+                                        int64_t n_w, int64_t n_dlq, void* stream) {
+    if (!g_dev || !w || !dlpz_out || n_w <= 0 || (n_dlq > 0 && !dlq_inout)) return MMVAE_E_ARG;
+    int64_t blocks = ((n_w > n_dlq ? n_w : n_dlq) + 255) / 256;
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    if (blocks > cap) blocks = cap;
+    iwae_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g_dev, w, dlq_inout, dlpz_out, n_w, n_dlq);
+    MMVAE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mmvae_prior_scale_fwd(const float* logits, int D, float* s0, void* stream) {
+    if (!logits || !s0 || D <= 0) return MMVAE_E_ARG;
+    prior_scale_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, D, s0);
+    MMVAE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mmvae_prior_scale_bwd(const float* s0, const float* ds0, int D, float* dlogits, void* stream) {
+    if (!s0 || !ds0 || !dlogits || D <= 0) return MMVAE_E_ARG;
+    prior_scale_bwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(s0, ds0, D, dlogits);
     MMVAE_LAUNCH_CHECK();
     return 0;
 }

@@ -64,6 +64,13 @@ class TorchMMVAE(nn.Module):
         """(mu0, softmax(_pz_params[1], 1) * D) -- mmvae_models.py:28-30 and siblings."""
         return self._pz_params[0], F.softmax(self._pz_params[1], dim=1) * self._pz_params[1].size(-1)
 
+    def _prior(self):
+        """pz_params for the kernels: same values as the `pz_params` property, the softmax*D evaluated by one tiny
+        kernel each way (ops.prior_scale) instead of four eager ones."""
+        if self._pz_params[1].is_cuda:
+            return self._pz_params[0], ops.prior_scale(self._pz_params[1])
+        return self.pz_params
+
     @property
     def latent_factorization(self):
         return any(v.private_latents is not None for v in self.vaes.values())

@@ -161,21 +161,29 @@ class MOE(TorchMMVAE):
             kld = torch.stack([k["kl"] for k in kls])  # (M,B)
             loss = total + (beta / M) * n_keep * kld.sum()  # total KL once per kept row (objectives.py:67)
             return {"loss": loss, "reconstruction_loss": torch.stack(rows_log), "kld": kld}
-        mu, s, codes, z, lq, lpz = self._sample(names, enc, K, self.pz_params, through_z=True)
+        mu, s, codes, z, lq, lpz = self._sample(names, enc, K, self._prior(), through_z=True)
         B = mu.shape[1]
-        lpx = []
+        L = 1 if M == 1 else 2
+        # the row kernels write straight into slices of one (M, L, K*B) buffer: the list of row vectors IS the stacked
+        # tensor the reference builds with torch.stack (no concatenation copies)
+        buf = torch.empty((M, L, K * B), dtype=torch.float32, device=mu.device)
+        rows = []
         for r, name in enumerate(names):
             vae = self.vaes[name]
             self.obj_fn.set_ltype(vae.ltype)
-            terms = [self.obj_fn.lpx_rows(_first(vae.dec({"latents": z[r], "masks": data[name]["masks"]})), data[name],
-                                          vae.llik_scaling, ltype=_ltype(vae), family="normal")]
+            rows.append(self.obj_fn.lpx_rows(_first(vae.dec({"latents": z[r], "masks": data[name]["masks"]})), data[name],
+                                             vae.llik_scaling, ltype=_ltype(vae), family="normal", out=buf[r, 0]))
             src = self._cross_source(M, r)
             if src is not None:
-                terms.append(self.obj_fn.lpx_rows(_first(vae.dec({"latents": z[src], "masks": data[name]["masks"]})),
-                                                  data[name], vae.llik_scaling, ltype=_ltype(vae), family=_family(vae)))
-            lpx.append(torch.stack(terms))
-        lpx = torch.stack(lpx).view(M, -1, K, B)
-        return self.obj_fn.calculate_loss({"lpz": lpz, "lq": lq, "lpx_z": lpx})
+                rows.append(self.obj_fn.lpx_rows(_first(vae.dec({"latents": z[src], "masks": data[name]["masks"]})),
+                                                 data[name], vae.llik_scaling, ltype=_ltype(vae), family=_family(vae),
+                                                 out=buf[r, 1]))
+        d = {"lpz": lpz, "lq": lq, "lpx_z": buf.view(M, L, K, B)}
+        if self.obj_fn.obj_name == "iwae":
+            d["lpx_rows"] = rows
+        else:  # DReG combine reads the stacked tensor; route the gradient through a differentiable stack
+            d["lpx_z"] = torch.stack(rows).view(M, L, K, B)
+        return self.obj_fn.calculate_loss(d)
 
     def modality_mixing(self, mods):
         return mods
@@ -228,7 +236,7 @@ class POE(TorchMMVAE):
         B = mu.shape[1]
         subsets = poe_subsets(range(M))
         eps = torch.cat([self._noise("normal", (1, B, D), mu.device).reshape(-1) for _ in subsets])
-        mu0, s0 = self.pz_params
+        mu0, s0 = self._prior()
         res = ops.latent_draws(mu, s, mu0, s0, eps,
                                [Draw(mods=sub, prior=True, kl_mode=1, width=D, K=1) for sub in subsets])
         total, kl_rows = 0.0, []
@@ -337,7 +345,7 @@ class MoPOE(TorchMMVAE):
         subs = self._available(set(range(M)))
         row_masks = self._row_masks(subs, B, mu.device)
         eps = torch.cat([self._noise("normal", (K, B, D), mu.device).reshape(-1) for _ in names])
-        mu0, s0 = self.pz_params
+        mu0, s0 = self._prior()
         draws = [Draw(rowmask=True, kl_mode=1 if i == 0 else 0, width=D, K=K) for i in range(M)]
         draws += [Draw(mods=(i,), direct=True, kl_mode=1, width=D) for i in range(M)]
         res = ops.latent_draws(mu, s, mu0, s0, eps, draws, row_masks)
@@ -434,7 +442,7 @@ class DMVAE(TorchMMVAE):
         B = mu.shape[1]
         draws, index = self._draws(names, K)
         eps = torch.cat([self._noise("normal", (d.K, B, d.width), mu.device).reshape(-1) for d in draws])
-        mu0, s0 = self.pz_params
+        mu0, s0 = self._prior()
         res = ops.latent_draws(mu, s, mu0, s0, eps, draws)
         return names, enc, mu, s, res, index
 

@@ -19,13 +19,16 @@ class ReconLoss:
     feature axis) -- the only form the model plugins consume."""
 
     @staticmethod
-    def _rows(ltype, loc, target, lam, likelihood, group=None):
+    def _rows(ltype, loc, target, lam, likelihood, group=None, out=None):
         if ltype in ELEMENTWISE:
-            return ops.loglik_rows(loc, target, ltype, likelihood, lam)
+            return ops.loglik_rows(loc, target, ltype, likelihood, lam, out=out)
         if ltype == "category_ce":
-            return ops.catce_rows(loc, target, lam)
+            return ops.catce_rows(loc, target, lam, out=out)
         if ltype == "optimal_sigma":
-            return ops.osigma_rows(loc, target, lam, group)
+            rows = ops.osigma_rows(loc, target, lam, group)
+            if out is not None:  # three-stage kernel sequence with its own output; mirror it into the stacked buffer
+                out.view(-1).copy_(rows.detach())
+            return rows
         raise NotImplementedError(ltype)
 
     @staticmethod
@@ -104,14 +107,15 @@ class BaseObjective:
             loc = loc.reshape(rows, *data.shape[1:])
         return loc, data
 
-    def lpx_rows(self, px_z, target, lam=1.0, ltype=None, family=None):
-        """(recon_loss_fn(px_z, target, K) * lam).sum(-1) of the reference -> (K*B,) rows, k-major."""
+    def lpx_rows(self, px_z, target, lam=1.0, ltype=None, family=None, out=None):
+        """(recon_loss_fn(px_z, target, K) * lam).sum(-1) of the reference -> (K*B,) rows, k-major.
+        out: optional contiguous (K*B,) fp32 slice the kernel writes into (a row of a stacked buffer)."""
         ltype = ltype or self.ltype
         if ltype == "lprob" and target.get("masks") is not None:
             raise NotImplementedError("lprob with padding masks (reference overwrites scale with loc, objectives.py:45)")
         loc, family = _loc_family(px_z, family)
         loc, data = self._prep(loc, target)
-        return ReconLoss._rows(ltype, loc, data, float(lam), family, self.group)
+        return ReconLoss._rows(ltype, loc, data, float(lam), family, self.group, out)
 
     def lpx_weighted_sum(self, px_z, target, lam=1.0, w_rows=None, w_const=1.0, ltype=None, family=None):
         """S = sum_r w_r * rows[r] (+ rows for logging) with the gradient produced in the same pass."""
@@ -163,7 +167,11 @@ class MultimodalObjective(BaseObjective):
 
     def iwae(self, data):
         """objectives.py:342-359.  data: lpz (M,K,B), lq (M,M,K,B), lpx_z (M,L,K,B) from ops.moe_logdens / lpx_rows."""
-        loss, lw = ops.iwae_combine(data["lpz"], data["lq"], data["lpx_z"], self.beta)
+        if data.get("lpx_rows") is not None:  # list of M*L row vectors (views of the stacked buffer): no stack copy
+            L = len(data["lpx_rows"]) // data["lpz"].shape[0]
+            loss, lw = ops.iwae_combine_rows(data["lpz"], data["lq"], data["lpx_rows"], L, self.beta)
+        else:
+            loss, lw = ops.iwae_combine(data["lpz"], data["lq"], data["lpx_z"], self.beta)
         return {"loss": loss, "kld": torch.tensor(0), "reconstruction_loss": data["lpx_z"], "lw": lw}
 
     def dreg(self, data):

@@ -77,14 +77,14 @@ class _LoglikRows(torch.autograd.Function):
     priori: IWAE / DReG).  include/mmvae_b200.h mmvae_loglik_rowreduce_{fwd,bwd}."""
 
     @staticmethod
-    def forward(ctx, recon, target, lt, scale, lam):
+    def forward(ctx, recon, target, lt, scale, lam, out=None):
         _need_cuda(recon, target)
         rows, B = recon.shape[0], target.shape[0]
         x, P, ldx = _rows2d(recon.detach(), rows)
         t, Pt, ldt = _rows2d(target.detach(), B)
         if Pt != P or rows % B != 0:
             raise RuntimeError("mmvae_b200: recon rows x P (%d x %d) incompatible with target (%d x %d)" % (rows, P, B, Pt))
-        out = torch.empty(rows, dtype=torch.float32, device=recon.device)
+        out = _row_out(out, rows, recon.device)
         nws = _lib.load().mmvae_loglik_workspace_bytes(rows, P, _dt(x))
         ws = torch.empty(max(nws // 4, 1), dtype=torch.float32, device=recon.device)
         call("mmvae_loglik_rowreduce_fwd", _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, P, lt, scale, lam,
@@ -101,7 +101,7 @@ class _LoglikRows(torch.autograd.Function):
         g = torch.empty((rows, P), dtype=x.dtype, device=x.device)
         call("mmvae_loglik_rowreduce_bwd", _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, P, lt, scale, lam,
              _ptr(w), _ptr(g), P, _stream())
-        return g.view(shape), None, None, None, None
+        return g.view(shape), None, None, None, None, None
 
 
 class _LoglikWeightedSum(torch.autograd.Function):
@@ -147,8 +147,18 @@ class _LoglikWeightedSum(torch.autograd.Function):
         return g.view(ctx.shape), None, gw, None, None, None, None
 
 
-def loglik_rows(recon, target, ltype, likelihood="normal", lam=1.0, scale=0.75):
-    return _LoglikRows.apply(recon, target, ltype_code(ltype, likelihood), float(scale), float(lam))
+def _row_out(out, rows, device):
+    """Destination of a row kernel: a fresh (rows,) fp32 tensor, or a caller-provided contiguous slice of a stacked
+    buffer (so that the list of row vectors IS the stacked tensor, no concatenation copy)."""
+    if out is None:
+        return torch.empty(rows, dtype=torch.float32, device=device)
+    if out.dtype != torch.float32 or out.numel() != rows or not out.is_contiguous() or out.device != device:
+        raise RuntimeError("mmvae_b200: `out` must be a contiguous fp32 (rows,) slice on the same device")
+    return out.view(rows)
+
+
+def loglik_rows(recon, target, ltype, likelihood="normal", lam=1.0, scale=0.75, out=None):
+    return _LoglikRows.apply(recon, target, ltype_code(ltype, likelihood), float(scale), float(lam), out)
 
 
 def loglik_weighted_sum(recon, target, ltype, likelihood="normal", lam=1.0, scale=0.75, w_rows=None, w_const=1.0):
@@ -177,10 +187,10 @@ def _catce_geom(recon, target):
 
 class _CatceRows(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, recon, target, lam):
+    def forward(ctx, recon, target, lam, out=None):
         _need_cuda(recon, target)
         x, t, rows, B, C, d, ldx, ldt = _catce_geom(recon.detach(), target.detach())
-        out = torch.empty(rows, dtype=torch.float32, device=recon.device)
+        out = _row_out(out, rows, recon.device)
         stats = torch.empty((rows, 2, d), dtype=torch.float32, device=recon.device)  # cached column statistics
         call("mmvae_catce_rows", 0, _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, C, d, lam, _P(0), 0.0,
              _ptr(out), _P(0), 0, _ptr(stats), _stream())
@@ -196,7 +206,7 @@ class _CatceRows(torch.autograd.Function):
         g = torch.empty((rows, C * d), dtype=x.dtype, device=x.device)
         call("mmvae_catce_rows", 1, _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, C, d, lam, _ptr(w), 0.0,
              _P(0), _ptr(g), C * d, _ptr(stats), _stream())
-        return g.view(shape), None, None
+        return g.view(shape), None, None, None
 
 
 class _CatceWeightedSum(torch.autograd.Function):
@@ -232,8 +242,8 @@ class _CatceWeightedSum(torch.autograd.Function):
         return g.view(ctx.shape), None, gw, None, None
 
 
-def catce_rows(recon, target, lam=1.0):
-    return _CatceRows.apply(recon, target, float(lam))
+def catce_rows(recon, target, lam=1.0, out=None):
+    return _CatceRows.apply(recon, target, float(lam), out)
 
 
 def catce_weighted_sum(recon, target, lam=1.0, w_rows=None, w_const=1.0):
@@ -492,6 +502,77 @@ class _Iwae(torch.autograd.Function):
 
 def iwae_combine(lpz, lq, lpx, beta):
     return _Iwae.apply(lpz, lq, lpx, float(beta))
+
+
+class _IwaeRows(torch.autograd.Function):
+    """IWAE combine over a LIST of likelihood row vectors (index r*L + l, (K*B,) each) read through a pointer table
+    (no stack copy); the backward is one launch and hands every row vector of modality r the same gradient -g*w[r]."""
+
+    @staticmethod
+    def forward(ctx, lpz, lq, beta, L, *rows):
+        _need_cuda(lpz, lq, *rows)
+        M, K, B = lpz.shape
+        f = lambda t: t.detach().float().contiguous()
+        lpz_c, lq_c = f(lpz), f(lq)
+        rows_c = [f(r).reshape(-1) for r in rows]
+        if len(rows_c) != M * L or any(r.numel() != K * B for r in rows_c):
+            raise RuntimeError("mmvae_b200: iwae needs M*L row vectors of K*B elements")
+        ptrs = (ctypes.c_void_p * (M * L))(*[r.data_ptr() for r in rows_c])
+        dev = lpz.device
+        lw = torch.empty((M * K, B), dtype=torch.float32, device=dev)
+        loss_b = torch.empty(B, dtype=torch.float32, device=dev)
+        w = torch.empty((M, K, B), dtype=torch.float32, device=dev)
+        dlq = torch.empty((M, M, K, B), dtype=torch.float32, device=dev)
+        call("mmvae_objective_iwae_ptrs", _ptr(lpz_c), _ptr(lq_c), _P(0), ptrs, M, L, K, B, float(beta), _ptr(lw),
+             _ptr(loss_b), _ptr(w), _ptr(dlq), _stream())
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        call("mmvae_reduce_sum", _ptr(loss_b), B, 1.0, _ptr(loss), _stream())
+        ctx.save_for_backward(w, dlq)
+        ctx.meta = (M, L, K, B, [r.shape for r in rows])
+        ctx.mark_non_differentiable(lw)
+        return loss, lw
+
+    @staticmethod
+    def backward(ctx, g, _glw):
+        w, dlq = ctx.saved_tensors
+        M, L, K, B, shapes = ctx.meta
+        gs = g.detach().float().contiguous()
+        dlpz = torch.empty_like(w)
+        dlq_out = dlq  # scaled in place by g (single-use buffer, like the fused ELBO gradient)
+        call("mmvae_objective_iwae_bwd", _ptr(gs), _ptr(w), _ptr(dlq_out), _ptr(dlpz), w.numel(), dlq_out.numel(), _stream())
+        row_grads = [dlpz[i // L].reshape(shapes[i]) for i in range(M * L)]
+        return (dlpz, dlq_out, None, None) + tuple(row_grads)
+
+
+def iwae_combine_rows(lpz, lq, rows, L, beta):
+    """rows: list of M*L tensors (K*B,), index r*L + l."""
+    return _IwaeRows.apply(lpz, lq, float(beta), int(L), *rows)
+
+
+class _PriorScale(torch.autograd.Function):
+    """s0 = softmax(logits, 1) * D of the learnable prior (reference mmvae_models.py:28-30), one tiny kernel each way."""
+
+    @staticmethod
+    def forward(ctx, logits):
+        _need_cuda(logits)
+        lg = logits.detach().float().contiguous()
+        D = lg.shape[-1]
+        s0 = torch.empty_like(lg)
+        call("mmvae_prior_scale_fwd", _ptr(lg), D, _ptr(s0), _stream())
+        ctx.save_for_backward(s0)
+        return s0
+
+    @staticmethod
+    def backward(ctx, ds0):
+        (s0,) = ctx.saved_tensors
+        d = ds0.detach().float().contiguous()
+        out = torch.empty_like(s0)
+        call("mmvae_prior_scale_bwd", _ptr(s0), _ptr(d), s0.shape[-1], _ptr(out), _stream())
+        return out
+
+
+def prior_scale(logits):
+    return _PriorScale.apply(logits)
 
 
 class _Dreg(torch.autograd.Function):

@@ -176,7 +176,7 @@ class LeafStep:
                                        w_const=w_const)
 
     def _prior(self):
-        return self._mu0, F.softmax(self.pz_logits, dim=1) * self.D
+        return self._mu0, ops.prior_scale(self.pz_logits)
 
     # -- objectives -----------------------------------------------------------------------------------------
     def loss(self):
@@ -230,9 +230,9 @@ class LeafStep:
             z, lq, lpz = ops.moe_logdens(self.mu, self.s, mu0, s0, eps, self.codes, True)
             rows = [self._rows(i) for i in range(len(self.plan))]
         L = len(rows) // M
-        lpx = torch.stack(rows).view(M, L, K, B)
         if self.obj == "iwae":
-            return ops.iwae_combine(lpz, lq, lpx, self.beta)[0]
+            return ops.iwae_combine_rows(lpz, lq, rows, L, self.beta)[0]
+        lpx = torch.stack(rows).view(M, L, K, B)
         return ops.dreg_combine(lpz, lq, lpx, self.group)[0]
 
     def _poe(self):

@@ -500,3 +500,30 @@ def test_bce_logits_fused_decoder_tail(ops, dtype, tol):
     S, _ = ops.loglik_weighted_sum(yc2, t.cuda(), "bce_logits", "normal", 0.8, w_rows=w.cuda())
     S.backward()
     assert rel(yc2.grad, yo.grad) < tol
+
+
+def test_prior_scale_and_iwae_rows(ops):
+    """The folded glue kernels: softmax*D prior scale (fwd/bwd) and the pointer-table IWAE combine + one-launch bwd."""
+    g = torch.Generator().manual_seed(63)
+    lg = torch.randn(1, 37, generator=g)
+    a = lg.clone().requires_grad_(True)
+    ref = torch.softmax(a, 1) * 37
+    w = torch.randn(1, 37, generator=g)
+    (ref * w).sum().backward()
+    b = lg.cuda().requires_grad_(True)
+    out = ops.prior_scale(b)
+    (out * w.cuda()).sum().backward()
+    assert rel(out, ref) < FP32_TOL and rel(b.grad, a.grad) < FP32_TOL
+    M, L, K, B = 2, 2, 7, 45
+    lpz = torch.randn(M, K, B, generator=g) * 3
+    lq = torch.randn(M, M, K, B, generator=g) * 3
+    rows = [torch.randn(K * B, generator=g) * 30 for _ in range(M * L)]
+    x = [t.cuda().requires_grad_(True) for t in [lpz, lq] + rows]
+    loss, _ = ops.iwae_combine(x[0], x[1], torch.stack(x[2:]).view(M, L, K, B), 0.7)
+    (1.5 * loss).backward()
+    y = [t.cuda().requires_grad_(True) for t in [lpz, lq] + rows]
+    loss2, _ = ops.iwae_combine_rows(y[0], y[1], y[2:], L, 0.7)
+    (1.5 * loss2).backward()
+    assert torch.equal(loss, loss2)
+    for p, q in zip(x, y):
+        assert rel(q.grad, p.grad) < 1e-6
