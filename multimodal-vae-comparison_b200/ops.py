@@ -78,6 +78,7 @@ class _LoglikRows(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, recon, target, lt, scale, lam, out=None):
+        ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(recon, target)
         rows, B = recon.shape[0], target.shape[0]
         x, P, ldx = _rows2d(recon.detach(), rows)
@@ -95,6 +96,8 @@ class _LoglikRows(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_rows):
+        if g_rows is None:
+            return None, None, None, None, None, None
         x, t = ctx.saved_tensors
         rows, B, P, ldx, ldt, lt, scale, lam, shape = ctx.meta
         w = g_rows.detach().to(torch.float32).contiguous()
@@ -111,6 +114,7 @@ class _LoglikWeightedSum(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, recon, target, w_rows, w_const, lt, scale, lam):
+        ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(recon, target, w_rows)
         rows, B = recon.shape[0], target.shape[0]
         x, P, ldx = _rows2d(recon.detach(), rows)
@@ -138,6 +142,8 @@ class _LoglikWeightedSum(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gS, _g_rows):
+        if gS is None:
+            return None, None, None, None, None, None, None
         if ctx.g is None:
             raise RuntimeError("mmvae_b200: the fused ELBO gradient buffer is single-use (retain_graph unsupported)")
         g, ctx.g = ctx.g, None
@@ -188,6 +194,7 @@ def _catce_geom(recon, target):
 class _CatceRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, recon, target, lam, out=None):
+        ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(recon, target)
         x, t, rows, B, C, d, ldx, ldt = _catce_geom(recon.detach(), target.detach())
         out = _row_out(out, rows, recon.device)
@@ -200,6 +207,8 @@ class _CatceRows(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_rows):
+        if g_rows is None:
+            return None, None, None, None
         x, t, stats = ctx.saved_tensors
         rows, B, C, d, ldx, ldt, lam, shape = ctx.meta
         w = g_rows.detach().to(torch.float32).contiguous()
@@ -212,6 +221,7 @@ class _CatceRows(torch.autograd.Function):
 class _CatceWeightedSum(torch.autograd.Function):
     @staticmethod
     def forward(ctx, recon, target, w_rows, w_const, lam):
+        ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(recon, target, w_rows)
         x, t, rows, B, C, d, ldx, ldt = _catce_geom(recon.detach(), target.detach())
         out = torch.empty(rows, dtype=torch.float32, device=recon.device)
@@ -233,6 +243,8 @@ class _CatceWeightedSum(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gS, _g_rows):
+        if gS is None:
+            return None, None, None, None, None
         if ctx.g is None:
             raise RuntimeError("mmvae_b200: the fused ELBO gradient buffer is single-use (retain_graph unsupported)")
         g, ctx.g = ctx.g, None
@@ -256,6 +268,7 @@ def catce_weighted_sum(recon, target, lam=1.0, w_rows=None, w_const=1.0):
 class _OsigmaRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, recon, target, lam, group):
+        ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(recon, target)
         rows, B = recon.shape[0], target.shape[0]
         x, P, ldx = _rows2d(recon.detach(), rows)
@@ -279,6 +292,8 @@ class _OsigmaRows(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_rows):
+        if g_rows is None:
+            return None, None, None, None
         x, t, stat = ctx.saved_tensors
         rows, B, P, ldx, ldt, lam, n_total, shape, group = ctx.meta
         w = g_rows.detach().to(torch.float32).contiguous()
@@ -342,6 +357,7 @@ class _LatentDraws(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mu, s, mu0, s0, eps, draws, row_masks):
+        ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(mu, s, mu0, s0, eps, row_masks)
         M, B, Dtot = mu.shape
         arr, ne, npar, nkl = _pack_descs(draws, B)
@@ -428,6 +444,7 @@ class _MoeLogdens(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mu, s, mu0, s0, eps, dists, through_z):
+        ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(mu, s, mu0, s0, eps)
         M, B, D = mu.shape
         K = eps.shape[1]
@@ -474,6 +491,7 @@ class _Iwae(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, lpz, lq, lpx, beta):
+        ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(lpz, lq, lpx)
         M, K, B = lpz.shape
         L = lpx.shape[1]
@@ -495,6 +513,8 @@ class _Iwae(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, _glw):
+        if g is None:
+            return None, None, None, None
         w, dlq = ctx.saved_tensors
         gw = g * w  # (M,K,B) -- tiny
         return -gw, g * dlq, (-gw).unsqueeze(1).expand(-1, ctx.L, -1, -1), None
@@ -510,6 +530,7 @@ class _IwaeRows(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, lpz, lq, beta, L, *rows):
+        ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(lpz, lq, *rows)
         M, K, B = lpz.shape
         f = lambda t: t.detach().float().contiguous()
@@ -536,6 +557,8 @@ class _IwaeRows(torch.autograd.Function):
     def backward(ctx, g, _glw):
         w, dlq = ctx.saved_tensors
         M, L, K, B, shapes = ctx.meta
+        if g is None:
+            return (None, None, None, None) + (None,) * (M * L)
         gs = g.detach().float().contiguous()
         dlpz = torch.empty_like(w)
         dlq_out = dlq  # scaled in place by g (single-use buffer, like the fused ELBO gradient)
@@ -554,6 +577,7 @@ class _PriorScale(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, logits):
+        ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(logits)
         lg = logits.detach().float().contiguous()
         D = lg.shape[-1]
@@ -564,6 +588,8 @@ class _PriorScale(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, ds0):
+        if ds0 is None:
+            return None
         (s0,) = ctx.saved_tensors
         d = ds0.detach().float().contiguous()
         out = torch.empty_like(s0)
@@ -581,6 +607,7 @@ class _Dreg(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, lpz, lq, lpx, group):
+        ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(lpz, lq, lpx)
         M, K, B = lpz.shape
         L = lpx.shape[1]
@@ -606,6 +633,8 @@ class _Dreg(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, _glw):
+        if g is None:
+            return None, None, None, None
         wt, lq_soft = ctx.saved_tensors
         M, L, K, B = ctx.meta
         c = (g / M) * wt  # (M,K): -dloss/dlw
