@@ -186,6 +186,17 @@ MMVAE_API int mmvae_latent_draws_bwd(const float* mu, const float* s, int M, int
                            const float* dpar_loc, const float* dpar_scale,
                            float* dmu, float* ds, float* dprior_ws, float* dmu0, float* ds0, void* stream);
 
+/* Element-wise KL(q || N(loc0, scale0)): the (n, D) tensor reference calc_kld returns (objectives.py:148-161,
+ * utils.py:399-405) and the per-dimension KL tables of the analysis hooks use (utils.py:130-162).  q is Normal or
+ * Laplace (dist), the prior row (D) is broadcast over n.  The backward's prior gradient is reduced over n in two
+ * stages (shared-memory accumulation inside a CTA, ordered sum across CTAs through ws). */
+MMVAE_API int mmvae_kl_elementwise_fwd(const float* loc, const float* scale, const float* loc0, const float* scale0,
+                             int dist, int64_t n, int D, float* out, void* stream);
+MMVAE_API int64_t mmvae_kl_elementwise_ws_floats(int64_t n, int D);
+MMVAE_API int mmvae_kl_elementwise_bwd(const float* loc, const float* scale, const float* loc0, const float* scale0,
+                             int dist, int64_t n, int D, const float* upstream, float* dloc, float* dscale,
+                             float* ws, float* dloc0, float* dscale0, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * MoE sample + log-densities (fused): replaces MOE.forward's rsample (mmvae_models.py:99), the importance
  * terms of the ELBO branch (:56-62) and the log p(z) / log-mean q_j(z) terms of MultimodalObjective.iwae /

@@ -41,6 +41,9 @@ SIGNATURES = {
     "mmvae_latent_draws_bwd_ws_floats": (c_i64, [c_i64, c_i]),
     "mmvae_latent_draws_bwd": (c_i, [c_p, c_p, c_i, c_i64, c_i, ctypes.POINTER(DrawDesc), c_i, c_p, c_p, c_p, c_p,
                                      c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "mmvae_kl_elementwise_fwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i64, c_i, c_p, c_p]),
+    "mmvae_kl_elementwise_ws_floats": (c_i64, [c_i64, c_i]),
+    "mmvae_kl_elementwise_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i64, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "mmvae_moe_logdens_fwd": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_i, ctypes.POINTER(ctypes.c_int32), c_p, c_p, c_p,
                                     c_p, c_p, c_p, c_p]),
     "mmvae_moe_logdens_bwd_ws_floats": (c_i64, [c_i64, c_i, c_i]),

@@ -225,6 +225,42 @@ __global__ void __launch_bounds__(kWarps * 32) draws_bwd_kernel(const DrawsParam
     }
 }
 
+// Element-wise KL(q || N(loc0, scale0)) for a (n, D) posterior against a (D) prior row -- the (B, D) tensor that
+// calc_kld returns in the reference (objectives.py:148-161) and that the per-dimension analysis tables need
+// (utils.py:130-162).  mode 0: forward; mode 1: backward (dl, ds and per-CTA partials of the prior gradient).
+__global__ void __launch_bounds__(256) kl_elem_kernel(const float* __restrict__ loc, const float* __restrict__ scale,
+                                                      const float* __restrict__ loc0, const float* __restrict__ scale0,
+                                                      int laplace, int64_t n, int D, float* __restrict__ out,
+                                                      const float* __restrict__ up, float* __restrict__ dloc,
+                                                      float* __restrict__ dscale, float* __restrict__ ws) {
+    extern __shared__ float pri[];  // 2*D prior-gradient accumulators of this CTA (backward only)
+    const bool bwd = up != nullptr;
+    if (bwd) {
+        for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) pri[i] = 0.f;
+        __syncthreads();
+    }
+    const int64_t total = n * D;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % D);
+        const float l = loc[i], sg = scale[i], m0 = __ldg(loc0 + c), s0 = __ldg(scale0 + c);
+        if (!bwd) {
+            out[i] = kl_value(laplace != 0, l, sg, m0, s0);
+        } else {
+            float dl, dsg, dm0, ds0;
+            kl_grads(laplace != 0, l, sg, m0, s0, dl, dsg, dm0, ds0);
+            const float u = up[i];
+            dloc[i] = u * dl;
+            dscale[i] = u * dsg;
+            atomicAdd(&pri[c], u * dm0);  // shared-memory accumulation, the cross-CTA stage is ordered
+            atomicAdd(&pri[D + c], u * ds0);
+        }
+    }
+    if (bwd) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) ws[(size_t)blockIdx.x * 2 * D + i] = pri[i];
+    }
+}
+
 static unsigned draws_grid(int64_t B) {
     int64_t g = (B + kWarps - 1) / kWarps;
     const int64_t cap = (int64_t)kNumSMs * 4;
@@ -303,6 +339,43 @@ extern "C" int mmvae_latent_draws_bwd(const float* mu, const float* s, int M, in
     MMVAE_LAUNCH_CHECK();
     if (dmu0 && ds0) {
         partial_sum_kernel<<<2 * Dtot, 128, 0, st>>>(dprior_ws, (int)grid, 2 * Dtot, Dtot, dmu0, ds0);
+        MMVAE_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+static unsigned kl_grid(int64_t total) {
+    int64_t g = (total + 255) / 256;
+    const int64_t cap = (int64_t)kNumSMs * 4;
+    return (unsigned)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+extern "C" int64_t mmvae_kl_elementwise_ws_floats(int64_t n, int D) { return (int64_t)kl_grid(n * D) * 2 * D; }
+
+extern "C" int mmvae_kl_elementwise_fwd(const float* loc, const float* scale, const float* loc0, const float* scale0,
+                                        int dist, int64_t n, int D, float* out, void* stream) {
+    if (!loc || !scale || !loc0 || !scale0 || !out || n <= 0 || D <= 0) return MMVAE_E_ARG;
+    if (dist != MMVAE_NORMAL && dist != MMVAE_LAPLACE) return MMVAE_E_ENUM;
+    kl_elem_kernel<<<kl_grid(n * D), 256, 0, (cudaStream_t)stream>>>(loc, scale, loc0, scale0, dist, n, D, out, nullptr,
+                                                                     nullptr, nullptr, nullptr);
+    MMVAE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mmvae_kl_elementwise_bwd(const float* loc, const float* scale, const float* loc0, const float* scale0,
+                                        int dist, int64_t n, int D, const float* upstream, float* dloc, float* dscale,
+                                        float* ws, float* dloc0, float* dscale0, void* stream) {
+    if (!loc || !scale || !loc0 || !scale0 || !upstream || !dloc || !dscale || !ws || n <= 0 || D <= 0)
+        return MMVAE_E_ARG;
+    if (dist != MMVAE_NORMAL && dist != MMVAE_LAPLACE) return MMVAE_E_ENUM;
+    if (D > 4096) return MMVAE_E_LIMIT;
+    const unsigned grid = kl_grid(n * D);
+    cudaStream_t st = (cudaStream_t)stream;
+    kl_elem_kernel<<<grid, 256, 2 * D * sizeof(float), st>>>(loc, scale, loc0, scale0, dist, n, D, nullptr, upstream,
+                                                             dloc, dscale, ws);
+    MMVAE_LAUNCH_CHECK();
+    if (dloc0 && dscale0) {
+        partial_sum_kernel<<<2 * D, 128, 0, st>>>(ws, (int)grid, 2 * D, D, dloc0, dscale0);
         MMVAE_LAUNCH_CHECK();
     }
     return 0;

@@ -646,6 +646,48 @@ def dreg_combine(lpz, lq, lpx, group=None):
     return _Dreg.apply(lpz, lq, lpx, group)
 
 
+class _KlElementwise(torch.autograd.Function):
+    """include/mmvae_b200.h mmvae_kl_elementwise_{fwd,bwd}: (n, D) KL(q || N(loc0, scale0)), prior broadcast over n."""
+
+    @staticmethod
+    def forward(ctx, loc, scale, loc0, scale0, dist_code):
+        ctx.set_materialize_grads(False)
+        _need_cuda(loc, scale, loc0, scale0)
+        D = loc.shape[-1]
+        f = lambda t: t.detach().float().contiguous()
+        l, sg = f(loc).reshape(-1, D), f(scale).reshape(-1, D)
+        l0 = f(loc0).reshape(-1).expand(D).contiguous() if loc0.numel() == 1 else f(loc0).reshape(-1)
+        s0 = f(scale0).reshape(-1).expand(D).contiguous() if scale0.numel() == 1 else f(scale0).reshape(-1)
+        if l0.numel() != D or s0.numel() != D:
+            raise RuntimeError("mmvae_b200: the prior must broadcast as a single (D) row")
+        out = torch.empty_like(l)
+        call("mmvae_kl_elementwise_fwd", _ptr(l), _ptr(sg), _ptr(l0), _ptr(s0), int(dist_code), l.shape[0], D, _ptr(out),
+             _stream())
+        ctx.save_for_backward(l, sg, l0, s0)
+        ctx.meta = (int(dist_code), loc.shape, scale.shape, loc0.shape, scale0.shape)
+        return out.view(loc.shape)
+
+    @staticmethod
+    def backward(ctx, up):
+        if up is None:
+            return None, None, None, None, None
+        l, sg, l0, s0 = ctx.saved_tensors
+        code, sh_l, sh_s, sh_l0, sh_s0 = ctx.meta
+        n, D = l.shape
+        u = up.detach().float().contiguous().reshape(n, D)
+        dl, ds = torch.empty_like(l), torch.empty_like(sg)
+        ws = torch.empty(_lib.load().mmvae_kl_elementwise_ws_floats(n, D), dtype=torch.float32, device=l.device)
+        dp = torch.empty(2, D, dtype=torch.float32, device=l.device)
+        call("mmvae_kl_elementwise_bwd", _ptr(l), _ptr(sg), _ptr(l0), _ptr(s0), code, n, D, _ptr(u), _ptr(dl), _ptr(ds),
+             _ptr(ws), _ptr(dp[0]), _ptr(dp[1]), _stream())
+        red = lambda g, shp: g.sum().reshape(shp) if len(shp) == 0 or int(torch.tensor(shp).prod()) == 1 else g.reshape(shp)
+        return dl.view(sh_l), ds.view(sh_s), red(dp[0], sh_l0), red(dp[1], sh_s0), None
+
+
+def kl_elementwise(loc, scale, loc0, scale0, laplace=False):
+    return _KlElementwise.apply(loc, scale, loc0, scale0, 1 if laplace else 0)
+
+
 def reduce_sum(x, scale=1.0):
     """Deterministic single-CTA sum (forward only helper for logging values)."""
     _need_cuda(x)

@@ -527,3 +527,31 @@ def test_prior_scale_and_iwae_rows(ops):
     assert torch.equal(loss, loss2)
     for p, q in zip(x, y):
         assert rel(q.grad, p.grad) < 1e-6
+
+
+@pytest.mark.parametrize("laplace", [False, True])
+def test_kl_elementwise_and_objective_api(ops, laplace):
+    """calc_kld / weighted_group_kld of the objective plugin (reference objectives.py:148-201) on the element-wise KL
+    kernel, against torch.distributions.kl (what utils.kl_divergence dispatches to)."""
+    import torch.distributions as dist
+    import mmvae_b200
+    import mmvae_b200.synthetic as syn
+    g = torch.Generator().manual_seed(71)
+    B, D = 37, 16
+    mu, s = syn.make_posterior(g, B, D)
+    lg = torch.randn(1, D, generator=g) * 0.3
+    w = torch.randn(B, D, generator=g)
+    Q = dist.Laplace if laplace else dist.Normal
+
+    def run(dev):
+        a, b, c = mu.clone().to(dev).requires_grad_(True), s.clone().to(dev).requires_grad_(True), lg.clone().to(dev).requires_grad_(True)
+        prior = dist.Normal(torch.zeros(1, D, device=dev), torch.softmax(c, 1) * D)
+        if dev == "cpu":
+            kl = dist.kl_divergence(Q(a, b), prior)
+        else:
+            kl = mmvae_b200.MultimodalObjective("elbo").calc_kld(Q(a, b), prior)
+        (kl * w.to(dev)).sum().backward()
+        return kl, a.grad, b.grad, c.grad
+    r, o = run("cpu"), run("cuda")
+    for x, y in zip(o, r):
+        assert rel(x, y) < FP32_TOL
