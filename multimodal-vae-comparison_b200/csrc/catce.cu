@@ -27,6 +27,25 @@ struct CatceParams {
 
 __host__ __device__ __forceinline__ size_t up16(size_t v) { return (v + 15) & ~(size_t)15; }
 
+// n elements global -> shared with 4-byte cp.async when both addresses are 4-byte aligned (always for fp32; for bf16
+// when the row starts on an even element), element-wise otherwise.
+template <typename T>
+__device__ __forceinline__ void stage_row_async(T* sdst, const T* gsrc, int n, int tid, int nthreads) {
+    constexpr int per = 4 / (int)sizeof(T);  // elements per 4-byte word
+    const bool ok = ((reinterpret_cast<uintptr_t>(gsrc) | reinterpret_cast<uintptr_t>(sdst)) & 3u) == 0;
+    if (ok) {
+        const int words = n / per;
+        const uint32_t s0 = smem_u32(sdst);
+        for (int w = tid; w < words; w += nthreads)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s0 + 4u * w),
+                         "l"(reinterpret_cast<const char*>(gsrc) + 4 * (size_t)w)
+                         : "memory");
+        for (int e = words * per + tid; e < n; e += nthreads) sdst[e] = gsrc[e];
+    } else {
+        for (int e = tid; e < n; e += nthreads) sdst[e] = gsrc[e];
+    }
+}
+
 template <typename TX, typename TT, int MODE>  // 0 fwd, 1 bwd, 2 fused
 __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -62,15 +81,17 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
         if (warp == 0) mbar_wait(bar, 0);
         __syncthreads();
     } else {
+        // rows that miss TMA's 16-byte alignment: 4-byte cp.async (LDGSTS) -- asynchronous and register free, so a
+        // CTA keeps its whole slab in flight (scalar staging loads left the SM with ~16 KB in flight: ncu r1,
+        // long-scoreboard bound at 1.5 TB/s on the CUB caption rows); plain loads only for odd 2-byte rows
         for (int r = 0; r < nrows; ++r) {
             const TX* xr = xg + (row0 + r) * p.ldx;
             const TT* tr = tg + ((row0 + r) % p.B) * p.ldt;
-#pragma unroll 8
-            for (int e = threadIdx.x; e < n; e += blockDim.x) {
-                sx[r * n + e] = xr[e];
-                st[r * n + e] = tr[e];
-            }
+            stage_row_async(sx + (size_t)r * n, xr, n, threadIdx.x, blockDim.x);
+            stage_row_async(st + (size_t)r * n, tr, n, threadIdx.x, blockDim.x);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
     }
     const bool live = rl < nrows;
@@ -223,7 +244,6 @@ static size_t catce_smem(int R, int W, int n, int d, int sx, int st) {
 template <typename TX, typename TT>
 static int launch_catce(int mode, CatceParams p, cudaStream_t st) {
     const int n = p.C * p.d, sx = (int)sizeof(TX), stt = (int)sizeof(TT);
-    // warps per row: split long class axes; rows per CTA: fill ~8 warps, prefer a TMA-able (16 B multiple) run
     const bool fast_bwd = (mode == 1 && p.stats != nullptr);
     // warps per row split the class axis (short dependency chains); the cached-statistics backward has no per-row
     // reduction and simply strides all warps over the staged class rows
