@@ -7,6 +7,8 @@
 //     (R is chosen so that R*C*d*elemsize is a multiple of 16); otherwise by coalesced element loads;
 //   * W warps per row split the class axis (W = 1 for short class axes: then there is no block barrier on the compute
 //     path at all); lanes own columns j, so the smem walk along the class axis is conflict free;
+//   * (measured r1: staging only x and reading the L2-resident targets from global halves the smem footprint but
+//     slowed the streaming backward from 21.7 to 35.6 us and left the forward unchanged -- both slabs stay staged)
 //   * two passes over the class axis (max, then exp-sum / target sums: one MUFU.EX2 per element), warp-shuffle row
 //     sum; the gradient is written in place over the staged x and leaves through one TMA bulk store.
 #include "common.cuh"

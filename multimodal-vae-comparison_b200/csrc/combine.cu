@@ -44,47 +44,62 @@ __device__ __forceinline__ float lw_value(const CombParams& p, int r, int k, int
     return v - beta * lme_j(p, r, k, b, vals, mx, se);
 }
 
-// CTA: 32 consecutive batch rows (lanes, coalesced along b) x up to 32 warps that split the M*K (r,k) pairs.  The
-// log-weights are parked in shared memory between the logsumexp pass and the weight pass; the (r,k) logsumexp is
-// an online-softmax merge across warps.
-__global__ void __launch_bounds__(1024) iwae_kernel(const CombParams p) {
+// CTA: 8 consecutive batch rows x 32 (r,k) slots (256 threads).  A warp covers 8 b (one 32-byte sector per row vector
+// access) x 4 slots, so B = 256 already yields 32 CTAs (the 32-b tile of the first version left 140 SMs idle and ran
+// as one latency chain: 15 us).  The log-weights are parked in shared memory between the logsumexp pass and the
+// weight pass; the (r,k) logsumexp is an online-softmax merge: warp shuffles across the 4 slots, then smem across
+// the 8 warps ("warp-shuffle reductions for the K-logsumexp").
+constexpr int kIwaeBT = 8, kIwaeSlots = 32;
+
+__device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2) {
+    const float nm = fmaxf(m, m2);
+    if (nm == -INFINITY) {
+        s = 0.f;
+    } else {
+        s = s * __expf(m - nm) + s2 * __expf(m2 - nm);
+    }
+    m = nm;
+}
+
+__global__ void __launch_bounds__(kIwaeBT * kIwaeSlots) iwae_kernel(const CombParams p) {
     extern __shared__ float sm[];
     const int n = p.M * p.K;
-    const int nw = blockDim.x >> 5;
-    float* s_lw = sm;               // n x 32
-    float* s_m = s_lw + n * 32;     // nw x 32
-    float* s_s = s_m + nw * 32;     // nw x 32
+    float* s_lw = sm;                 // n x 8
+    float* s_m = s_lw + n * kIwaeBT;  // 8 warps x 8
+    float* s_s = s_m + 8 * kIwaeBT;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t b = (int64_t)blockIdx.x * 32 + lane;
+    const int bl = lane & 7, slot = wid * 4 + (lane >> 3);
+    const int64_t b = (int64_t)blockIdx.x * kIwaeBT + bl;
     const bool ok = b < p.B;
     float vals[MMVAE_MAX_MODS];
     float run_m = -INFINITY, run_s = 0.f;
     if (ok) {
-        for (int q = wid; q < n; q += nw) {
+        for (int q = slot; q < n; q += kIwaeSlots) {
             const int r = q / p.K, k = q - r * p.K;
             float mx, se;
             const float lw = lw_value(p, r, k, b, p.beta, vals, mx, se);
             p.lw[((int64_t)r * p.K + k) * p.B + b] = lw;
-            s_lw[q * 32 + lane] = lw;
-            const float nm = fmaxf(run_m, lw);
-            run_s = run_s * __expf(run_m - nm) + __expf(lw - nm);
-            run_m = nm;
+            s_lw[q * kIwaeBT + bl] = lw;
+            lse_merge(run_m, run_s, lw, 1.0f);
         }
     }
-    s_m[wid * 32 + lane] = run_m;
-    s_s[wid * 32 + lane] = run_s;
+#pragma unroll
+    for (int o = 8; o < 32; o <<= 1)
+        lse_merge(run_m, run_s, __shfl_xor_sync(0xffffffffu, run_m, o), __shfl_xor_sync(0xffffffffu, run_s, o));
+    if (lane < 8) {
+        s_m[wid * kIwaeBT + bl] = run_m;
+        s_s[wid * kIwaeBT + bl] = run_s;
+    }
     __syncthreads();
-    float tm = -INFINITY;
-    for (int w = 0; w < nw; ++w) tm = fmaxf(tm, s_m[w * 32 + lane]);
-    float ts = 0.f;
-    for (int w = 0; w < nw; ++w)
-        if (s_s[w * 32 + lane] > 0.f) ts += s_s[w * 32 + lane] * __expf(s_m[w * 32 + lane] - tm);
+    float tm = -INFINITY, ts = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) lse_merge(tm, ts, s_m[w * kIwaeBT + bl], s_s[w * kIwaeBT + bl]);
     const float lse = tm + logf(ts);
     if (!ok) return;
-    if (wid == 0) p.loss_b[b] = -(lse - logf((float)n));
-    for (int q = wid; q < n; q += nw) {
+    if (threadIdx.x < kIwaeBT) p.loss_b[b] = -(lse - logf((float)n));
+    for (int q = slot; q < n; q += kIwaeSlots) {
         const int r = q / p.K, k = q - r * p.K;
-        const float wv = expf(s_lw[q * 32 + lane] - lse);
+        const float wv = expf(s_lw[q * kIwaeBT + bl] - lse);
         p.w[((int64_t)r * p.K + k) * p.B + b] = wv;
         if (p.dlq) {
             float mx, se;
@@ -267,14 +282,13 @@ extern "C" int mmvae_objective_iwae_ptrs(const float* lpz, const float* lq, cons
     if (!lw || !loss_b || !w) return MMVAE_E_ARG;
     p.beta = beta; p.lw = lw; p.loss_b = loss_b; p.w = w; p.dlq = dlq;
     const int n = M * K;
-    int nw = n < 32 ? n : 32;
-    const size_t smem = (size_t)(n * 32 + 2 * nw * 32) * sizeof(float);
+    const size_t smem = (size_t)(n * kIwaeBT + 2 * 8 * kIwaeBT) * sizeof(float);
     if (smem > 200 * 1024) return MMVAE_E_LIMIT;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(iwae_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    iwae_kernel<<<(unsigned)((B + 31) / 32), nw * 32, smem, (cudaStream_t)stream>>>(p);
+    iwae_kernel<<<(unsigned)((B + kIwaeBT - 1) / kIwaeBT), kIwaeBT * kIwaeSlots, smem, (cudaStream_t)stream>>>(p);
     MMVAE_LAUNCH_CHECK();
     return 0;
 }
