@@ -13,10 +13,18 @@ enum { MODE_FWD = 0, MODE_BWD = 1, MODE_FUSED = 2 };
 
 constexpr int kThreads = 256;
 // 128-bit loads in flight per thread and tensor.
+// tuning knobs (tools/tune_loglik.sh compiles variants with -D and times them on the box)
+#ifndef MMVAE_FWD_UNROLL
+#define MMVAE_FWD_UNROLL 4
+#endif
+#ifndef MMVAE_FWD_MINBLOCKS
+#define MMVAE_FWD_MINBLOCKS 5  // r1: 77.6 -> 71.8 us for the C2 forward (5 CTAs of 256 threads per SM, <= 51 registers)
+#endif
 template <int MODE>
 struct Tune {
-    static constexpr int kUnroll = 4;      // measured: 2 in flight / 32 regs / 8 CTAs per SM was 6% slower for MODE 0
-    static constexpr int kMinBlocks = 4;
+    // measured r1 (see profiles/r1_tune_loglik_fwd.txt)
+    static constexpr int kUnroll = (MODE == 0) ? MMVAE_FWD_UNROLL : 4;
+    static constexpr int kMinBlocks = (MODE == 0) ? MMVAE_FWD_MINBLOCKS : 4;
 };
 constexpr int kUnrollMax = 4;
 
