@@ -191,7 +191,6 @@ def cpu_baseline(args):
 
 
 def plugin_e2e(cfg, B, dev, steps, fused_tail=False):
-    import math
     import torch
     import mmvae_b200
     import mmvae_b200.synthetic as syn

@@ -12,7 +12,6 @@ tests/ and by bench.py's cpu_baseline leg.
 import math
 
 import torch
-import torch.nn.functional as F
 
 from . import ops
 from . import synthetic as syn

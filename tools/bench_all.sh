@@ -1,6 +1,7 @@
 #!/bin/bash
 # r1 helper: bench every BASELINE.json configuration at N=1 (run under gpurun); one JSON line per workload
 set -u
+cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 : > gpurun_out/bench_all.jsonl
 python bench.py --workload c2_moe_iwae_cdsprites_l5 --steps 30 --warmup 5 >> gpurun_out/bench_all.jsonl 2>> gpurun_out/bench_all.err
