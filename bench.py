@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -97,7 +97,9 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "how": "nvidia-smi -lms 20 from the start of the timed region; the same step loop keeps running "
+                       "(untimed) until >= 0.3 s of load have been sampled"}
 
 
 class KernelTimer:
@@ -309,7 +311,14 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    t_load = time.perf_counter()
     ms = timed(K_, one)
+    # the timed region is only a few milliseconds: keep the identical load running so that the clock / throttle record
+    # covers a representative stretch under load (not timed, not counted)
+    while time.perf_counter() - t_load < 0.3:
+        for _ in range(10):
+            one()
+        torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     value = B * world * K_ / (ms / 1e3)
 
