@@ -398,6 +398,23 @@ class MoPOE(TorchMMVAE):
             px_d[mod] = vae.px_z(*vae.dec(z_d[mod]))
         return self.make_output_dict(qz_d, px_d, z_d, qz_joint)
 
+    def reweight_weights(self, w):
+        """mmvae_models.py:377-378."""
+        return w / w.sum()
+
+    def poe_fusion(self, mus, logvars):
+        """mmvae_models.py:385-394 on a (m, B, D) stack of the subset's experts: the prior expert (0, 0) is appended
+        only when the subset holds every modality; returns [(1,B,D) mu, (1,B,D) var-as-scale]."""
+        m = mus.shape[0]
+        res = ops.latent_draws(mus, logvars, None, None, None,
+                               [Draw(mods=tuple(range(m)), prior=(m == len(self.vaes)), width=mus.shape[-1],
+                                     want_params=True)])
+        return [res[0]["loc"].unsqueeze(0), res[0]["scale"].unsqueeze(0)]
+
+    def moe_fusion(self, mus, logvars, weights):
+        """mmvae_models.py:380-383."""
+        return self.mixture_component_selection(mus, logvars, self.reweight_weights(weights))
+
     def mixture_component_selection(self, mus, logvars, w_modalities=None):
         """mmvae_models.py:396-410 on a (S, n, ...) stack: contiguous chunks of dim 1, chunk k from component k."""
         S, n = mus.shape[0], mus.shape[1]

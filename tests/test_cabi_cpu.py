@@ -135,3 +135,20 @@ def test_algorithmic_bytes_match_survey():
     # C5: bf16 reconstructions + gradients (2R) against fp32 targets (T): 3 terms per modality, 8 bytes per feature
     c5 = W.algorithmic_bytes(dict(syn.WORKLOADS["c5_dmvae_elbo_cub"]), torch.bfloat16)
     assert abs(c5 - 3 * 8 * (12288 + 6642)) / c5 < 0.01
+
+
+def test_helper_module_matches_reference_semantics(golden):
+    import mmvae_b200.utils as U
+    from oracle import refmath
+    v = torch.randn(6, 5)
+    assert torch.equal(U.log_mean_exp(v), refmath.log_mean_exp(v))
+    assert U.combinatorial(["a", "b", "c"]) == [("a", "b"), ("a", "c"), ("b", "c")]
+    batch = {"mod_1": {"data": torch.zeros(3, 2), "masks": None, "categorical": False},
+             "mod_2": {"data": torch.ones(3, 4), "masks": torch.ones(3, 4, dtype=torch.bool), "categorical": True}}
+    subs = U.subsample_input_modalities(batch)
+    assert len(subs) == 3 and U.find_out_batch_size(subs[1]) == 3
+    assert subs[0]["mod_2"]["data"] is None and subs[0]["mod_2"]["masks"] is None and subs[0]["mod_2"]["categorical"] is True
+    assert subs[2]["mod_1"]["data"] is batch["mod_1"]["data"]  # shared, not deep-copied
+    import torch.distributions as dist
+    p, q = dist.Normal(torch.zeros(4, 3), torch.ones(4, 3) * 0.5), dist.Normal(torch.zeros(1, 3), torch.ones(1, 3))
+    assert torch.allclose(U.kl_divergence(p, q), refmath.kl_normal_normal(p.loc, p.scale, q.loc, q.scale))  # CPU: torch registry

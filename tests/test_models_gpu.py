@@ -250,3 +250,25 @@ def test_unimodal_elbo_matches_reference_golden(golden):
         assert _rel(o2["loss"], ref["loss"]) < TOL
         with pytest.raises(NotImplementedError):
             mmvae_b200.UnimodalObjective("iwae").calculate_loss(None, None, None, None, None, None)
+
+
+def test_mopoe_fusion_methods_match_oracle():
+    """MoPOE.poe_fusion / moe_fusion / mixture_component_selection as standalone methods (mmvae_models.py:377-410)."""
+    import mmvae_b200
+    from oracle import refmath
+    case = [c for c in cases.case_list() if c["name"] == "mopoe_elbo_m3"][0]
+    model = mmvae_b200.mopoe(cases.build_vaes(case, "cuda"), case["D"], {"obj": "elbo", "beta": 1.0, "K": 1}, None).cuda()
+    g = torch.Generator().manual_seed(3)
+    B, D = 16, case["D"]
+    mus, lvs = torch.randn(3, B, D, generator=g), torch.rand(3, B, D, generator=g)
+    mu_g, var_g = model.poe_fusion(mus.cuda(), lvs.cuda())
+    mu_r, var_r = refmath.product_of_experts(torch.cat((mus, torch.zeros(1, B, D))), torch.cat((lvs, torch.zeros(1, B, D))))
+    assert mu_g.shape == (1, B, D) and _rel(mu_g[0], mu_r) < TOL and _rel(var_g[0], var_r) < TOL
+    mu_g, var_g = model.poe_fusion(mus[:2].cuda(), lvs[:2].cuda())  # partial subset: no prior expert
+    mu_r, var_r = refmath.product_of_experts(mus[:2], lvs[:2])
+    assert _rel(mu_g[0], mu_r) < TOL and _rel(var_g[0], var_r) < TOL
+    S = 7
+    stack = torch.randn(S, B, D, generator=g)
+    sel, _ = model.moe_fusion(stack.cuda(), stack.cuda(), torch.ones(S).cuda() / S)
+    ref_sel, _ = refmath.mixture_component_selection(stack, stack, torch.ones(S) / S)
+    assert torch.equal(sel.cpu(), ref_sel)  # index work: bit exact
