@@ -234,18 +234,20 @@ __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_bwd_kernel(const MoePar
 // cross-warp combine.  r1 ncu on C4 (D=64, K=50): the smem-staged kernels executed 35 M / 44 M warp instructions
 // (~175 per column, constants re-read and accumulators read-modify-written in smem inside the loop).
 // ---------------------------------------------------------------------------------------------------------
-template <int MT, int NC>
+// LM: 0 = every posterior Normal, 1 = every posterior Laplace, 2 = mixed (decided at run time per modality);
+// FULL: D == 32*NC, every lane owns NC valid columns (no column guards, no divergence around the shuffles).
+template <int MT, int NC, int LM, bool FULL>
 __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_fwd_reg_kernel(const MoeParams p) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     bool lap[MT];
 #pragma unroll
-    for (int j = 0; j < MT; ++j) lap[j] = p.dist[j] == MMVAE_LAPLACE;
+    for (int j = 0; j < MT; ++j) lap[j] = LM == 2 ? (p.dist[j] == MMVAE_LAPLACE) : (LM == 1);
     float pmu[NC], pinv[NC], pcst[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
         const int c = lane + 32 * i;
-        const float sg = c < p.D ? __ldg(p.s0 + c) : 1.f;
-        pmu[i] = c < p.D ? __ldg(p.mu0 + c) : 0.f;
+        const float sg = (FULL || c < p.D) ? __ldg(p.s0 + c) : 1.f;
+        pmu[i] = (FULL || c < p.D) ? __ldg(p.mu0 + c) : 0.f;
         pinv[i] = 1.0f / sg;
         pcst[i] = -logf(sg) - kLogSqrt2Pi;
     }
@@ -257,8 +259,8 @@ __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_fwd_reg_kernel(const Mo
             for (int i = 0; i < NC; ++i) {
                 const int c = lane + 32 * i;
                 const int64_t o = ((int64_t)j * p.B + b) * p.D + c;
-                const float sg = c < p.D ? __ldg(p.s + o) : 1.f;
-                rmu[j][i] = c < p.D ? __ldg(p.mu + o) : 0.f;
+                const float sg = (FULL || c < p.D) ? __ldg(p.s + o) : 1.f;
+                rmu[j][i] = (FULL || c < p.D) ? __ldg(p.mu + o) : 0.f;
                 rsig[j][i] = sg;
                 rinv[j][i] = 1.0f / sg;
                 rcst[j][i] = lap[j] ? -logf(2.0f * sg) : -logf(sg) - kLogSqrt2Pi;
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_fwd_reg_kernel(const Mo
 #pragma unroll
                 for (int i = 0; i < NC; ++i) {
                     const int c = lane + 32 * i;
-                    e[r][i] = c < p.D ? __ldg(p.eps + (((int64_t)r * p.K + k) * p.B + b) * p.D + c) : 0.f;
+                    e[r][i] = (FULL || c < p.D) ? __ldg(p.eps + (((int64_t)r * p.K + k) * p.B + b) * p.D + c) : 0.f;
                 }
 #pragma unroll
             for (int r = 0; r < MT; ++r) {
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_fwd_reg_kernel(const Mo
 #pragma unroll
                 for (int i = 0; i < NC; ++i) {
                     const int c = lane + 32 * i;
-                    if (c < p.D) {
+                    if (FULL || c < p.D) {
                         const float zz = rmu[r][i] + eff_noise(e[r][i], lap[r]) * rsig[r][i];
                         p.z[base + c] = zz;
 #pragma unroll
@@ -305,20 +307,20 @@ __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_fwd_reg_kernel(const Mo
     }
 }
 
-template <int MT, int NC>
+template <int MT, int NC, int LM, bool FULL>
 __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_bwd_reg_kernel(const MoeParams p) {
     extern __shared__ float sm[];  // nw x (2*MT*NC + 2*NC) x 32 : per-warp register dumps for the combine
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     constexpr int kAcc = 2 * MT * NC, kPri = 2 * NC, kPer = (kAcc + kPri) * 32;
     bool lap[MT];
 #pragma unroll
-    for (int j = 0; j < MT; ++j) lap[j] = p.dist[j] == MMVAE_LAPLACE;
+    for (int j = 0; j < MT; ++j) lap[j] = LM == 2 ? (p.dist[j] == MMVAE_LAPLACE) : (LM == 1);
     float pmu[NC], pinv[NC], q_mu[NC], q_s[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
         const int c = lane + 32 * i;
-        pmu[i] = c < p.D ? __ldg(p.mu0 + c) : 0.f;
-        pinv[i] = 1.0f / (c < p.D ? __ldg(p.s0 + c) : 1.f);
+        pmu[i] = (FULL || c < p.D) ? __ldg(p.mu0 + c) : 0.f;
+        pinv[i] = 1.0f / ((FULL || c < p.D) ? __ldg(p.s0 + c) : 1.f);
         q_mu[i] = 0.f;
         q_s[i] = 0.f;
     }
@@ -330,8 +332,8 @@ __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_bwd_reg_kernel(const Mo
             for (int i = 0; i < NC; ++i) {
                 const int c = lane + 32 * i;
                 const int64_t o = ((int64_t)j * p.B + b) * p.D + c;
-                const float sg = c < p.D ? __ldg(p.s + o) : 1.f;
-                rmu[j][i] = c < p.D ? __ldg(p.mu + o) : 0.f;
+                const float sg = (FULL || c < p.D) ? __ldg(p.s + o) : 1.f;
+                rmu[j][i] = (FULL || c < p.D) ? __ldg(p.mu + o) : 0.f;
                 rsig[j][i] = sg;
                 rinv[j][i] = 1.0f / sg;
                 a_mu[j][i] = 0.f;
@@ -349,15 +351,15 @@ __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_bwd_reg_kernel(const Mo
                 for (int i = 0; i < NC; ++i) {
                     const int c = lane + 32 * i;
                     const int64_t o = (((int64_t)r * p.K + k) * p.B + b) * p.D + c;
-                    e[r][i] = c < p.D ? __ldg(p.eps + o) : 0.f;
-                    dzx[r][i] = (c < p.D && p.dz_ext) ? __ldg(p.dz_ext + o) : 0.f;
+                    e[r][i] = (FULL || c < p.D) ? __ldg(p.eps + o) : 0.f;
+                    dzx[r][i] = ((FULL || c < p.D) && p.dz_ext) ? __ldg(p.dz_ext + o) : 0.f;
                 }
             }
 #pragma unroll
             for (int r = 0; r < MT; ++r)
 #pragma unroll
                 for (int i = 0; i < NC; ++i) {
-                    if (lane + 32 * i < p.D) {
+                    if (FULL || lane + 32 * i < p.D) {
                         const float ef = eff_noise(e[r][i], lap[r]);
                         const float zz = rmu[r][i] + ef * rsig[r][i];
                         float dzt = dzx[r][i], dz_ld = 0.f;
@@ -405,7 +407,7 @@ __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_bwd_reg_kernel(const Mo
             for (int w = 0; w < nw; ++w) tot += sm[(size_t)w * kPer + t];
             const int ln = t & 31, q = t >> 5, which = q & 1, ji = q >> 1, j = ji / NC, i = ji - j * NC;
             const int c = ln + 32 * i;
-            if (c < p.D) {
+            if (FULL || c < p.D) {
                 const int64_t o = ((int64_t)j * p.B + b) * p.D + c;
                 if (which == 0) p.dmu[o] = tot;
                 else p.ds[o] = tot;
@@ -430,12 +432,28 @@ __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_bwd_reg_kernel(const Mo
 }
 
 typedef void (*moe_kernel_t)(const MoeParams);
+template <bool FWD, int MT_, int NC_>
+static moe_kernel_t pick_variant(int lm, bool full) {
+#define MOE_V(LM_, FULL_) \
+    (FWD ? (moe_kernel_t)moe_fwd_reg_kernel<MT_, NC_, LM_, FULL_> : (moe_kernel_t)moe_bwd_reg_kernel<MT_, NC_, LM_, FULL_>)
+    if (MT_ * NC_ <= 4) {  // common shapes get the family / full-lane specialisations
+        if (lm == 0) return full ? MOE_V(0, true) : MOE_V(0, false);
+        if (lm == 1) return full ? MOE_V(1, true) : MOE_V(1, false);
+    }
+    return MOE_V(2, false);
+#undef MOE_V
+}
+
 template <bool FWD>
-static moe_kernel_t pick_reg_kernel(int M, int D, int* nc_out) {
+static moe_kernel_t pick_reg_kernel(int M, int D, const int* dist, int* nc_out) {
     const int nc = D <= 32 ? 1 : (D <= 64 ? 2 : (D <= 128 ? 4 : 8));
     *nc_out = nc;
+    int nlap = 0;
+    for (int j = 0; j < M; ++j) nlap += dist[j] == MMVAE_LAPLACE;
+    const int lm = nlap == 0 ? 0 : (nlap == M ? 1 : 2);
+    const bool full = D == 32 * nc;
 #define MOE_PICK(MT_, NC_) \
-    if (M == MT_ && nc == NC_) return FWD ? (moe_kernel_t)moe_fwd_reg_kernel<MT_, NC_> : (moe_kernel_t)moe_bwd_reg_kernel<MT_, NC_>;
+    if (M == MT_ && nc == NC_) return pick_variant<FWD, MT_, NC_>(lm, full);
     MOE_PICK(1, 1) MOE_PICK(1, 2) MOE_PICK(1, 4) MOE_PICK(1, 8)
     MOE_PICK(2, 1) MOE_PICK(2, 2) MOE_PICK(2, 4)
     MOE_PICK(3, 1) MOE_PICK(3, 2)
@@ -476,7 +494,7 @@ extern "C" int mmvae_moe_logdens_fwd(const float* mu, const float* s, int M, int
     p.z = z; p.lq = lq; p.lpz = lpz;
     const size_t smem = (size_t)(4 * M * D + 3 * D) * sizeof(float);
     int nc = 0;
-    if (moe_kernel_t kr = pick_reg_kernel<true>(M, D, &nc)) {
+    if (moe_kernel_t kr = pick_reg_kernel<true>(M, D, p.dist, &nc)) {
         kr<<<moe_grid(B), moe_warps(K) * 32, 0, (cudaStream_t)stream>>>(p);
         MMVAE_LAUNCH_CHECK();
         return 0;
@@ -508,7 +526,7 @@ extern "C" int mmvae_moe_logdens_bwd(const float* mu, const float* s, int M, int
     auto kb = M == 1 ? moe_bwd_kernel<1> : M == 2 ? moe_bwd_kernel<2> : M == 3 ? moe_bwd_kernel<3>
                                                                               : M == 4 ? moe_bwd_kernel<4> : moe_bwd_kernel<0>;
     int nc = 0;
-    if (moe_kernel_t kr = pick_reg_kernel<false>(M, D, &nc)) {
+    if (moe_kernel_t kr = pick_reg_kernel<false>(M, D, p.dist, &nc)) {
         const size_t smem_r = (size_t)nw * (2 * M * nc + 2 * nc) * 32 * sizeof(float);
         if (smem_r > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute((const void*)kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
