@@ -112,10 +112,10 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
             const float* sl = s_lse + r * 2 * p.d;
             TX* gr = reinterpret_cast<TX*>(p.g) + (row0 + r) * p.ldg;
             for (int j = lane; j < p.d; j += 32) {
-                const float lse = sl[j], ts = sl[p.d + j];
+                const float nl = -sl[j] * kLog2e, wts = -wl * sl[p.d + j];
                 for (int c = warp; c < p.C; c += nwarps) {
                     const int e = r * n + c * p.d + j;
-                    const float gv = wl * (Elem<TT>::get(st + e) - __expf(Elem<TX>::get(sx + e) - lse) * ts);
+                    const float gv = fmaf(exp_shifted(Elem<TX>::get(sx + e), nl), wts, wl * Elem<TT>::get(st + e));
                     if (p.tma)
                         Elem<TX>::store1(sx + e, gv);
                     else
@@ -143,10 +143,11 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
 #pragma unroll 5
                 for (int c = 0; c < p.C; ++c) m = fmaxf(m, Elem<TX>::get(px + c * p.d));
                 float se = 0.f, ts = 0.f, txs = 0.f;
+                const float nm = -m * kLog2e;
 #pragma unroll 5
                 for (int c = 0; c < p.C; ++c) {
                     const float xv = Elem<TX>::get(px + c * p.d), tv = Elem<TT>::get(pt + c * p.d);
-                    se += __expf(xv - m);
+                    se += exp_shifted(xv, nm);
                     ts += tv;
                     txs = fmaf(tv, xv, txs);
                 }
@@ -174,12 +175,13 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
                 float m = -INFINITY;
                 for (int ww = 0; ww < W; ++ww) m = fmaxf(m, part[((size_t)(rl * W + ww) * p.d + j) * 4]);
                 float se = 0.f, ts = 0.f, txs = 0.f;
+                const float nm = -m * kLog2e;
                 const TX* px = rx + w * p.d + j;
                 const TT* pt = rt + w * p.d + j;
 #pragma unroll 4
                 for (int c = w; c < p.C; c += W, px += step, pt += step) {
                     const float xv = Elem<TX>::get(px), tv = Elem<TT>::get(pt);
-                    se += __expf(xv - m);
+                    se += exp_shifted(xv, nm);
                     ts += tv;
                     txs = fmaf(tv, xv, txs);
                 }
@@ -224,13 +226,13 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
             const int step = W * p.d;
             TX* gdst = p.tma ? gs : gr;  // in-place smem staging (leaves through TMA) or straight to global
             for (int j = lane; j < p.d; j += 32) {
-                const float lse = s_lse[rl * p.d + j], ts = s_ts[rl * p.d + j];
+                const float nl = -s_lse[rl * p.d + j] * kLog2e, wts = -wl * s_ts[rl * p.d + j];
                 const TX* px = rx + w * p.d + j;
                 const TT* pt = rt + w * p.d + j;
                 TX* pg = gdst + w * p.d + j;
 #pragma unroll 4
-                for (int c = w; c < p.C; c += W, px += step, pt += step, pg += step)
-                    Elem<TX>::store1(pg, wl * (Elem<TT>::get(pt) - __expf(Elem<TX>::get(px) - lse) * ts));
+                for (int c = w; c < p.C; c += W, px += step, pt += step, pg += step)  // wl*t - wl*ts*softmax
+                    Elem<TX>::store1(pg, fmaf(exp_shifted(Elem<TX>::get(px), nl), wts, wl * Elem<TT>::get(pt)));
             }
         }
         if (p.tma) {

@@ -123,6 +123,17 @@ static __global__ void __launch_bounds__(128) partial_sum_kernel(const float* __
     }
 }
 
+// exp(x - m) for softmax-style sums as ONE FFMA + ONE MUFU.EX2: ex2.approx.ftz(x*log2(e) - m*log2(e)).  (__expf
+// expands to 6 instructions: scale, range test, two predicated fix-ups around MUFU for sub-normal RESULTS; results
+// below 2^-126 are flushed to 0 here, which is irrelevant next to a sum whose largest term is 1.)
+constexpr float kLog2e = 1.44269504088896340736f;
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float exp_shifted(float x, float neg_m_log2e) { return ex2_ftz(fmaf(x, kLog2e, neg_m_log2e)); }
+
 // ---- TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier ---------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
