@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--overlap", action="store_true", help="run small kernels on a side stream (measured slower on C2)")
+    ap.add_argument("--eager-sync", action="store_true",
+                    help="N>1: all-reduce after the step (eager NCCL call) instead of inside it (side stream, captured)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=8, help="samples per step of the bounded CPU sample")
@@ -264,13 +266,16 @@ def main():
     rdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     cfg, t = W.make_leaves(args.workload, B=args.batch, seed=1234 + rank, recon_dtype=rdt)
     B = cfg["B"]
-    step = W.LeafStep(cfg, t, device=dev, group=group, global_batch=B * world)
+    # the only replicated parameter on this leaf protocol is the prior logit vector: all-reduce(SUM) its gradient.
+    # Default: inside the step (parallel.GradSync hook -> side stream, overlapped with the likelihood backward and
+    # captured in the step graph); --eager-sync: one eager NCCL call after the step.
+    in_step_sync = world > 1 and not args.eager_sync
+    step = W.LeafStep(cfg, t, device=dev, group=group, global_batch=B * world, sync_grads=in_step_sync)
     step.overlap = args.overlap
     W_, K_ = max(args.warmup, 3), args.steps
 
     def sync_grads():
-        # the only replicated parameter on this leaf protocol is the prior logit vector: all-reduce(SUM) its grad
-        if world > 1:
+        if world > 1 and step.sync is None and step.pz_logits.grad is not None:
             dist.all_reduce(step.pz_logits.grad, group=group)
 
     # launches of our kernels per step, counted on one eager step
@@ -284,6 +289,11 @@ def main():
     needs_coll = world > 1 and (cfg["obj"] == "dreg" or any(m["ltype"] == "optimal_sigma" for m in cfg["mods"]))
     if not args.no_graph and not needs_coll:
         runner = W.GraphedStep(step)
+    sync_mode = "none (1 GPU)"
+    if world > 1:
+        sync_mode = ("in-step all-reduce on a side stream behind the latent backward, overlapped with the likelihood "
+                     "backward%s" % (", captured in the step graph" if runner is not step else "")) \
+            if step.sync is not None else "eager all-reduce after the step"
 
     def timed(nsteps, fn):
         if world > 1:
@@ -315,10 +325,11 @@ def main():
     ms = timed(K_, one)
     # the timed region is only a few milliseconds: keep the identical load running so that the clock / throttle record
     # covers a representative stretch under load (not timed, not counted)
-    while time.perf_counter() - t_load < 0.3:
-        for _ in range(10):
-            one()
-        torch.cuda.synchronize()
+    # (the iteration count comes from the all-reduced step time, so every rank runs the same number of collectives)
+    n_extra = int(min(max(0.3 - (time.perf_counter() - t_load), 0.0) if world == 1 else 0.3, 0.3) / (ms / K_ * 1e-3)) + 1
+    for _ in range(n_extra):
+        one()
+    torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     value = B * world * K_ / (ms / 1e3)
 
@@ -410,6 +421,7 @@ def main():
                        "latent_dim": cfg["D"], "batch_per_gpu": B, "global_batch": B * world,
                        "mods": [{"data_dim": list(m["data_dim"]), "ltype": m["ltype"]} for m in cfg["mods"]],
                        "parallelism": "batch-sharded x%d, NCCL all-reduce of replicated grads" % world,
+                       "grad_sync": sync_mode,
                        "l2": "per-step working set %.2f GB >> 126 MB L2, no flush" % (step_bytes / 1e9),
                        "launch_mode": "cuda-graph" if runner is not step else "eager",
                        "streams": "side stream overlaps small kernels" if step.overlap else "single stream"},
@@ -424,6 +436,9 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        if runner is not step:
+            runner.close()  # the graph holds the captured all-reduce: it must go before the communicator
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

@@ -24,6 +24,8 @@ struct CatceParams {
     float* stats;  // (rows, 2, d): logsumexp and target sum per column; written by fwd, read by bwd (may be NULL)
     int64_t ldx, ldt, ldg, rows, B;
     int C, d, R, W, tma;
+    int G;               // v2 column kernel: rows per warp (32 / d for d < 32, else 1)
+    float inv_n, inv_d;  // v2 flat backward: 1/(C*d), 1/d for the exact float-reciprocal index split
     float lam, w_const;
 };
 
@@ -246,14 +248,277 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// v2 (default): no shared-memory staging.
+//
+// ncu r1 on the TMA-staged kernel above (C2 text term, 7680 x 45 x 27 fp32): 18.7 us forward / 21.7 us backward for
+// 37 / 76 MB -- one-shot CTAs alternate between a TMA round trip and a short compute phase, and the L2-resident target
+// slab goes through the same smem pipe as the streamed reconstruction.  v2 splits the work by access pattern:
+//
+//   catce_cols_kernel      a warp owns 32/d rows (d < 32) or one row; a lane owns one column j and walks the class
+//                          axis in register chunks of CH values with an online (running max / rescaled sum)
+//                          softmax: CH independent loads per tensor in flight per lane, one pass over x and t, no
+//                          barrier, no smem, any alignment or row stride.  Writes the row value and the per-column
+//                          (logsumexp, sum t) statistics; MODE 1/2 add a second chunked pass that re-reads the row
+//                          (L1/L2 hits) and writes the gradient.
+//   catce_flat_bwd_kernel  with cached statistics the gradient is ELEMENT-WISE: g[e] = wl*t[e] - wl*ts[j]*exp(x[e] -
+//                          lse[j]); a CTA takes a dense slab of R rows as a flat run of 128-bit vectors (streaming
+//                          loads / stores as in loglik.cu) and looks its column statistics up in a few hundred bytes
+//                          of smem.  2R+T bytes, ~12 instructions per element.
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef MMVAE_CATCE_IMPL
+#define MMVAE_CATCE_IMPL 1  // 0: TMA-staged kernel for everything, 1: + flat streaming backward, 2: v2 kernels only
+#endif
+#ifndef MMVAE_CATCE_CH
+#define MMVAE_CATCE_CH 16
+#endif
+#ifndef MMVAE_CATCE_COLS_MINBLOCKS
+#define MMVAE_CATCE_COLS_MINBLOCKS 3
+#endif
+
+template <typename TX, typename TT, int CH, bool FULL>
+__device__ __forceinline__ void cols_load(const TX* px, const TT* pt, int c0, int C, int d, float* xv, float* tv) {
+#pragma unroll
+    for (int u = 0; u < CH; ++u) xv[u] = (FULL || c0 + u < C) ? Elem<TX>::load1(px + (c0 + u) * d) : -INFINITY;
+#pragma unroll
+    for (int u = 0; u < CH; ++u) tv[u] = (FULL || c0 + u < C) ? Elem<TT>::load1(pt + (c0 + u) * d) : 0.f;
+}
+
+template <int CH, bool FULL>
+__device__ __forceinline__ void cols_accum(const float* xv, const float* tv, int c0, int C, float& m, float& se,
+                                           float& ts, float& txs) {
+    float cm = xv[0];
+#pragma unroll
+    for (int u = 1; u < CH; ++u) cm = fmaxf(cm, xv[u]);
+    const float mn = fmaxf(m, cm);
+    const float nm = (mn == -INFINITY) ? 0.f : -mn * kLog2e;  // a column of -inf so far keeps se == 0
+    se *= ex2_ftz(fmaf(m, kLog2e, nm));
+#pragma unroll
+    for (int u = 0; u < CH; ++u) {
+        se += ex2_ftz(fmaf(xv[u], kLog2e, nm));
+        ts += tv[u];
+        if (FULL || c0 + u < C) txs = fmaf(tv[u], xv[u], txs);
+    }
+    m = mn;
+}
+
+template <typename TX, typename TT, int MODE>  // 0 fwd (+ stats), 1 bwd without cached stats, 2 fused
+__global__ void __launch_bounds__(256, MMVAE_CATCE_COLS_MINBLOCKS) catce_cols_kernel(const CatceParams p) {
+    constexpr int CH = MMVAE_CATCE_CH;
+    const int lane = threadIdx.x & 31, d = p.d, C = p.C, G = p.G;
+    const int rsub = d < 32 ? lane / d : 0;
+    const int jl = lane - rsub * d;
+    const bool lane_ok = d >= 32 || rsub < G;
+    const int wpc = blockDim.x >> 5;
+    const int64_t nwarps = (int64_t)gridDim.x * wpc;
+    const int64_t groups = (p.rows + G - 1) / G;
+    const TX* __restrict__ xg = reinterpret_cast<const TX*>(p.x);
+    const TT* __restrict__ tg = reinterpret_cast<const TT*>(p.t);
+    for (int64_t grp = (int64_t)blockIdx.x * wpc + (threadIdx.x >> 5); grp < groups; grp += nwarps) {
+        const int64_t row = grp * G + rsub;
+        const bool ok = lane_ok && row < p.rows;
+        float acc = 0.f;
+        if (ok) {
+            const TX* xr = xg + row * p.ldx;
+            const TT* tr = tg + (row % p.B) * p.ldt;
+            float wl = 0.f;
+            if (MODE != 0) wl = (p.w_rows ? __ldg(p.w_rows + row) : p.w_const) * p.lam;
+            for (int j = jl; j < d; j += 32) {
+                const TX* px = xr + j;
+                const TT* pt = tr + j;
+                float m = -INFINITY, se = 0.f, ts = 0.f, txs = 0.f;
+                int c0 = 0;
+                for (; c0 + CH <= C; c0 += CH) {
+                    float xv[CH], tv[CH];
+                    cols_load<TX, TT, CH, true>(px, pt, c0, C, d, xv, tv);
+                    cols_accum<CH, true>(xv, tv, c0, C, m, se, ts, txs);
+                }
+                if (c0 < C) {
+                    float xv[CH], tv[CH];
+                    cols_load<TX, TT, CH, false>(px, pt, c0, C, d, xv, tv);
+                    cols_accum<CH, false>(xv, tv, c0, C, m, se, ts, txs);
+                }
+                const float lse = m + logf(se);
+                acc += txs - lse * ts;
+                if (MODE == 0 && p.stats) {
+                    p.stats[row * 2 * d + j] = lse;
+                    p.stats[row * 2 * d + d + j] = ts;
+                }
+                if (MODE != 0) {  // second pass: the row was just read, so these loads hit L1 / L2
+                    const float nl = -lse * kLog2e, wts = -wl * ts;
+                    TX* pg = reinterpret_cast<TX*>(p.g) + row * p.ldg + j;
+                    for (c0 = 0; c0 < C; c0 += CH) {
+                        float xv[CH], tv[CH];
+                        if (c0 + CH <= C) cols_load<TX, TT, CH, true>(px, pt, c0, C, d, xv, tv);
+                        else cols_load<TX, TT, CH, false>(px, pt, c0, C, d, xv, tv);
+#pragma unroll
+                        for (int u = 0; u < CH; ++u)
+                            if (c0 + u < C)  // wl*t - wl*ts*softmax
+                                Elem<TX>::store1(pg + (c0 + u) * d, fmaf(ex2_ftz(fmaf(xv[u], kLog2e, nl)), wts, wl * tv[u]));
+                    }
+                }
+            }
+        }
+        if (MODE != 1) {
+            float v = acc;
+            if (d >= 32) {
+                v = warp_sum(v);
+            } else {  // segmented sum over the d lanes of a row
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float nb = __shfl_down_sync(0xffffffffu, v, o);
+                    if (jl + o < d) v += nb;
+                }
+            }
+            if (ok && jl == 0) p.out_rows[row] = p.lam * v;
+        }
+    }
+}
+
+template <typename TX, typename TT, int V>  // V = 16 / sizeof(TX): dense aligned slabs; V = 1: any stride / alignment
+__global__ void __launch_bounds__(256, 3) catce_flat_bwd_kernel(const CatceParams p) {
+    extern __shared__ __align__(16) float sm2[];
+    constexpr int U = V >= 8 ? 3 : 6, T = 256;  // 24 data registers per tensor and batch
+    const int d = p.d, n = p.C * p.d, R = p.R;
+    float* s_nl = sm2;           // R*d: -logsumexp * log2(e)
+    float* s_wts = sm2 + R * d;  // R*d: -w*lam * sum_c t
+    float* s_wl = s_wts + R * d; // R:   w*lam
+    const int64_t row0 = (int64_t)blockIdx.x * R;
+    const int nrows = (int)min((int64_t)R, p.rows - row0);
+    const int total = nrows * n;
+    const int rb0 = (int)(row0 % p.B);
+    const TX* __restrict__ xg = reinterpret_cast<const TX*>(p.x);
+    const TT* __restrict__ tg = reinterpret_cast<const TT*>(p.t);
+    TX* __restrict__ gg = reinterpret_cast<TX*>(p.g);
+
+    auto split = [&](int off, int& r, int& ee) {  // off = r*n + ee, exact for R*n < 2^21 (host checks)
+        r = (int)(((float)off + 0.5f) * p.inv_n);
+        ee = off - r * n;
+    };
+    float xv[U][V], tv[U][V];
+    auto load = [&](int e0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int off = e0 + u * T * V;
+            if (off < total) {
+                if (V > 1) {
+                    load_vec<TX, V>(xg + row0 * n + off, xv[u], true);
+                    load_vec<TT, V>(tg + (int64_t)rb0 * n + off, tv[u], false);
+                } else {
+                    int r, ee;
+                    split(off, r, ee);
+                    xv[u][0] = Elem<TX>::load1(xg + (row0 + r) * p.ldx + ee);
+                    tv[u][0] = Elem<TT>::load1(tg + (int64_t)((rb0 + r) % (int)p.B) * p.ldt + ee);
+                }
+            }
+        }
+    };
+    int e0 = threadIdx.x * V;
+    load(e0);  // in flight while the column statistics are staged
+    for (int i = threadIdx.x; i < nrows * d; i += T) {
+        const int r = (int)(((float)i + 0.5f) * p.inv_d), j = i - r * d;
+        const float* st = p.stats + (row0 + r) * 2 * d;
+        const float wl = __ldg(p.w_rows + row0 + r) * p.lam;
+        s_nl[i] = -__ldg(st + j) * kLog2e;
+        s_wts[i] = -wl * __ldg(st + d + j);
+        if (j == 0) s_wl[r] = wl;
+    }
+    __syncthreads();
+    while (true) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int off = e0 + u * T * V;
+            if (off < total) {
+                int r, ee;
+                split(off, r, ee);
+                int j = ee - (int)(((float)ee + 0.5f) * p.inv_d) * d;
+                int rd = r * d;
+                float wl = s_wl[r];
+                float gv[V];
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    gv[i] = fmaf(ex2_ftz(fmaf(xv[u][i], kLog2e, s_nl[rd + j])), s_wts[rd + j], wl * tv[u][i]);
+                    if (V > 1) {
+                        ++j; ++ee;
+                        if (j == d) j = 0;
+                        if (ee == n && i + 1 < V) { ee = 0; j = 0; ++r; rd += d; wl = s_wl[r]; }
+                    }
+                }
+                if constexpr (V > 1) stg_stream(gg + row0 * n + off, Elem<TX>::pack(gv));
+                else Elem<TX>::store1(gg + (row0 + r) * p.ldg + ee, gv[0]);
+            }
+        }
+        e0 += U * T * V;
+        if (e0 >= total) break;
+        load(e0);
+    }
+}
+
 static size_t catce_smem(int R, int W, int n, int d, int sx, int st) {
     size_t off = up16((size_t)R * n * sx) + up16((size_t)R * n * st);
     off = up16(off + (size_t)(2 * R * d + 4 * R * W * d) * 4);
     return off + 16;
 }
 
+
+static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
+
+template <typename TX, typename TT>
+static int launch_catce_v2(int mode, CatceParams p, cudaStream_t st) {
+    const int n = p.C * p.d;
+    if (mode == 1 && p.stats) {
+        constexpr int V = 16 / (int)sizeof(TX);
+        constexpr int kSlab = 256 * 24;  // elements a CTA keeps in flight per tensor (U*V = 24 per thread)
+        p.inv_n = 1.0f / (float)n;
+        p.inv_d = 1.0f / (float)p.d;
+        const bool dense = p.ldx == n && p.ldt == n && p.ldg == n && aligned16(p.x) && aligned16(p.t) && aligned16(p.g);
+        int R = 0;
+        bool vec = false;
+        if (dense && p.B < (1LL << 30)) {  // R rows: R*n a multiple of V, R | B (a slab never straddles the target wrap)
+            const int u = V / gcd_i(n, V);
+            for (int64_t r = u; r <= p.B && r * p.d <= 4096 && (r * n <= kSlab || r == u); r *= 2)
+                if (p.B % r == 0) R = (int)r;
+            vec = R > 0;
+        }
+        if (!vec && p.d <= 4096 && p.B < (1LL << 30)) {
+            int64_t r = kSlab / n;
+            if (r > 4096 / p.d) r = 4096 / p.d;
+            R = (int)(r < 1 ? 1 : r);
+        }
+        if (R > 0) {
+            p.R = R;
+            const size_t smem = (size_t)(2 * R * p.d + R) * sizeof(float);
+            const int64_t grid = (p.rows + R - 1) / R;
+            if (grid > 0x7fffffffLL) return MMVAE_E_LIMIT;
+            if (vec) catce_flat_bwd_kernel<TX, TT, V><<<(unsigned)grid, 256, smem, st>>>(p);
+            else catce_flat_bwd_kernel<TX, TT, 1><<<(unsigned)grid, 256, smem, st>>>(p);
+            MMVAE_LAUNCH_CHECK();
+            return 0;
+        }
+        // column statistics wider than the smem table: recompute them in the column kernel
+    }
+    p.G = p.d < 32 ? 32 / p.d : 1;
+    const int64_t groups = (p.rows + p.G - 1) / p.G;
+    int64_t grid = (groups + 7) / 8;
+    if (grid > (int64_t)kNumSMs * 16) grid = (int64_t)kNumSMs * 16;  // grid-stride over row groups beyond that
+    if (mode == 0) catce_cols_kernel<TX, TT, 0><<<(unsigned)grid, 256, 0, st>>>(p);
+    else if (mode == 1) catce_cols_kernel<TX, TT, 1><<<(unsigned)grid, 256, 0, st>>>(p);
+    else catce_cols_kernel<TX, TT, 2><<<(unsigned)grid, 256, 0, st>>>(p);
+    MMVAE_LAUNCH_CHECK();
+    return 0;
+}
+
 template <typename TX, typename TT>
 static int launch_catce(int mode, CatceParams p, cudaStream_t st) {
+#if MMVAE_CATCE_IMPL == 2
+    return launch_catce_v2<TX, TT>(mode, p, st);
+#elif MMVAE_CATCE_IMPL == 1
+    // measured r1 (tools/tune_catce.sh, profiles/r1_tune_catce.txt): the flat streaming backward beats the staged one
+    // everywhere (C2 text 27.9 -> 22.9 us, C5 bf16 captions 65.7 -> 55.2 us); the column kernel only ties the staged
+    // forward and loses the fused pass, so those stay on the TMA-staged kernel
+    if (mode == 1 && p.stats) return launch_catce_v2<TX, TT>(mode, p, st);
+#endif
     const int n = p.C * p.d, sx = (int)sizeof(TX), stt = (int)sizeof(TT);
     const bool fast_bwd = (mode == 1 && p.stats != nullptr);
     // warps per row split the class axis (short dependency chains); the cached-statistics backward has no per-row

@@ -106,6 +106,29 @@ struct Elem<__nv_bfloat16> {
     __device__ static __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
 
+// V elements of T -> fp32 registers: 128-bit loads (streaming or cached), 8-byte load for 4 bf16 next to fp32 data
+template <typename T, int V>
+__device__ __forceinline__ void load_vec(const T* p, float* o, bool stream) {
+    if (V == 1) {
+        o[0] = Elem<T>::load1(p);
+    } else {
+        constexpr int per = Elem<T>::kPer16B;
+        if (V >= per) {
+#pragma unroll
+            for (int i = 0; i < V / per; ++i) {
+                const uint4 v = stream ? ldg_stream(p + i * per) : ldg_keep(p + i * per);
+                Elem<T>::unpack(v, o + i * per);
+            }
+        } else {  // bf16 target next to an fp32 reconstruction: 4 x bf16 = 8 bytes
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+            o[0] = __uint_as_float(v.x << 16);
+            o[1] = __uint_as_float(v.x & 0xffff0000u);
+            o[2] = __uint_as_float(v.y << 16);
+            o[3] = __uint_as_float(v.y & 0xffff0000u);
+        }
+    }
+}
+
 // Second stage of the deterministic batch reductions (learnable-prior gradients): ws holds `parts` partial vectors
 // of length n_total (row-major); output element i = sum_q ws[q][i].  One CTA per output element, strided loads,
 // fixed-shape block reduction -> bit-reproducible; out0 receives elements [0, n0), out1 the rest.

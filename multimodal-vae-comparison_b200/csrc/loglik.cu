@@ -20,6 +20,9 @@ constexpr int kThreads = 256;
 #ifndef MMVAE_FWD_MINBLOCKS
 #define MMVAE_FWD_MINBLOCKS 5  // r1: 77.6 -> 71.8 us for the C2 forward (5 CTAs of 256 threads per SM, <= 51 registers)
 #endif
+#ifndef MMVAE_BCE_FAST
+#define MMVAE_BCE_FAST 1  // unclamped BCE forward with one finiteness test per vector (exact slow path behind it)
+#endif
 template <int MODE>
 struct Tune {
     // measured r1 (see profiles/r1_tune_loglik_fwd.txt)
@@ -144,28 +147,6 @@ struct LogP {
     }
 };
 
-template <typename T, int V>
-__device__ __forceinline__ void load_vec(const T* p, float* o, bool stream) {
-    if (V == 1) {
-        o[0] = Elem<T>::load1(p);
-    } else {
-        constexpr int per = Elem<T>::kPer16B;
-        if (V >= per) {
-#pragma unroll
-            for (int i = 0; i < V / per; ++i) {
-                const uint4 v = stream ? ldg_stream(p + i * per) : ldg_keep(p + i * per);
-                Elem<T>::unpack(v, o + i * per);
-            }
-        } else {  // bf16 target next to an fp32 reconstruction: 4 x bf16 = 8 bytes
-            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
-            o[0] = __uint_as_float(v.x << 16);
-            o[1] = __uint_as_float(v.x & 0xffff0000u);
-            o[2] = __uint_as_float(v.y << 16);
-            o[3] = __uint_as_float(v.y & 0xffff0000u);
-        }
-    }
-}
-
 template <typename TX, typename TT, int LT, int MODE, bool VECT, bool SHORT>
 __global__ void __launch_bounds__(kThreads, Tune<MODE>::kMinBlocks) loglik_kernel(const LoglikParams p) {
     const int tpr = SHORT ? p.tpr : kThreads;  // compile-time 256 for long rows: keeps the hot variant lean
@@ -212,6 +193,34 @@ __global__ void __launch_bounds__(kThreads, Tune<MODE>::kMinBlocks) loglik_kerne
 
     auto process = [&](const float* xv, const float* tv, int i) {
         float gv[V];
+        if (MMVAE_BCE_FAST && LT == MMVAE_LT_BCE && MODE == MODE_FWD && V > 1) {
+            // Value-only BCE fast path.  The clamps max(log x, -100), max(log(1-x), -100) of F.binary_cross_entropy can
+            // only fire for x == 1 (1-x == 0), x == 0 or a sub-normal x (log x < -100 needs x < 3.7e-44; lg2.ftz flushes
+            // those to log 0); in each of these cases -- and for NaN / out-of-range inputs -- an unclamped log is -inf
+            // or NaN and so is the sum over the vector.  So: evaluate the vector unclamped (2 MUFU.LG2 + 2 FADD + FFMA +
+            // FADD per element), test the running sum ONCE per vector for finiteness, and redo the vector with the exact clamped
+            // expression in the (for decoder outputs, clamped to [1e-6, 1-1e-6] by the reference, never taken) rare case.
+            float part = acc;  // same summation order as the clamped evaluation: fwd rows == fused rows bit for bit
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const float l1 = lg2_ftz(1.0f - xv[e]);
+                part += fmaf(tv[e], lg2_ftz(xv[e]) - l1, l1);
+            }
+            if (__builtin_expect(fabsf(part) < INFINITY, 1)) {
+                acc = part;
+            } else {
+                for (int e = 0; e < V; ++e) {
+                    const float x = xv[e];
+                    if (x > 0.f && x < 1.17549435e-38f) {
+                        acc += LogP<LT>::bce_value_subnormal(x, tv[e]);
+                    } else {  // NaN / negative inputs propagate exactly like the clamped expression
+                        float v = 0.f, d = 0.f;
+                        f.template eval<true, false>(x, tv[e], v, d);
+                        acc += v;
+                    }
+                }
+            }
+        } else {
 #pragma unroll
         for (int e = 0; e < V; ++e) {
             float v = 0.f, d = 0.f;
@@ -219,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, Tune<MODE>::kMinBlocks) loglik_kerne
             if (NEED_V) acc += v;
             if (NEED_D) gv[e] = wl * d;
         }
-        if (LT == MMVAE_LT_BCE && NEED_V) {  // (not needed for BCE_LOGITS: 1+e is never sub-normal)
+        if (LT == MMVAE_LT_BCE && NEED_V) {
             // vector-level guard for sub-normal reconstructions (never taken for decoder outputs, which the
             // reference clamps to [1e-6, 1-1e-6]): redo those elements exactly
             float mn = xv[0];
@@ -239,6 +248,7 @@ __global__ void __launch_bounds__(kThreads, Tune<MODE>::kMinBlocks) loglik_kerne
                 Elem<TX>::store1(g + i, gv[0]);
             else
                 stg_stream(g + i, Elem<TX>::pack(gv));
+        }
         }
     };
 

@@ -103,7 +103,7 @@ class LeafStep:
     """One objective fwd+bwd on device-resident leaves through the CUDA path.  ``run()`` returns the loss tensor;
     gradients land in ``.grad`` of ``self.mu / self.s / self.pz_logits / self.recon[i]``."""
 
-    def __init__(self, cfg, tensors, device="cuda", beta=1.0, group=None, global_batch=None):
+    def __init__(self, cfg, tensors, device="cuda", beta=1.0, group=None, global_batch=None, sync_grads=False):
         self.cfg, self.beta, self.group = cfg, beta, group
         self.model, self.obj = cfg["model"], cfg["obj"]
         self.M, self.K, self.D, self.pv, self.B = len(cfg["mods"]), cfg["K"], cfg["D"], cfg.get("private") or 0, cfg["B"]
@@ -137,6 +137,19 @@ class LeafStep:
         nbytes = [r.numel() * r.element_size() for r in self.recon]
         self.small = [nb < 0.25 * max(nbytes) for nb in nbytes]
         self.overlap = False
+        # sync_grads: all-reduce(SUM) the gradient of the replicated prior logits INSIDE the step, launched from a
+        # post-accumulate-grad hook on a side stream (parallel.GradSync.arm) and joined at the end of run().  The
+        # IWAE / DReG branch creates the latent nodes after the likelihood nodes, so autograd (highest sequence number
+        # first) runs the latent backward -- which produces that gradient -- before the long likelihood backward
+        # kernels, and the collective hides behind them.
+        self.sync = None
+        if sync_grads and group is not None:
+            from .parallel import GradSync
+            self.sync = GradSync([self.pz_logits], group).arm()
+
+    def finish(self):
+        if self.sync is not None:
+            self.sync.wait()
 
     def leaves(self):
         return [self.mu, self.s, self.pz_logits] + self.recon
@@ -185,13 +198,14 @@ class LeafStep:
         self.zero_grad()
         loss = self.loss()
         loss.backward()
+        self.finish()
         return loss
 
     def _moe(self):
         M, K, B = self.M, self.K, self.B
-        mu0, s0 = self._prior()
         eps = self.eps_stacked
         if self.obj == "elbo":
+            mu0, s0 = self._prior()
             z, lq, _ = ops.moe_logdens(self.mu, self.s, mu0.detach(), s0.detach(), eps, self.codes, False)
             kls = ops.latent_draws(self.mu, self.s, None, None, None,
                                    [Draw(mods=(m,), direct=True, laplace=bool(self.codes[m]), kl_mode=2, width=self.D)
@@ -211,6 +225,7 @@ class LeafStep:
             kld = torch.stack([k["kl"] for k in kls])
             return total + (self.beta / M) * n_keep * kld.sum()
         if self.overlap and self.side is not None and any(self.small) and not all(self.small):
+            mu0, s0 = self._prior()
             cur = torch.cuda.current_stream()
             self.side.wait_stream(cur)
             rows = [None] * len(self.plan)
@@ -226,8 +241,10 @@ class LeafStep:
             for t in [lq, lpz] + [rows[i] for i in range(len(self.plan)) if self.small[i]]:
                 t.record_stream(cur)
         else:
-            z, lq, lpz = ops.moe_logdens(self.mu, self.s, mu0, s0, eps, self.codes, True)
+            # likelihood rows first, latent nodes last: the backward then starts with the latent kernels (see __init__)
             rows = [self._rows(i) for i in range(len(self.plan))]
+            mu0, s0 = self._prior()
+            z, lq, lpz = ops.moe_logdens(self.mu, self.s, mu0, s0, eps, self.codes, True)
         L = len(rows) // M
         if self.obj == "iwae":
             return ops.iwae_combine_rows(lpz, lq, rows, L, self.beta)[0]
@@ -295,8 +312,17 @@ class GraphedStep:
         with torch.cuda.graph(self.graph):
             self.loss = step.loss()
             self.loss.backward()
+            step.finish()  # joins the side stream of an in-step gradient all-reduce into the capture
         self.grads = [t.grad for t in step.leaves()]
 
     def run(self):
         self.graph.replay()
         return self.loss
+
+    def close(self):
+        """Destroy the captured graph.  Required before ``dist.destroy_process_group()`` when the step carries an
+        in-graph NCCL all-reduce: a communicator waits for every graph that captured it to be destroyed (measured r1:
+        destroy_process_group() blocks forever otherwise)."""
+        if self.graph is not None:
+            self.graph.reset()
+            self.graph = None

@@ -57,6 +57,21 @@ def _worker(rank, world, port, q):
             e = [rel(loss, full_loss), rel(step.mu.grad, full.mu.grad[:, lo:hi])]
             if full.pz_logits.grad is not None and float(full.pz_logits.grad.abs().max()) > 0:
                 e.append(rel(step.pz_logits.grad, full.pz_logits.grad))
+                # in-step gradient sync (hook -> side stream), eager and captured in the step's CUDA graph
+                s2 = W.LeafStep(c2, t2, device="cuda", group=dist.group.WORLD, global_batch=B, sync_grads=True)
+                s2.run()
+                torch.cuda.synchronize()
+                e.append(rel(s2.pz_logits.grad, full.pz_logits.grad))
+                e.append(rel(s2.mu.grad, step.mu.grad))
+                if cfg["obj"] != "dreg":  # (a forward collective keeps the DReG step eager)
+                    gs = W.GraphedStep(s2)
+                    for _ in range(3):
+                        gs.run()
+                    torch.cuda.synchronize()
+                    e.append(rel(s2.pz_logits.grad, full.pz_logits.grad))
+                    e.append(rel(s2.mu.grad, step.mu.grad))
+                    gs.close()  # a graph that captured the communicator must be destroyed before the process group
+                s2.sync.disarm()
             res[name] = max(e)
         if rank == 0:
             q.put(res)

@@ -6,11 +6,11 @@ cd "$(dirname "$0")/.."
 SRC=multimodal-vae-comparison_b200/csrc
 OUT=gpurun_out/tune; mkdir -p $OUT
 declare -A V
-V[base]=""
-V[mb5]="-DMMVAE_FWD_MINBLOCKS=5"
-V[mb6_u3]="-DMMVAE_FWD_MINBLOCKS=6 -DMMVAE_FWD_UNROLL=3"
-V[mb8_u2]="-DMMVAE_FWD_MINBLOCKS=8 -DMMVAE_FWD_UNROLL=2"
-V[mb4]="-DMMVAE_FWD_MINBLOCKS=4"
+V[base]="-DMMVAE_BCE_FAST=0"
+V[fast]="-DMMVAE_BCE_FAST=1"
+V[fast_mb6]="-DMMVAE_BCE_FAST=1 -DMMVAE_FWD_MINBLOCKS=6"
+V[fast_mb4]="-DMMVAE_BCE_FAST=1 -DMMVAE_FWD_MINBLOCKS=4"
+V[fast_mb6_u3]="-DMMVAE_BCE_FAST=1 -DMMVAE_FWD_MINBLOCKS=6 -DMMVAE_FWD_UNROLL=3"
 for k in "${!V[@]}"; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -Iinclude ${V[$k]} -shared $SRC/loglik.cu -o $OUT/lib_$k.so -lcudart > $OUT/build_$k.log 2>&1 &
 done
