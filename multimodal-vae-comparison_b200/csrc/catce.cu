@@ -24,7 +24,8 @@ struct CatceParams {
     float* stats;  // (rows, 2, d): logsumexp and target sum per column; written by fwd, read by bwd (may be NULL)
     int64_t ldx, ldt, ldg, rows, B;
     int C, d, R, W, tma;
-    int G;               // v2 column kernel: rows per warp (32 / d for d < 32, else 1)
+    int G;               // rows a warp works on at once (32 / d for d < 32, else 1): lane -> (row in group, column)
+    int S, TS;           // ring kernel: x stages, target slots
     float inv_n, inv_d;  // v2 flat backward: 1/(C*d), 1/d for the exact float-reciprocal index split
     float lam, w_const;
 };
@@ -47,6 +48,99 @@ __device__ __forceinline__ void stage_row_async(T* sdst, const T* gsrc, int n, i
         for (int e = words * per + tid; e < n; e += nthreads) sdst[e] = gsrc[e];
     } else {
         for (int e = tid; e < n; e += nthreads) sdst[e] = gsrc[e];
+    }
+}
+
+
+// ---- register-chunked walk along the class axis ---------------------------------------------------------------
+// A lane owns one column j and walks the class axis in chunks of CH values held in registers: CH independent loads
+// per tensor issued back to back (smem: ~30 cycles each, global: one DRAM round trip for the whole chunk), then an
+// online softmax update (running max, rescaled sum) with TWO accumulators per sum.  ncu r1 on the element-at-a-time
+// loops this replaces: every class paid LDS -> FFMA -> MUFU -> FADD in sequence (~57 cycles, 45 times per row), the
+// staged kernels were bound by that dependency chain at 2-5 warps per scheduler, not by memory.
+#ifndef MMVAE_CATCE_CH
+#define MMVAE_CATCE_CH 16  // global-memory column kernel
+#endif
+#ifndef MMVAE_CATCE_SCH
+#define MMVAE_CATCE_SCH 15  // smem kernels (C = 45 -> three full chunks)
+#endif
+
+template <typename TX, typename TT, int CH, bool FULL, bool GLOBAL>
+__device__ __forceinline__ void cols_load(const TX* px, const TT* pt, int c0, int C, int d, float* xv, float* tv) {
+#pragma unroll
+    for (int u = 0; u < CH; ++u)
+        xv[u] = (FULL || c0 + u < C) ? (GLOBAL ? Elem<TX>::load1(px + (c0 + u) * d) : Elem<TX>::get(px + (c0 + u) * d))
+                                     : -INFINITY;
+#pragma unroll
+    for (int u = 0; u < CH; ++u)
+        tv[u] = (FULL || c0 + u < C) ? (GLOBAL ? Elem<TT>::load1(pt + (c0 + u) * d) : Elem<TT>::get(pt + (c0 + u) * d))
+                                     : 0.f;
+}
+
+struct ColAcc {  // running column statistics: max, sum exp(x - max), sum t, sum t*x (two partial sums each)
+    float m = -INFINITY, se0 = 0.f, se1 = 0.f, ts0 = 0.f, ts1 = 0.f, tx0 = 0.f, tx1 = 0.f;
+    __device__ __forceinline__ float se() const { return se0 + se1; }
+    __device__ __forceinline__ float ts() const { return ts0 + ts1; }
+    __device__ __forceinline__ float txs() const { return tx0 + tx1; }
+};
+
+template <int CH, bool FULL>
+__device__ __forceinline__ void cols_accum(const float* xv, const float* tv, int c0, int C, ColAcc& a) {
+    float cm = xv[0];
+#pragma unroll
+    for (int u = 1; u < CH; ++u) cm = fmaxf(cm, xv[u]);
+    const float mn = fmaxf(a.m, cm);
+    const float nm = (mn == -INFINITY) ? 0.f : -mn * kLog2e;  // a column of -inf so far keeps the sums at 0
+    const float rs = ex2_ftz(fmaf(a.m, kLog2e, nm));           // rescale the running sum to the new max
+    a.se0 *= rs;
+    a.se1 *= rs;
+#pragma unroll
+    for (int u = 0; u < CH; ++u) {
+        const float e = ex2_ftz(fmaf(xv[u], kLog2e, nm));
+        if (u & 1) {
+            a.se1 += e;
+            a.ts1 += tv[u];
+            if (FULL || c0 + u < C) a.tx1 = fmaf(tv[u], xv[u], a.tx1);
+        } else {
+            a.se0 += e;
+            a.ts0 += tv[u];
+            if (FULL || c0 + u < C) a.tx0 = fmaf(tv[u], xv[u], a.tx0);
+        }
+    }
+    a.m = mn;
+}
+
+// (logsumexp, sum t, sum t*x) of one column; px / pt point at class 0 of the column, consecutive classes d apart
+template <typename TX, typename TT, int CH, bool GLOBAL>
+__device__ __forceinline__ void col_stats(const TX* px, const TT* pt, int C, int d, float& lse, float& ts, float& txs) {
+    ColAcc a;
+    int c0 = 0;
+    for (; c0 + CH <= C; c0 += CH) {
+        float xv[CH], tv[CH];
+        cols_load<TX, TT, CH, true, GLOBAL>(px, pt, c0, C, d, xv, tv);
+        cols_accum<CH, true>(xv, tv, c0, C, a);
+    }
+    if (c0 < C) {
+        float xv[CH], tv[CH];
+        cols_load<TX, TT, CH, false, GLOBAL>(px, pt, c0, C, d, xv, tv);
+        cols_accum<CH, false>(xv, tv, c0, C, a);
+    }
+    lse = a.m + logf(a.se());
+    ts = a.ts();
+    txs = a.txs();
+}
+
+// gradient of one column, chunked the same way: g[c] = wl*t[c] - wl*ts*exp(x[c] - lse); pg may alias px (in place)
+template <typename TX, typename TT, int CH, bool GLOBAL>
+__device__ __forceinline__ void col_grad(const TX* px, const TT* pt, TX* pg, int C, int d, float lse, float ts, float wl) {
+    const float nl = -lse * kLog2e, wts = -wl * ts;
+    for (int c0 = 0; c0 < C; c0 += CH) {
+        float xv[CH], tv[CH];
+        if (c0 + CH <= C) cols_load<TX, TT, CH, true, GLOBAL>(px, pt, c0, C, d, xv, tv);
+        else cols_load<TX, TT, CH, false, GLOBAL>(px, pt, c0, C, d, xv, tv);
+#pragma unroll
+        for (int u = 0; u < CH; ++u)
+            if (c0 + u < C) Elem<TX>::store1(pg + (c0 + u) * d, fmaf(ex2_ftz(fmaf(xv[u], kLog2e, nl)), wts, wl * tv[u]));
     }
 }
 
@@ -139,21 +233,8 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
     if (W == 1) {  // one warp owns the whole row: no block barrier on the compute path
         if (live) {
             for (int j = lane; j < p.d; j += 32) {
-                float m = -INFINITY;
-                const TX* px = rx + j;
-                const TT* pt = rt + j;
-#pragma unroll 5
-                for (int c = 0; c < p.C; ++c) m = fmaxf(m, Elem<TX>::get(px + c * p.d));
-                float se = 0.f, ts = 0.f, txs = 0.f;
-                const float nm = -m * kLog2e;
-#pragma unroll 5
-                for (int c = 0; c < p.C; ++c) {
-                    const float xv = Elem<TX>::get(px + c * p.d), tv = Elem<TT>::get(pt + c * p.d);
-                    se += exp_shifted(xv, nm);
-                    ts += tv;
-                    txs = fmaf(tv, xv, txs);
-                }
-                const float lse = m + logf(se);
+                float lse, ts, txs;
+                col_stats<TX, TT, MMVAE_CATCE_SCH, false>(rx + j, rt + j, p.C, p.d, lse, ts, txs);
                 s_lse[rl * p.d + j] = lse;
                 s_ts[rl * p.d + j] = ts;
                 acc += txs - lse * ts;
@@ -228,6 +309,11 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
             const int step = W * p.d;
             TX* gdst = p.tma ? gs : gr;  // in-place smem staging (leaves through TMA) or straight to global
             for (int j = lane; j < p.d; j += 32) {
+                if (W == 1) {
+                    col_grad<TX, TT, MMVAE_CATCE_SCH, false>(rx + j, rt + j, gdst + j, p.C, p.d, s_lse[rl * p.d + j],
+                                                             s_ts[rl * p.d + j], wl);
+                    continue;
+                }
                 const float nl = -s_lse[rl * p.d + j] * kLog2e, wts = -wl * s_ts[rl * p.d + j];
                 const TX* px = rx + w * p.d + j;
                 const TT* pt = rt + w * p.d + j;
@@ -270,38 +356,9 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
 #ifndef MMVAE_CATCE_IMPL
 #define MMVAE_CATCE_IMPL 1  // 0: TMA-staged kernel for everything, 1: + flat streaming backward, 2: v2 kernels only
 #endif
-#ifndef MMVAE_CATCE_CH
-#define MMVAE_CATCE_CH 16
-#endif
 #ifndef MMVAE_CATCE_COLS_MINBLOCKS
 #define MMVAE_CATCE_COLS_MINBLOCKS 3
 #endif
-
-template <typename TX, typename TT, int CH, bool FULL>
-__device__ __forceinline__ void cols_load(const TX* px, const TT* pt, int c0, int C, int d, float* xv, float* tv) {
-#pragma unroll
-    for (int u = 0; u < CH; ++u) xv[u] = (FULL || c0 + u < C) ? Elem<TX>::load1(px + (c0 + u) * d) : -INFINITY;
-#pragma unroll
-    for (int u = 0; u < CH; ++u) tv[u] = (FULL || c0 + u < C) ? Elem<TT>::load1(pt + (c0 + u) * d) : 0.f;
-}
-
-template <int CH, bool FULL>
-__device__ __forceinline__ void cols_accum(const float* xv, const float* tv, int c0, int C, float& m, float& se,
-                                           float& ts, float& txs) {
-    float cm = xv[0];
-#pragma unroll
-    for (int u = 1; u < CH; ++u) cm = fmaxf(cm, xv[u]);
-    const float mn = fmaxf(m, cm);
-    const float nm = (mn == -INFINITY) ? 0.f : -mn * kLog2e;  // a column of -inf so far keeps se == 0
-    se *= ex2_ftz(fmaf(m, kLog2e, nm));
-#pragma unroll
-    for (int u = 0; u < CH; ++u) {
-        se += ex2_ftz(fmaf(xv[u], kLog2e, nm));
-        ts += tv[u];
-        if (FULL || c0 + u < C) txs = fmaf(tv[u], xv[u], txs);
-    }
-    m = mn;
-}
 
 template <typename TX, typename TT, int MODE>  // 0 fwd (+ stats), 1 bwd without cached stats, 2 fused
 __global__ void __launch_bounds__(256, MMVAE_CATCE_COLS_MINBLOCKS) catce_cols_kernel(const CatceParams p) {
@@ -327,37 +384,15 @@ __global__ void __launch_bounds__(256, MMVAE_CATCE_COLS_MINBLOCKS) catce_cols_ke
             for (int j = jl; j < d; j += 32) {
                 const TX* px = xr + j;
                 const TT* pt = tr + j;
-                float m = -INFINITY, se = 0.f, ts = 0.f, txs = 0.f;
-                int c0 = 0;
-                for (; c0 + CH <= C; c0 += CH) {
-                    float xv[CH], tv[CH];
-                    cols_load<TX, TT, CH, true>(px, pt, c0, C, d, xv, tv);
-                    cols_accum<CH, true>(xv, tv, c0, C, m, se, ts, txs);
-                }
-                if (c0 < C) {
-                    float xv[CH], tv[CH];
-                    cols_load<TX, TT, CH, false>(px, pt, c0, C, d, xv, tv);
-                    cols_accum<CH, false>(xv, tv, c0, C, m, se, ts, txs);
-                }
-                const float lse = m + logf(se);
+                float lse, ts, txs;
+                col_stats<TX, TT, CH, true>(px, pt, C, d, lse, ts, txs);
                 acc += txs - lse * ts;
                 if (MODE == 0 && p.stats) {
                     p.stats[row * 2 * d + j] = lse;
                     p.stats[row * 2 * d + d + j] = ts;
                 }
-                if (MODE != 0) {  // second pass: the row was just read, so these loads hit L1 / L2
-                    const float nl = -lse * kLog2e, wts = -wl * ts;
-                    TX* pg = reinterpret_cast<TX*>(p.g) + row * p.ldg + j;
-                    for (c0 = 0; c0 < C; c0 += CH) {
-                        float xv[CH], tv[CH];
-                        if (c0 + CH <= C) cols_load<TX, TT, CH, true>(px, pt, c0, C, d, xv, tv);
-                        else cols_load<TX, TT, CH, false>(px, pt, c0, C, d, xv, tv);
-#pragma unroll
-                        for (int u = 0; u < CH; ++u)
-                            if (c0 + u < C)  // wl*t - wl*ts*softmax
-                                Elem<TX>::store1(pg + (c0 + u) * d, fmaf(ex2_ftz(fmaf(xv[u], kLog2e, nl)), wts, wl * tv[u]));
-                    }
-                }
+                if (MODE != 0)  // second pass: the row was just read, so these loads hit L1 / L2
+                    col_grad<TX, TT, CH, true>(px, pt, reinterpret_cast<TX*>(p.g) + row * p.ldg + j, C, d, lse, ts, wl);
             }
         }
         if (MODE != 1) {
@@ -455,6 +490,216 @@ __global__ void __launch_bounds__(256, 3) catce_flat_bwd_kernel(const CatceParam
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Ring kernel (forward / fused, default when the slabs are TMA-able): persistent CTAs, producer / consumer.
+//
+// The one-shot staged kernel above spends its life waiting: every CTA does TMA round trip -> short compute -> exit, and
+// 2.6 waves of that cost 18.7 us for 37 MB (C2 text).  Here a CTA owns a contiguous range of ITEMS (R consecutive
+// rows each) and keeps S slabs in flight:
+//   * warp NW (one elected lane) is the producer: waits for a stage to drain (`empty` mbarrier, one arrival per compute
+//     warp), [fused mode: sends the gradient written in place over that stage out with one bulk store], then issues
+//     the TMA bulk load of the next item into it (`full` mbarrier, complete_tx);
+//   * warps 0..NW-1 compute: wait `full`, walk their rows (lanes over columns, two smem passes over the class axis:
+//     max, then exp-sum / target sums), write row value + column statistics [+ gradient in place], arrive on `empty`.
+//   * items are enumerated TARGET-major (item = bgroup*K + k, rows k*B + bgroup*R ...): consecutive items of a CTA
+//     share their R target rows, so the target slab is loaded once per bgroup instead of once per item (K = 30 at
+//     C2: the L2 -> SM traffic of the targets drops from 1x the reconstruction to ~1/6 of it).  Target slabs live in
+//     their own TS slots (2 when K >= S, else S).
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef MMVAE_CATCE_RING
+// Measured r1 (profiles/r1_tune_catce.txt, profiles/r1_ncu_catce_notes.txt): correct, but SLOWER than the one-shot
+// staged kernel on every benchmark shape (C2 text forward 22.5 vs 18.7 us, fused 34 vs 31 us): the kernel is not
+// memory bound -- a row costs ~900 warp instructions at 2 consumer warps per scheduler (97 KB of smem per CTA caps
+// the SM at 8 consumer warps), while the one-shot kernel keeps 20 warps per SM resident.  Kept as an opt-in
+// experiment (-DMMVAE_CATCE_RING=1); off by default.
+#define MMVAE_CATCE_RING 0
+#endif
+#ifndef MMVAE_CATCE_RING_XB
+#define MMVAE_CATCE_RING_XB (24 * 1024)  // preferred bytes of one x stage
+#endif
+#ifndef MMVAE_CATCE_RING_SMEM
+#define MMVAE_CATCE_RING_SMEM (110 * 1024)  // preferred smem per CTA (2 CTAs per SM)
+#endif
+
+template <typename TX, typename TT, int MODE>  // 0 fwd (+ stats), 2 fused
+__global__ void __launch_bounds__(288) catce_ring_kernel(const CatceParams p) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const int n = p.C * p.d, d = p.d, C = p.C, R = p.R, S = p.S, TS = p.TS, G = p.G;
+    const uint32_t xb = (uint32_t)((size_t)R * n * sizeof(TX)), tb = (uint32_t)((size_t)R * n * sizeof(TT));
+    unsigned char* sx = smraw;
+    unsigned char* stg = smraw + (size_t)S * xb;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smraw + (size_t)S * xb + (size_t)TS * tb);
+    uint64_t* empty = full + S;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NW = (blockDim.x >> 5) - 1;
+    const int64_t K = p.rows / p.B;
+    const int64_t items = p.rows / R;
+    const int64_t q = items / gridDim.x, rem = items % gridDim.x;
+    const int64_t i0 = (int64_t)blockIdx.x * q + min((int64_t)blockIdx.x, rem);
+    const int cnt = (int)(q + ((int64_t)blockIdx.x < rem ? 1 : 0));
+    const TX* __restrict__ xg = reinterpret_cast<const TX*>(p.x);
+    const TT* __restrict__ tg = reinterpret_cast<const TT*>(p.t);
+    TX* __restrict__ gg = reinterpret_cast<TX*>(p.g);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, NW);
+        }
+    }
+    __syncthreads();
+
+    // item -> (target group, sample k) -> first row; one 64-bit division per CTA, then incremental
+    struct Cursor {
+        int64_t bg, k;
+    };
+    const Cursor c0{i0 / K, i0 % K};
+    auto advance = [&](Cursor& c) {
+        if (++c.k == K) {
+            c.k = 0;
+            ++c.bg;
+        }
+    };
+    auto first_row = [&](const Cursor& c) { return c.k * p.B + c.bg * R; };
+
+    if (warp == NW) {  // ---- producer ----
+        if (lane == 0) {
+            int64_t prev_bg = -1;
+            Cursor cl = c0, cs = c0;  // load cursor (item li), store cursor (item li - S)
+            int s = 0, ph = 0;        // stage and use count parity of item li
+            for (int li = 0; li < cnt; ++li) {
+                if (li >= S) {
+                    mbar_wait(empty + s, ph ^ 1);
+                    if (MODE == 2) {
+                        bulk_s2g(gg + first_row(cs) * n, sx + (size_t)s * xb, xb);
+                        bulk_wait_read();  // the stage is overwritten next
+                    }
+                    advance(cs);
+                }
+                const bool newt = cl.bg != prev_bg;
+                prev_bg = cl.bg;
+                mbar_expect_tx(full + s, xb + (newt ? tb : 0u));
+                bulk_g2s(sx + (size_t)s * xb, xg + first_row(cl) * n, xb, full + s);
+                if (newt) bulk_g2s(stg + (size_t)(cl.bg % TS) * tb, tg + cl.bg * R * n, tb, full + s);
+                advance(cl);
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+            if (MODE == 2) {  // drain: gradients of the last min(cnt, S) items (cs points at item max(0, cnt - S))
+                for (int li = max(0, cnt - S); li < cnt; ++li) {
+                    const int s2 = li % S;
+                    mbar_wait(empty + s2, (li / S) & 1);
+                    bulk_s2g(gg + first_row(cs) * n, sx + (size_t)s2 * xb, xb);
+                    advance(cs);
+                }
+                bulk_wait_read();  // smem must outlive the reads of the bulk stores
+            }
+        }
+        return;
+    }
+
+    // ---- consumers ----
+    const int rsub = d < 32 ? lane / d : 0;
+    const int jl = lane - rsub * d;
+    const bool lane_ok = d >= 32 || rsub < G;
+    Cursor cc = c0;
+    int s = 0, ph = 0;
+    for (int li = 0; li < cnt; ++li) {
+        if (lane == 0) mbar_wait(full + s, ph);
+        __syncwarp();
+        const int64_t xrow0 = first_row(cc);
+        TX* bx = reinterpret_cast<TX*>(sx + (size_t)s * xb);
+        const TT* bt = reinterpret_cast<const TT*>(stg + (size_t)(cc.bg % TS) * tb);
+        for (int rg = warp; rg * G < R; rg += NW) {
+            const int rl = rg * G + rsub;
+            const bool ok = lane_ok && rl < R;
+            float acc = 0.f;
+            if (ok) {
+                const int64_t row = xrow0 + rl;
+                float wl = 0.f;
+                if (MODE != 0) wl = (p.w_rows ? __ldg(p.w_rows + row) : p.w_const) * p.lam;
+                for (int j = jl; j < d; j += 32) {
+                    TX* px = bx + (size_t)rl * n + j;
+                    const TT* pt = bt + (size_t)rl * n + j;
+                    float lse, ts, txs;
+                    col_stats<TX, TT, MMVAE_CATCE_SCH, false>(px, pt, C, d, lse, ts, txs);
+                    acc += txs - lse * ts;
+                    if (MODE == 0 && p.stats) {
+                        p.stats[row * 2 * d + j] = lse;
+                        p.stats[row * 2 * d + d + j] = ts;
+                    }
+                    // gradient in place over the staged reconstruction
+                    if (MODE != 0) col_grad<TX, TT, MMVAE_CATCE_SCH, false>(px, pt, px, C, d, lse, ts, wl);
+                }
+            }
+            float v = acc;
+            if (d >= 32) {
+                v = warp_sum(v);
+            } else {  // segmented sum over the d lanes of a row
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float nb = __shfl_down_sync(0xffffffffu, v, o);
+                    if (jl + o < d) v += nb;
+                }
+            }
+            if (ok && jl == 0) p.out_rows[xrow0 + rl] = p.lam * v;
+        }
+        if (MODE == 2) fence_async_smem();  // generic-proxy gradient writes -> visible to the bulk store
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+        advance(cc);
+        if (++s == S) {
+            s = 0;
+            ph ^= 1;
+        }
+    }
+}
+
+// R, S, TS, NW for the ring kernel; false when the shape is not ring-able (unaligned / strided / slabs too large)
+template <typename TX, typename TT>
+static bool ring_plan(int mode, CatceParams& p, int* nw, size_t* smem, int* grid) {
+    const int n = p.C * p.d, sx = (int)sizeof(TX), stt = (int)sizeof(TT);
+    if (mode == 1) return false;
+    const bool dense = p.ldx == n && p.ldt == n && (mode == 0 || p.ldg == n) && aligned16(p.x) && aligned16(p.t) &&
+                       (mode == 0 || aligned16(p.g));
+    if (!dense || p.rows % p.B != 0) return false;
+    int u = 1;  // alignment unit: rows per 16-byte aligned slab
+    while (u <= 16 && (((size_t)u * n * sx) % 16 != 0 || ((size_t)u * n * stt) % 16 != 0)) u <<= 1;
+    if (u > 16 || p.B % u != 0) return false;
+    const int G = p.d < 32 ? 32 / p.d : 1;
+    const int64_t K = p.rows / p.B;
+    // R: the largest u*2^k dividing B with an x stage <= the preferred size and <= 4 row groups per compute warp,
+    // reduced again while the launch would have fewer than 2 items per SM
+    int64_t R = u;
+    while (R * 2 <= p.B && p.B % (R * 2) == 0 && (size_t)(R * 2) * n * sx <= MMVAE_CATCE_RING_XB && R * 2 <= 8 * G * 4) R *= 2;
+    while (R > u && p.rows / R < 2 * kNumSMs) R /= 2;
+    const size_t xb = (size_t)R * n * sx, tb = (size_t)R * n * stt;
+    int S = 0, TS = 0;
+    size_t need = 0;
+    for (size_t budget : {(size_t)MMVAE_CATCE_RING_SMEM, (size_t)216 * 1024}) {
+        for (int s = 4; s >= 2 && !S; --s) {
+            const int ts = K >= s ? 2 : s;
+            const size_t b = s * xb + ts * tb + 2 * s * sizeof(uint64_t) + 16;
+            if (b <= budget) { S = s; TS = ts; need = b; }
+        }
+        if (S) break;
+    }
+    if (!S) return false;
+    p.R = (int)R; p.S = S; p.TS = TS; p.G = G;
+    const int groups = (int)((R + G - 1) / G);
+    *nw = groups < 8 ? groups : 8;
+    *smem = need;
+    int cps = (int)((size_t)227 * 1024 / (need + 1024));
+    if (cps > 4) cps = 4;
+    if (cps < 1) cps = 1;
+    const int64_t items = p.rows / R;
+    *grid = (int)(items < (int64_t)kNumSMs * cps ? items : (int64_t)kNumSMs * cps);
+    return true;
+}
+
 static size_t catce_smem(int R, int W, int n, int d, int sx, int st) {
     size_t off = up16((size_t)R * n * sx) + up16((size_t)R * n * st);
     off = up16(off + (size_t)(2 * R * d + 4 * R * W * d) * 4);
@@ -511,13 +756,33 @@ static int launch_catce_v2(int mode, CatceParams p, cudaStream_t st) {
 
 template <typename TX, typename TT>
 static int launch_catce(int mode, CatceParams p, cudaStream_t st) {
+#if MMVAE_CATCE_RING
+    {
+        int nw, grid;
+        size_t smem;
+        CatceParams q = p;
+        if (ring_plan<TX, TT>(mode, q, &nw, &smem, &grid)) {
+            auto k = mode == 0 ? catce_ring_kernel<TX, TT, 0> : catce_ring_kernel<TX, TT, 2>;
+            if (smem > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return (int)e;
+            }
+            k<<<(unsigned)grid, (nw + 1) * 32, smem, st>>>(q);
+            MMVAE_LAUNCH_CHECK();
+            return 0;
+        }
+    }
+#endif
 #if MMVAE_CATCE_IMPL == 2
     return launch_catce_v2<TX, TT>(mode, p, st);
 #elif MMVAE_CATCE_IMPL == 1
     // measured r1 (tools/tune_catce.sh, profiles/r1_tune_catce.txt): the flat streaming backward beats the staged one
     // everywhere (C2 text 27.9 -> 22.9 us, C5 bf16 captions 65.7 -> 55.2 us); the column kernel only ties the staged
-    // forward and loses the fused pass, so those stay on the TMA-staged kernel
+    // forward on long rows and loses the fused pass, so those stay on the TMA-staged kernel
     if (mode == 1 && p.stats) return launch_catce_v2<TX, TT>(mode, p, st);
+    // rows of a few hundred bytes (actions, attributes, MNIST-sized label maps): the column kernel needs no staging
+    // round trip (K = 50, 10 x 12: forward 37 -> 26 us, fused 57 -> 41 us)
+    if ((size_t)p.C * p.d * sizeof(TX) <= 512) return launch_catce_v2<TX, TT>(mode, p, st);
 #endif
     const int n = p.C * p.d, sx = (int)sizeof(TX), stt = (int)sizeof(TT);
     const bool fast_bwd = (mode == 1 && p.stats != nullptr);

@@ -7,12 +7,12 @@ cd "$(dirname "$0")/.."
 SRC=multimodal-vae-comparison_b200/csrc
 OUT=gpurun_out/tune_catce; mkdir -p $OUT; rm -f $OUT/lib_*.so
 declare -A V
-V[v1_tma]="-DMMVAE_CATCE_IMPL=0"
-V[v2_ch16_mb3]="-DMMVAE_CATCE_CH=16 -DMMVAE_CATCE_COLS_MINBLOCKS=3"
-V[v2_ch16_mb4]="-DMMVAE_CATCE_CH=16 -DMMVAE_CATCE_COLS_MINBLOCKS=4"
-V[v2_ch8_mb5]="-DMMVAE_CATCE_CH=8 -DMMVAE_CATCE_COLS_MINBLOCKS=5"
-V[v2_ch12_mb3]="-DMMVAE_CATCE_CH=12 -DMMVAE_CATCE_COLS_MINBLOCKS=3"
-V[v2_ch24_mb2]="-DMMVAE_CATCE_CH=24 -DMMVAE_CATCE_COLS_MINBLOCKS=2"
+V[v1_tma]="-DMMVAE_CATCE_IMPL=0 -DMMVAE_CATCE_RING=0"
+V[v1_flatbwd]="-DMMVAE_CATCE_IMPL=1 -DMMVAE_CATCE_RING=0"
+V[v2_cols_ch16]="-DMMVAE_CATCE_IMPL=2 -DMMVAE_CATCE_RING=0"
+V[ring_xb24]="-DMMVAE_CATCE_RING=1"
+V[ring_xb40]="-DMMVAE_CATCE_RING=1 -DMMVAE_CATCE_RING_XB=40960 -DMMVAE_CATCE_RING_SMEM=221184"
+V[ring_xb12]="-DMMVAE_CATCE_RING=1 -DMMVAE_CATCE_RING_XB=12288 -DMMVAE_CATCE_RING_SMEM=75000"
 for k in "${!V[@]}"; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -Iinclude ${V[$k]} -shared $SRC/catce.cu -o $OUT/lib_$k.so -lcudart > $OUT/build_$k.log 2>&1 &
 done
@@ -23,6 +23,7 @@ c_p, c_i, c_i64, c_f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_f
 flush = torch.empty(64 << 20, device="cuda")
 # (name, rows, B, C, d, recon dtype)
 SHAPES = [("c2_text", 7680, 256, 45, 27, torch.float32), ("c5_text_bf16", 4096, 4096, 246, 27, torch.bfloat16),
+          ("c2_text_b32", 960, 32, 45, 27, torch.float32), ("c4like_k50", 51200, 1024, 10, 12, torch.float32),
           ("c1_text", 4096, 4096, 7, 27, torch.float32), ("c3_actions", 4096, 4096, 9, 1, torch.float32),
           ("c3_attrs", 4096, 4096, 4, 6, torch.float32), ("wide_d", 2048, 256, 12, 80, torch.float32)]
 def ref(x, t, rows, B, C, d, w):
