@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--overlap", action="store_true", help="run small kernels on a side stream (measured slower on C2)")
+    ap.add_argument("--overlap-latent", action="store_true", help="run only the latent kernels on a side stream")
     ap.add_argument("--eager-sync", action="store_true",
                     help="N>1: all-reduce after the step (eager NCCL call) instead of inside it (side stream, captured)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -271,7 +272,7 @@ def main():
     # captured in the step graph); --eager-sync: one eager NCCL call after the step.
     in_step_sync = world > 1 and not args.eager_sync
     step = W.LeafStep(cfg, t, device=dev, group=group, global_batch=B * world, sync_grads=in_step_sync)
-    step.overlap = args.overlap
+    step.overlap = "latent" if args.overlap_latent else args.overlap
     W_, K_ = max(args.warmup, 3), args.steps
 
     def sync_grads():

@@ -65,7 +65,9 @@ def make_leaves(name, B=None, seed=1234, recon_dtype=torch.float32):
     post = [syn.make_posterior(g, B, D + pv) for _ in range(M)]
     t = {"mu": torch.stack([p[0] for p in post]), "s": torch.stack([p[1] for p in post]),
          "pz_logits": torch.zeros(1, D)}
-    t["targets"] = [syn.make_target(g, m["target"], B, m["data_dim"]) for m in cfg["mods"]]
+    # bf16 configurations carry bf16 inputs AND outputs (T counted at 2 bytes): targets are rounded to
+    # bf16 once, here; the oracle sees the same rounded values
+    t["targets"] = [syn.make_target(g, m["target"], B, m["data_dim"]).to(recon_dtype) for m in cfg["mods"]]
     Kr = K if cfg["model"] == "moe" else 1
     if cfg.get("latent_only"):
         # synthetic likelihood ROWS (one value per decoder row) instead of reconstructions
@@ -91,7 +93,7 @@ def algorithmic_bytes(cfg, recon_dtype=torch.float32):
             tot += 2 * Kr * 4  # the row value read, its gradient written
             continue
         P = int(math.prod(cfg["mods"][tm]["data_dim"]))
-        R, T = Kr * P * e, P * 4
+        R, T = Kr * P * e, P * e
         tot += (2 * R + T) if cfg["obj"] == "elbo" else (3 * R + 2 * T)
     n_noise = sum(int(math.prod(shape[2:])) * shape[0] for _, shape in
                   _noise_plan(cfg["model"], M, K, 1, D, pv, [m["dist"] for m in cfg["mods"]]))
@@ -224,7 +226,7 @@ class LeafStep:
                 total, n_keep = total + S, n_keep + (S != 0).float()
             kld = torch.stack([k["kl"] for k in kls])
             return total + (self.beta / M) * n_keep * kld.sum()
-        if self.overlap and self.side is not None and any(self.small) and not all(self.small):
+        if self.overlap is True and self.side is not None and any(self.small) and not all(self.small):
             mu0, s0 = self._prior()
             cur = torch.cuda.current_stream()
             self.side.wait_stream(cur)
@@ -239,6 +241,18 @@ class LeafStep:
                     rows[i] = self._rows(i)
             cur.wait_stream(self.side)
             for t in [lq, lpz] + [rows[i] for i in range(len(self.plan)) if self.small[i]]:
+                t.record_stream(cur)
+        elif self.overlap == "latent" and self.side is not None:
+            # only the latency-bound latent kernels (prior scale, sample + log-densities; their backward follows them
+            # onto the same stream) run beside the streaming likelihood kernels
+            cur = torch.cuda.current_stream()
+            self.side.wait_stream(cur)
+            rows = [self._rows(i) for i in range(len(self.plan))]
+            with torch.cuda.stream(self.side):
+                mu0, s0 = self._prior()
+                z, lq, lpz = ops.moe_logdens(self.mu, self.s, mu0, s0, eps, self.codes, True)
+            cur.wait_stream(self.side)
+            for t in (lq, lpz):
                 t.record_stream(cur)
         else:
             # likelihood rows first, latent nodes last: the backward then starts with the latent kernels (see __init__)
