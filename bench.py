@@ -38,8 +38,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default: the workload's batch)")
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
-    ap.add_argument("--overlap", action="store_true", help="run small kernels on a side stream (measured slower on C2)")
-    ap.add_argument("--overlap-latent", action="store_true", help="run only the latent kernels on a side stream")
+    ap.add_argument("--streams", type=int, default=3, choices=[1, 3],
+                    help="3: likelihood terms alternate between two streams + latent kernels on a third (default); 1: one stream")
     ap.add_argument("--eager-sync", action="store_true",
                     help="N>1: all-reduce after the step (eager NCCL call) instead of inside it (side stream, captured)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -272,7 +272,7 @@ def main():
     # captured in the step graph); --eager-sync: one eager NCCL call after the step.
     in_step_sync = world > 1 and not args.eager_sync
     step = W.LeafStep(cfg, t, device=dev, group=group, global_batch=B * world, sync_grads=in_step_sync)
-    step.overlap = "latent" if args.overlap_latent else args.overlap
+    step.streams = args.streams
     W_, K_ = max(args.warmup, 3), args.steps
 
     def sync_grads():
@@ -340,9 +340,11 @@ def main():
         dom = "mmvae_moe_logdens_fwd"
     kt = KernelTimer([dom, "mmvae_loglik_rowreduce_fwd", "mmvae_moe_logdens_bwd"])
     L.timer = kt
+    step.streams = 1  # per-kernel durations: one kernel at a time (the step itself runs two streaming kernels at once)
     for _ in range(min(K_, 10)):
         step.run()
     torch.cuda.synchronize()
+    step.streams = args.streams
     L.timer = None
     tms, dom_bytes = kt.biggest(dom)  # launches of the largest likelihood term, bytes from the actual arguments
     tms = tms[len(tms) // 5:] if len(tms) >= 5 else tms
@@ -425,7 +427,8 @@ def main():
                        "grad_sync": sync_mode,
                        "l2": "per-step working set %.2f GB >> 126 MB L2, no flush" % (step_bytes / 1e9),
                        "launch_mode": "cuda-graph" if runner is not step else "eager",
-                       "streams": "side stream overlaps small kernels" if step.overlap else "single stream"},
+                       "streams": "3 (likelihood terms alternate between two streams, latent kernels on a third; "
+                                  "forks/joins captured in the graph)" if step.streams == 3 else "single stream"},
             "roofline": roofline, "gpu_launches": launches_per_step * K_, "launches_per_step": launches_per_step,
             "clocks": clocks}
     if e2e is not None:

@@ -55,6 +55,14 @@ __device__ __forceinline__ float lg2_ftz(float x) {
     return r;
 }
 
+// MUFU.RCP without __fdividef's range rescue (2 FSETP + 2 predicated FMUL per call: ncu/SASS r1, bf16 fused pass at 32
+// instructions per element).  Callers guarantee a normal, positive argument.
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 template <int LT>
 struct LogP {
     // the accumulated values are multiplied by this once per row (BCE accumulates in log2 units)
@@ -95,7 +103,7 @@ struct LogP {
                 const float l0 = fmaxf(lg2_ftz(x), -144.26950408889634f);
                 v = fmaf(t, l0 - l1, l1);
             }
-            if (NEED_D) d = __fdividef(t - x, fmaxf((1.0f - x) * x, 1e-12f));
+            if (NEED_D) d = (t - x) * rcp_ftz(fmaxf((1.0f - x) * x, 1e-12f));  // denominator in [1e-12, 0.25]
         } else if (LT == MMVAE_LT_BCE_LOGITS) {
             // x holds the decoder logit y.  s = sigmoid(y), xc = clamp(s, lo, hi) with lo = fp32(1e-6), hi = fp32(1-1e-6)
             // (reference decoders.py:96-97), value = t log xc + (1-t) log(1-xc).  log is monotonic, so the clamp moves
@@ -113,7 +121,7 @@ struct LogP {
                 v = fmaf(t, l0 - l1, l1);
             }
             if (NEED_D) {
-                const float r = __fdividef(1.0f, 1.0f + e);
+                const float r = rcp_ftz(1.0f + e);  // 1 + e in [1, 2]
                 const float sg = x >= 0.f ? r : e * r;
                 // clamp passes the gradient only inside [lo, hi]; there x(1-x) >= 1e-6 >> 1e-12, so
                 // (t-x)/max((1-x)x,1e-12) * s(1-s) = t - s
@@ -193,8 +201,8 @@ __global__ void __launch_bounds__(kThreads, Tune<MODE>::kMinBlocks) loglik_kerne
 
     auto process = [&](const float* xv, const float* tv, int i) {
         float gv[V];
-        if (MMVAE_BCE_FAST && LT == MMVAE_LT_BCE && MODE == MODE_FWD && V > 1) {
-            // Value-only BCE fast path.  The clamps max(log x, -100), max(log(1-x), -100) of F.binary_cross_entropy can
+        if (MMVAE_BCE_FAST && LT == MMVAE_LT_BCE && NEED_V && V > 1) {
+            // BCE value fast path (forward and fused passes).  The clamps max(log x, -100), max(log(1-x), -100) of F.binary_cross_entropy can
             // only fire for x == 1 (1-x == 0), x == 0 or a sub-normal x (log x < -100 needs x < 3.7e-44; lg2.ftz flushes
             // those to log 0); in each of these cases -- and for NaN / out-of-range inputs -- an unclamped log is -inf
             // or NaN and so is the sum over the vector.  So: evaluate the vector unclamped (2 MUFU.LG2 + 2 FADD + FFMA +
@@ -219,6 +227,15 @@ __global__ void __launch_bounds__(kThreads, Tune<MODE>::kMinBlocks) loglik_kerne
                         acc += v;
                     }
                 }
+            }
+            if (NEED_D) {  // fused pass: the gradient does not depend on the clamps of the value
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    float v = 0.f, d = 0.f;
+                    f.template eval<false, true>(xv[e], tv[e], v, d);
+                    gv[e] = wl * d;
+                }
+                stg_stream(g + i, Elem<TX>::pack(gv));
             }
         } else {
 #pragma unroll

@@ -130,15 +130,17 @@ class LeafStep:
         else:
             self.eps_stacked = torch.stack(self.noise)  # (M,K,B,D), what mmvae_moe_logdens_* consume
         self._mu0 = torch.zeros(1, self.D, device=dev)
-        # Optional (off by default): run the latency-bound small kernels (latent kernels, short-row likelihood terms) on
-        # a side stream concurrently with the bandwidth-bound long-row terms (fork/join inside the captured graph;
-        # autograd replays each backward node on the stream of its forward).  Measured r1 on C2: 0.554 ms/step with
-        # the overlap vs 0.498 ms without -- the small kernels take SM slots from the streaming kernels -- so the
-        # single-stream order is the default.
-        self.side = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
-        nbytes = [r.numel() * r.element_size() for r in self.recon]
-        self.small = [nb < 0.25 * max(nbytes) for nb in nbytes]
-        self.overlap = False
+        # Stream plan (measured r1 on C2, CUDA-graph replay, ms/step): single stream 0.447; latent kernels on a second
+        # stream 0.439; likelihood terms alternating between two streams 0.430; both (the default, `streams = 3`)
+        # 0.416.  Two streaming kernels resident at a time cover each other's ramp-up and tail, and the latency-bound
+        # latent kernels fill SM slots beside them.  Rejected: long-row terms on one stream and short-row terms on the
+        # other (0.506: the category_ce CTAs take SM slots from the streaming kernels for their whole lifetime).
+        # Forks and joins are stream waits inside the captured graph; autograd replays every backward node on the
+        # stream of its forward, so the backward overlaps the same way.
+        self.streams = 3 if dev.type == "cuda" else 1
+        self.side = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None   # every other likelihood term
+        self.side2 = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None  # latent kernels
+        self._forked = []
         # sync_grads: all-reduce(SUM) the gradient of the replicated prior logits INSIDE the step, launched from a
         # post-accumulate-grad hook on a side stream (parallel.GradSync.arm) and joined at the end of run().  The
         # IWAE / DReG branch creates the latent nodes after the likelihood nodes, so autograd (highest sequence number
@@ -152,6 +154,44 @@ class LeafStep:
     def finish(self):
         if self.sync is not None:
             self.sync.wait()
+
+    # -- stream plan ------------------------------------------------------------------------------------------
+    def _terms(self, fn):
+        """[fn(i) for every likelihood term]; with 3 streams the odd terms are issued on the second stream."""
+        n = len(self.plan)
+        if self.streams == 1 or n < 2:
+            return [fn(i) for i in range(n)]
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        out = [None] * n
+        with torch.cuda.stream(self.side):
+            for i in range(1, n, 2):
+                out[i] = fn(i)
+        for i in range(0, n, 2):
+            out[i] = fn(i)
+        self._forked.append(self.side)
+        return out
+
+    def _latent(self, fn):
+        """fn() (the latent kernels) on the third stream."""
+        if self.streams == 1:
+            return fn()
+        self.side2.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side2):
+            out = fn()
+        self._forked.append(self.side2)
+        return out
+
+    def _join(self, *tensors):
+        """The current stream waits for the forked streams; `tensors` were produced there and are consumed here."""
+        cur = torch.cuda.current_stream()
+        for st in self._forked:
+            cur.wait_stream(st)
+        if self._forked:
+            for t in tensors:
+                if torch.is_tensor(t):
+                    t.record_stream(cur)
+        self._forked = []
 
     def leaves(self):
         return [self.mu, self.s, self.pz_logits] + self.recon
@@ -226,39 +266,15 @@ class LeafStep:
                 total, n_keep = total + S, n_keep + (S != 0).float()
             kld = torch.stack([k["kl"] for k in kls])
             return total + (self.beta / M) * n_keep * kld.sum()
-        if self.overlap is True and self.side is not None and any(self.small) and not all(self.small):
+        # likelihood rows first, latent nodes last: the backward then starts with the latent kernels (see __init__)
+        rows = self._terms(self._rows)
+
+        def latent():
             mu0, s0 = self._prior()
-            cur = torch.cuda.current_stream()
-            self.side.wait_stream(cur)
-            rows = [None] * len(self.plan)
-            with torch.cuda.stream(self.side):
-                z, lq, lpz = ops.moe_logdens(self.mu, self.s, mu0, s0, eps, self.codes, True)
-                for i in range(len(self.plan)):
-                    if self.small[i]:
-                        rows[i] = self._rows(i)
-            for i in range(len(self.plan)):
-                if not self.small[i]:
-                    rows[i] = self._rows(i)
-            cur.wait_stream(self.side)
-            for t in [lq, lpz] + [rows[i] for i in range(len(self.plan)) if self.small[i]]:
-                t.record_stream(cur)
-        elif self.overlap == "latent" and self.side is not None:
-            # only the latency-bound latent kernels (prior scale, sample + log-densities; their backward follows them
-            # onto the same stream) run beside the streaming likelihood kernels
-            cur = torch.cuda.current_stream()
-            self.side.wait_stream(cur)
-            rows = [self._rows(i) for i in range(len(self.plan))]
-            with torch.cuda.stream(self.side):
-                mu0, s0 = self._prior()
-                z, lq, lpz = ops.moe_logdens(self.mu, self.s, mu0, s0, eps, self.codes, True)
-            cur.wait_stream(self.side)
-            for t in (lq, lpz):
-                t.record_stream(cur)
-        else:
-            # likelihood rows first, latent nodes last: the backward then starts with the latent kernels (see __init__)
-            rows = [self._rows(i) for i in range(len(self.plan))]
-            mu0, s0 = self._prior()
-            z, lq, lpz = ops.moe_logdens(self.mu, self.s, mu0, s0, eps, self.codes, True)
+            return ops.moe_logdens(self.mu, self.s, mu0, s0, eps, self.codes, True)
+
+        z, lq, lpz = self._latent(latent)
+        self._join(lq, lpz, *rows)
         L = len(rows) // M
         if self.obj == "iwae":
             return ops.iwae_combine_rows(lpz, lq, rows, L, self.beta)[0]
@@ -267,30 +283,43 @@ class LeafStep:
 
     def _poe(self):
         M, D = self.M, self.D
-        mu0, s0 = self._prior()
         subsets = poe_subsets(range(M))
-        res = ops.latent_draws(self.mu, self.s, mu0, s0, self.eps_packed,
-                               [Draw(mods=sub, prior=True, kl_mode=1, width=D, K=1) for sub in subsets])
-        total = 0.0
-        for i in range(len(self.plan)):
-            total = total + self._wsum(i, w_const=-1.0)[0]
-        return total + self.beta * torch.stack([r["kl"] for r in res]).sum()
+
+        def latent():
+            mu0, s0 = self._prior()
+            res = ops.latent_draws(self.mu, self.s, mu0, s0, self.eps_packed,
+                                   [Draw(mods=sub, prior=True, kl_mode=1, width=D, K=1) for sub in subsets])
+            return self.beta * torch.stack([r["kl"] for r in res]).sum()
+
+        kl = self._latent(latent)
+        sums = self._terms(lambda i: self._wsum(i, w_const=-1.0)[0])
+        self._join(kl, *sums)
+        total = kl
+        for S in sums:
+            total = total + S
+        return total
 
     def _mopoe(self):
         M, D = self.M, self.D
-        mu0, s0 = self._prior()
         draws = [Draw(rowmask=True, kl_mode=1 if i == 0 else 0, width=D, K=1) for i in range(M)]
         draws += [Draw(mods=(i,), direct=True, kl_mode=1, width=D) for i in range(M)]
-        res = ops.latent_draws(self.mu, self.s, mu0, s0, self.eps_packed, draws, self.row_masks)
-        total = 0.0
-        for i in range(len(self.plan)):
-            total = total + self._wsum(i, w_const=-1.0 / self.Bt)[0]
-        kl_all = torch.stack([res[0]["kl"]] + [res[M + i]["kl"] for i in range(M)])
-        return total + self.beta * kl_all.sum() / ((M + 1) * self.Bt)
+
+        def latent():
+            mu0, s0 = self._prior()
+            res = ops.latent_draws(self.mu, self.s, mu0, s0, self.eps_packed, draws, self.row_masks)
+            kl_all = torch.stack([res[0]["kl"]] + [res[M + i]["kl"] for i in range(M)])
+            return self.beta * kl_all.sum() / ((M + 1) * self.Bt)
+
+        kl = self._latent(latent)
+        sums = self._terms(lambda i: self._wsum(i, w_const=-1.0 / self.Bt)[0])
+        self._join(kl, *sums)
+        total = kl
+        for S in sums:
+            total = total + S
+        return total
 
     def _dmvae(self):
         M, D, pv = self.M, self.D, self.pv
-        mu0, s0 = self._prior()
         draws = [Draw(mods=tuple(range(M)), kl_mode=1, width=D, K=1)]
         idx = []
         for i in range(M):
@@ -298,13 +327,22 @@ class LeafStep:
             draws.append(Draw(mods=(i,), direct=True, kl_mode=1, col0=0, width=D, K=1))
             draws.append(Draw(mods=(i,), direct=True, kl_mode=2, col0=D, width=pv, K=1))
             draws += [Draw(mods=(j,), direct=True, col0=0, width=D, K=1) for j in range(M) if j != i]
-        res = ops.latent_draws(self.mu, self.s, mu0, s0, self.eps_packed, draws)
-        total = 0.0
-        for i in range(len(self.plan)):
-            total = total + self._wsum(i, w_const=-1.0)[0]
-        for i in range(M):
-            total = total + self.beta * (res[idx[i]]["kl"].sum() + res[0]["kl"].sum()
-                                         + (M - 1) * res[idx[i] + 1]["kl"].sum())
+
+        def latent():
+            mu0, s0 = self._prior()
+            res = ops.latent_draws(self.mu, self.s, mu0, s0, self.eps_packed, draws)
+            kl = 0.0
+            for i in range(M):
+                kl = kl + self.beta * (res[idx[i]]["kl"].sum() + res[0]["kl"].sum()
+                                       + (M - 1) * res[idx[i] + 1]["kl"].sum())
+            return kl
+
+        kl = self._latent(latent)
+        sums = self._terms(lambda i: self._wsum(i, w_const=-1.0)[0])
+        self._join(kl, *sums)
+        total = kl
+        for S in sums:
+            total = total + S
         return total
 
 
