@@ -110,6 +110,24 @@ __device__ __forceinline__ void cols_accum(const float* xv, const float* tv, int
     a.m = mn;
 }
 
+// running statistics of C classes of one column; px / pt point at the first class, consecutive classes d apart
+template <typename TX, typename TT, int CH, bool GLOBAL>
+__device__ __forceinline__ ColAcc col_partial(const TX* px, const TT* pt, int C, int d) {
+    ColAcc a;
+    int c0 = 0;
+    for (; c0 + CH <= C; c0 += CH) {
+        float xv[CH], tv[CH];
+        cols_load<TX, TT, CH, true, GLOBAL>(px, pt, c0, C, d, xv, tv);
+        cols_accum<CH, true>(xv, tv, c0, C, a);
+    }
+    if (c0 < C) {
+        float xv[CH], tv[CH];
+        cols_load<TX, TT, CH, false, GLOBAL>(px, pt, c0, C, d, xv, tv);
+        cols_accum<CH, false>(xv, tv, c0, C, a);
+    }
+    return a;
+}
+
 // (logsumexp, sum t, sum t*x) of one column; px / pt point at class 0 of the column, consecutive classes d apart
 template <typename TX, typename TT, int CH, bool GLOBAL>
 __device__ __forceinline__ void col_stats(const TX* px, const TT* pt, int C, int d, float& lse, float& ts, float& txs) {
@@ -241,56 +259,50 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
             }
             __syncwarp();
         }
-    } else {  // W warps split the class axis of a row; merged through shared memory
-        const int step = W * p.d;  // running pointers: one IADD per access instead of an IMAD (ncu r1: 94 thread
-                                   // instructions per element on the CUB caption rows, issue bound)
+    } else {
+        // W warps split the class axis of a row into contiguous slices: partial (max, sum exp, sum t, sum t*x) per
+        // slice and column -> smem -> ONE barrier -> every warp merges the W partials of its columns (4 W loads) and
+        // goes straight on to the gradient of its own slice.  (r1: the strided element-at-a-time version with three
+        // barriers ran the CUB caption rows, C = 246, at 2.9 TB/s through the 4-byte cp.async path.)
+        const int Cw = (p.C + W - 1) / W, c_lo = w * Cw;
+        const int c_n = max(0, min(p.C, c_lo + Cw) - c_lo);
         if (live)
             for (int j = lane; j < p.d; j += 32) {
-                float m = -INFINITY;
-                const TX* px = rx + w * p.d + j;
-#pragma unroll 4
-                for (int c = w; c < p.C; c += W, px += step) m = fmaxf(m, Elem<TX>::get(px));
-                part[((size_t)(rl * W + w) * p.d + j) * 4] = m;
-            }
-        __syncthreads();
-        if (live)
-            for (int j = lane; j < p.d; j += 32) {
-                float m = -INFINITY;
-                for (int ww = 0; ww < W; ++ww) m = fmaxf(m, part[((size_t)(rl * W + ww) * p.d + j) * 4]);
-                float se = 0.f, ts = 0.f, txs = 0.f;
-                const float nm = -m * kLog2e;
-                const TX* px = rx + w * p.d + j;
-                const TT* pt = rt + w * p.d + j;
-#pragma unroll 4
-                for (int c = w; c < p.C; c += W, px += step, pt += step) {
-                    const float xv = Elem<TX>::get(px), tv = Elem<TT>::get(pt);
-                    se += exp_shifted(xv, nm);
-                    ts += tv;
-                    txs = fmaf(tv, xv, txs);
-                }
+                const ColAcc a = col_partial<TX, TT, MMVAE_CATCE_SCH, false>(rx + c_lo * p.d + j, rt + c_lo * p.d + j, c_n, p.d);
                 float* q = part + ((size_t)(rl * W + w) * p.d + j) * 4;
-                q[1] = se;
-                q[2] = ts;
-                q[3] = txs;
+                q[0] = a.m;
+                q[1] = a.se();
+                q[2] = a.ts();
+                q[3] = a.txs();
             }
         __syncthreads();
-        if (live && w == 0)
+        if (live) {
+            float wl = 0.f;
+            if (MODE != 0) wl = (p.w_rows ? __ldg(p.w_rows + row0 + rl) : p.w_const) * p.lam;
+            TX* gdst = p.tma ? sx + (size_t)rl * n : reinterpret_cast<TX*>(p.g) + (row0 + rl) * p.ldg;
             for (int j = lane; j < p.d; j += 32) {
-                float mm = -INFINITY;  // every slice summed exp(x - mm) against the same global max
+                float mm = -INFINITY;
                 for (int ww = 0; ww < W; ++ww) mm = fmaxf(mm, part[((size_t)(rl * W + ww) * p.d + j) * 4]);
+                const float nm = (mm == -INFINITY) ? 0.f : -mm * kLog2e;
                 float se = 0.f, ts = 0.f, txs = 0.f;
                 for (int ww = 0; ww < W; ++ww) {
                     const float* q = part + ((size_t)(rl * W + ww) * p.d + j) * 4;
-                    se += q[1];
+                    se = fmaf(q[1], ex2_ftz(fmaf(q[0], kLog2e, nm)), se);  // rescale each slice to the global max
                     ts += q[2];
                     txs += q[3];
                 }
                 const float lse = mm + logf(se);
-                s_lse[rl * p.d + j] = lse;
-                s_ts[rl * p.d + j] = ts;
-                acc += txs - lse * ts;
+                if (w == 0) {
+                    s_lse[rl * p.d + j] = lse;
+                    s_ts[rl * p.d + j] = ts;
+                    acc += txs - lse * ts;
+                }
+                if (MODE != 0)
+                    col_grad<TX, TT, MMVAE_CATCE_SCH, false>(rx + c_lo * p.d + j, rt + c_lo * p.d + j, gdst + c_lo * p.d + j,
+                                                             c_n, p.d, lse, ts, wl);
             }
-        __syncthreads();
+        }
+        __syncwarp();
     }
     if (MODE != 1 && live && w == 0) {
         acc = warp_sum(acc);
@@ -306,22 +318,11 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
         TX* gs = sx + (size_t)rl * n;  // in-place staging of the gradient when it leaves through TMA
         if (live) {
             const float wl = (p.w_rows ? __ldg(p.w_rows + row0 + rl) : p.w_const) * p.lam;
-            const int step = W * p.d;
             TX* gdst = p.tma ? gs : gr;  // in-place smem staging (leaves through TMA) or straight to global
-            for (int j = lane; j < p.d; j += 32) {
-                if (W == 1) {
+            if (W == 1)  // (W > 1: the gradient of every slice was written right after the merge above)
+                for (int j = lane; j < p.d; j += 32)
                     col_grad<TX, TT, MMVAE_CATCE_SCH, false>(rx + j, rt + j, gdst + j, p.C, p.d, s_lse[rl * p.d + j],
                                                              s_ts[rl * p.d + j], wl);
-                    continue;
-                }
-                const float nl = -s_lse[rl * p.d + j] * kLog2e, wts = -wl * s_ts[rl * p.d + j];
-                const TX* px = rx + w * p.d + j;
-                const TT* pt = rt + w * p.d + j;
-                TX* pg = gdst + w * p.d + j;
-#pragma unroll 4
-                for (int c = w; c < p.C; c += W, px += step, pt += step, pg += step)  // wl*t - wl*ts*softmax
-                    Elem<TX>::store1(pg, fmaf(exp_shifted(Elem<TX>::get(px), nl), wts, wl * Elem<TT>::get(pt)));
-            }
         }
         if (p.tma) {
             fence_async_smem();  // generic-proxy smem writes -> visible to the async (TMA) proxy
@@ -789,7 +790,10 @@ static int launch_catce(int mode, CatceParams p, cudaStream_t st) {
     // warps per row split the class axis (short dependency chains); the cached-statistics backward has no per-row
     // reduction and simply strides all warps over the staged class rows
     // (measured r1, C = 45: W = 1 -> 17 us, W = 4 -> 27 us: the merge costs more than the shorter chains save)
-    int W = fast_bwd ? 1 : (p.C >= 192 ? 8 : (p.C >= 96 ? 4 : 1));
+#ifndef MMVAE_CATCE_W_LONG
+#define MMVAE_CATCE_W_LONG 2
+#endif
+    int W = fast_bwd ? 1 : (p.C >= 96 ? MMVAE_CATCE_W_LONG : 1);
     int R = fast_bwd ? 4 : (W == 1 ? 8 : 16 / W);
     // a CTA's life is TMA latency + a short compute phase: favour many resident CTAs (<= 48 KB each) ...
     while (R > 1 && catce_smem(R, W, n, p.d, sx, stt) > 48 * 1024) R >>= 1;

@@ -7,12 +7,10 @@ cd "$(dirname "$0")/.."
 SRC=multimodal-vae-comparison_b200/csrc
 OUT=gpurun_out/tune_catce; mkdir -p $OUT; rm -f $OUT/lib_*.so
 declare -A V
-V[v1_tma]="-DMMVAE_CATCE_IMPL=0 -DMMVAE_CATCE_RING=0"
-V[v1_flatbwd]="-DMMVAE_CATCE_IMPL=1 -DMMVAE_CATCE_RING=0"
-V[v2_cols_ch16]="-DMMVAE_CATCE_IMPL=2 -DMMVAE_CATCE_RING=0"
-V[ring_xb24]="-DMMVAE_CATCE_RING=1"
-V[ring_xb40]="-DMMVAE_CATCE_RING=1 -DMMVAE_CATCE_RING_XB=40960 -DMMVAE_CATCE_RING_SMEM=221184"
-V[ring_xb12]="-DMMVAE_CATCE_RING=1 -DMMVAE_CATCE_RING_XB=12288 -DMMVAE_CATCE_RING_SMEM=75000"
+V[cur_w2]=""
+V[w4]="-DMMVAE_CATCE_W_LONG=4"
+V[w1]="-DMMVAE_CATCE_W_LONG=1"
+V[v2_cols]="-DMMVAE_CATCE_IMPL=2"
 for k in "${!V[@]}"; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -Iinclude ${V[$k]} -shared $SRC/catce.cu -o $OUT/lib_$k.so -lcudart > $OUT/build_$k.log 2>&1 &
 done
@@ -23,7 +21,7 @@ c_p, c_i, c_i64, c_f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_f
 flush = torch.empty(64 << 20, device="cuda")
 # (name, rows, B, C, d, recon dtype)
 SHAPES = [("c2_text", 7680, 256, 45, 27, torch.float32), ("c5_text_bf16", 4096, 4096, 246, 27, torch.bfloat16),
-          ("c2_text_b32", 960, 32, 45, 27, torch.float32), ("c4like_k50", 51200, 1024, 10, 12, torch.float32),
+          ("c5_text_f32", 4096, 4096, 246, 27, torch.float32), ("mid_c128", 4096, 4096, 128, 27, torch.float32),
           ("c1_text", 4096, 4096, 7, 27, torch.float32), ("c3_actions", 4096, 4096, 9, 1, torch.float32),
           ("c3_attrs", 4096, 4096, 4, 6, torch.float32), ("wide_d", 2048, 256, 12, 80, torch.float32)]
 def ref(x, t, rows, B, C, d, w):
@@ -39,18 +37,19 @@ for name, rows, B, C, d, dt in SHAPES:
     x = torch.randn(rows, n, device="cuda", generator=g).to(dt)
     t = torch.nn.functional.one_hot(torch.randint(d, (B, C), device="cuda", generator=g), d).float().view(B, n)
     t = t * (torch.rand(B, C, 1, device="cuda", generator=g) > 0.3).float().expand(B, C, d).reshape(B, n)  # padded positions
+    t = t.to(dt).contiguous()  # bf16 configurations carry bf16 targets
     w = torch.randn(rows, device="cuda", generator=g)
     rv, rg = ref(x, t, rows, B, C, d, w)
     out = torch.empty(rows, device="cuda"); grad = torch.empty_like(x); stats = torch.empty(rows, 2, d, device="cuda")
     dtc = 0 if dt == torch.float32 else 1
-    nb_f, nb_b = x.numel() * x.element_size() + t.numel() * 4, 2 * x.numel() * x.element_size() + t.numel() * 4
+    nb_f, nb_b = x.numel() * x.element_size() + t.numel() * t.element_size(), 2 * x.numel() * x.element_size() + t.numel() * t.element_size()
     for lib in sorted(glob.glob("gpurun_out/tune_catce/lib_*.so")):
         L = ctypes.CDLL(lib)
         f = L.mmvae_catce_rows; f.restype = c_i
         f.argtypes = [c_i, c_p, c_i64, c_i, c_p, c_i64, c_i, c_i64, c_i64, c_i64, c_i64, c_f, c_p, c_f, c_p, c_p, c_i64, c_p, c_p]
         st = torch.cuda.current_stream().cuda_stream
         def run(mode, with_stats=True):
-            rc = f(mode, x.data_ptr(), n, dtc, t.data_ptr(), n, 0, rows, B, C, d, 1.0, w.data_ptr(), 0.0, out.data_ptr(),
+            rc = f(mode, x.data_ptr(), n, dtc, t.data_ptr(), n, dtc, rows, B, C, d, 1.0, w.data_ptr(), 0.0, out.data_ptr(),
                    grad.data_ptr(), n, stats.data_ptr() if with_stats else None, st)
             assert rc == 0, (lib, mode, rc)
         tm = {}
