@@ -130,6 +130,7 @@ class LeafStep:
         else:
             self.eps_stacked = torch.stack(self.noise)  # (M,K,B,D), what mmvae_moe_logdens_* consume
         self._mu0 = torch.zeros(1, self.D, device=dev)
+        self._one = torch.ones((), device=dev)
         # Stream plan (measured r1 on C2, CUDA-graph replay, ms/step): single stream 0.447; latent kernels on a second
         # stream 0.439; likelihood terms alternating between two streams 0.430; both (the default, `streams = 3`)
         # 0.416.  Two streaming kernels resident at a time cover each other's ramp-up and tail, and the latency-bound
@@ -239,7 +240,7 @@ class LeafStep:
     def run(self):
         self.zero_grad()
         loss = self.loss()
-        loss.backward()
+        loss.backward(self._one)  # static root gradient: no ones_like fill kernel at the head of the backward
         self.finish()
         return loss
 
@@ -363,7 +364,7 @@ class GraphedStep:
         step.zero_grad()
         with torch.cuda.graph(self.graph):
             self.loss = step.loss()
-            self.loss.backward()
+            self.loss.backward(step._one)
             step.finish()  # joins the side stream of an in-step gradient all-reduce into the capture
         self.grads = [t.grad for t in step.leaves()]
 
