@@ -124,7 +124,8 @@ class GradSync:
         """Register the hooks (idempotent).  Every parameter of the bucket must receive a gradient in every backward."""
         if self._handles or not self.active():
             return self
-        self._side = torch.cuda.Stream(device=self.params[0].device)
+        dev = self.params[0].device
+        self._side = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None  # CPU tensors: reduce in the hook
         for p in self.params:
             self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad))
         return self
@@ -139,14 +140,24 @@ class GradSync:
         if self._seen < len(self.params):
             return
         self._seen = 0
-        cur = torch.cuda.current_stream()  # the stream the gradient was accumulated on
-        self._side.wait_stream(cur)
-        with torch.cuda.stream(self._side):
+        if self._side is None:
             self._reduce()
+        else:
+            cur = torch.cuda.current_stream()  # the stream the gradient was accumulated on
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self._reduce()
         self._inflight = True
 
     def wait(self):
-        """Join the side stream: after this the current stream sees the reduced gradients."""
+        """Join the side stream: after this the current stream sees the reduced gradients.  If the hooks did not
+        complete the bucket in this backward (a parameter received no gradient -- e.g. the prior logits under MoE-ELBO),
+        the collective runs here instead, so every rank still issues exactly one all-reduce per step."""
+        if not self._handles:
+            return
         if self._inflight:
-            torch.cuda.current_stream().wait_stream(self._side)
-            self._inflight = False
+            if self._side is not None:
+                torch.cuda.current_stream().wait_stream(self._side)
+        else:
+            self._reduce()
+        self._inflight, self._seen = False, 0

@@ -88,6 +88,23 @@ def _worker(rank, world, port, q):
         log_sigma = refmath.softclip((ss / x.numel()).sqrt().log(), -6)
         rows = -(((tt[lo:hi] - x[lo:hi]) / log_sigma.exp()) ** 2 + log_sigma + 0.5 * math.log(2 * math.pi)).sum(-1)
         res["osigma"] = float((rows - full[lo:hi]).abs().max() / full.abs().max())
+        # ---- armed GradSync: hooks fire the flat-bucket all-reduce once the LAST gradient exists; wait() runs it when
+        # a parameter got no gradient in this backward (every rank still issues exactly one collective per step)
+        a, b, c = (torch.nn.Parameter(torch.full((3,), float(i + 1))) for i in range(3))
+        sync = par.GradSync([a, b, c]).arm()
+        ((a * (rank + 1)).sum() + (b * 2.0).sum() + (c * 0.5 * (rank + 1)).sum()).backward()
+        fired_in_hook = sync._inflight
+        sync.wait()
+        ok = fired_in_hook and torch.allclose(a.grad, torch.full((3,), 3.0)) and torch.allclose(b.grad, torch.full((3,), 4.0)) \
+            and torch.allclose(c.grad, torch.full((3,), 1.5))
+        for p_ in (a, b, c):
+            p_.grad = None
+        ((a * (rank + 1)).sum() + (b * 2.0).sum()).backward()  # c unused: the bucket is completed in wait()
+        late = not sync._inflight
+        sync.wait()
+        ok = ok and late and torch.allclose(a.grad, torch.full((3,), 3.0)) and torch.allclose(c.grad, torch.zeros(3))
+        sync.disarm()
+        res["gradsync_armed"] = 0.0 if ok else 1.0
         if rank == 0:
             q.put(res)
     finally:

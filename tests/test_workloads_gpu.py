@@ -44,6 +44,35 @@ def test_leafstep_matches_oracle(name, B, tol, graphed):
         assert _rel(r.grad, ref_g["recon%d" % i]) < 5 * tol, i
 
 
+@pytest.mark.parametrize("name,B", [("c2_moe_iwae_cdsprites_l5", 16), ("c1_poe_elbo_cdsprites_l1", 64),
+                                    ("c3_mopoe_elbo_sprites", 8), ("c4_moe_dreg_mnistsvhn", 32), ("c5_dmvae_elbo_cub", 16)])
+def test_stream_plan_is_bit_identical(name, B):
+    """The 3-stream step (likelihood terms alternating between two streams, latent kernels on a third; eager and
+    captured) computes exactly what the single-stream step computes: the kernels are deterministic and the stream plan
+    only changes WHEN they run."""
+    import mmvae_b200.workloads as W
+    cfg, t = W.make_leaves(name, B=B, seed=81)
+    t["pz_logits"] = torch.randn(1, cfg["D"], generator=torch.Generator().manual_seed(6)) * 0.3
+    one = W.LeafStep(cfg, t)
+    one.streams = 1
+    l1 = one.run().detach().clone()
+    g1 = [x.grad.clone() for x in one.leaves()]
+    for graphed in (False, True):
+        three = W.LeafStep(cfg, t)
+        assert three.streams == 3
+        if graphed:
+            gs = W.GraphedStep(three)
+            gs.run()
+            l3 = gs.run()
+        else:
+            three.run()
+            l3 = three.run()
+        torch.cuda.synchronize()
+        assert torch.equal(l1, l3.detach()), (graphed, float(l1), float(l3))
+        for a, x in zip(g1, three.leaves()):
+            assert torch.equal(a, x.grad)
+
+
 def test_c5_bf16_matches_oracle():
     """Config 5: bf16 reconstructions / gradients, fp32 accumulation; tolerance 1e-2 (north_star)."""
     import mmvae_b200.workloads as W
