@@ -236,6 +236,16 @@ MMVAE_API int mmvae_objective_iwae(const float* lpz, const float* lq, const floa
 MMVAE_API int mmvae_objective_iwae_ptrs(const float* lpz, const float* lq, const float* lpx,
                               const float* const* lpx_ptrs_host, int M, int L, int K, int64_t B, float beta,
                               float* lw, float* loss_b, float* w, float* dlq, void* stream);
+/* same, plus what a backward with a UNIT upstream gradient needs and the batch sum of the loss, so that the serial
+ * section between the forward and the backward kernels of a step is one launch instead of four:
+ *   dlpz_unit (M,K,B) = -w (gradient of lpz and of every likelihood row vector of modality r for g == 1; dlq already
+ *   holds the g == 1 gradient of lq); loss_sum = sum_b loss_b, summed in a fixed order by the CTA that finishes last
+ *   (ticket: one zero-initialised unsigned int owned by the caller; it is zero again when the kernel ends).
+ * dlpz_unit, loss_sum and ticket may be NULL (loss_sum and ticket only together). */
+MMVAE_API int mmvae_objective_iwae_fused(const float* lpz, const float* lq, const float* lpx,
+                               const float* const* lpx_ptrs_host, int M, int L, int K, int64_t B, float beta,
+                               float* lw, float* loss_b, float* w, float* dlq, float* dlpz_unit, float* loss_sum,
+                               unsigned int* ticket, void* stream);
 /* IWAE backward in one launch: dlpz_out = -g*w (n_w floats; also the gradient of each likelihood row vector of the
  * same modality), dlq_inout *= g (n_dlq floats); g_dev: device scalar (upstream gradient of the loss). */
 MMVAE_API int mmvae_objective_iwae_bwd(const float* g_dev, const float* w, float* dlq_inout, float* dlpz_out,

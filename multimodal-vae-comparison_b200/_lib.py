@@ -52,6 +52,8 @@ SIGNATURES = {
     "mmvae_objective_iwae": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i64, c_f, c_p, c_p, c_p, c_p, c_p]),
     "mmvae_objective_iwae_ptrs": (c_i, [c_p, c_p, c_p, ctypes.POINTER(c_p), c_i, c_i, c_i, c_i64, c_f, c_p, c_p, c_p,
                                         c_p, c_p]),
+    "mmvae_objective_iwae_fused": (c_i, [c_p, c_p, c_p, ctypes.POINTER(c_p), c_i, c_i, c_i, c_i64, c_f, c_p, c_p, c_p,
+                                         c_p, c_p, c_p, c_p, c_p]),
     "mmvae_objective_iwae_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_p]),
     "mmvae_prior_scale_fwd": (c_i, [c_p, c_i, c_p, c_p]),
     "mmvae_prior_scale_bwd": (c_i, [c_p, c_p, c_i, c_p, c_p]),
@@ -67,7 +69,7 @@ launch_count = 0
 _LAUNCHES = {"mmvae_loglik_rowreduce_fwd": 1, "mmvae_loglik_rowreduce_bwd": 1, "mmvae_loglik_rowreduce_fused": 1,
              "mmvae_catce_rows": 1, "mmvae_osigma_sumsq": 1, "mmvae_osigma_fwd": 1, "mmvae_osigma_bwd": 2,
              "mmvae_latent_draws_fwd": 1, "mmvae_latent_draws_bwd": 2, "mmvae_moe_logdens_fwd": 1,
-             "mmvae_moe_logdens_bwd": 2, "mmvae_objective_iwae": 1, "mmvae_objective_dreg_stage1": 2,
+             "mmvae_moe_logdens_bwd": 2, "mmvae_objective_iwae": 1, "mmvae_objective_iwae_fused": 1, "mmvae_objective_dreg_stage1": 2,
              "mmvae_objective_dreg_stage2": 1, "mmvae_reduce_sum": 1, "mmvae_scale_inplace": 1}
 
 

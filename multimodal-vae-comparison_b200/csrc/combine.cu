@@ -18,6 +18,10 @@ struct CombParams {
     int64_t B;
     int M, L, K;
     float beta;
+    // fused variant (mmvae_objective_iwae_fused): gradients for a unit upstream gradient + in-kernel batch sum
+    float* dlpz_unit;      // (M,K,B): -w
+    float* loss_sum;       // scalar: sum_b loss_b, written by the last CTA in a fixed order
+    unsigned int* ticket;  // zero on entry, zero again on exit
 };
 
 // log-mean-exp over j of lq[r,j,k,b]; also returns max and sum for the softmax_j
@@ -95,12 +99,12 @@ __global__ void __launch_bounds__(kIwaeBT * kIwaeSlots) iwae_kernel(const CombPa
 #pragma unroll
     for (int w = 0; w < 8; ++w) lse_merge(tm, ts, s_m[w * kIwaeBT + bl], s_s[w * kIwaeBT + bl]);
     const float lse = tm + logf(ts);
-    if (!ok) return;
-    if (threadIdx.x < kIwaeBT) p.loss_b[b] = -(lse - logf((float)n));
-    for (int q = slot; q < n; q += kIwaeSlots) {
+    if (ok && threadIdx.x < kIwaeBT) p.loss_b[b] = -(lse - logf((float)n));
+    for (int q = slot; ok && q < n; q += kIwaeSlots) {
         const int r = q / p.K, k = q - r * p.K;
         const float wv = expf(s_lw[q * kIwaeBT + bl] - lse);
         p.w[((int64_t)r * p.K + k) * p.B + b] = wv;
+        if (p.dlpz_unit) p.dlpz_unit[((int64_t)r * p.K + k) * p.B + b] = -wv;
         if (p.dlq) {
             float mx, se;
             lme_j(p, r, k, b, vals, mx, se);
@@ -108,6 +112,26 @@ __global__ void __launch_bounds__(kIwaeBT * kIwaeSlots) iwae_kernel(const CombPa
 #pragma unroll
             for (int j = 0; j < MMVAE_MAX_MODS; ++j)
                 if (j < p.M) p.dlq[(((int64_t)r * p.M + j) * p.K + k) * p.B + b] = c * expf(vals[j] - mx);
+        }
+    }
+    if (p.loss_sum) {
+        // deterministic batch sum without a second launch: the CTA that takes the last ticket sums loss_b in a fixed
+        // order (threads stride over b, fixed-shape block reduction); the ticket is left at zero for the next call
+        __shared__ unsigned int s_last;
+        __shared__ float s_red[32];
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            float a = 0.f;
+            for (int64_t i = threadIdx.x; i < p.B; i += blockDim.x) a += __ldcg(p.loss_b + i);
+            const float tot = block_sum(a, s_red);
+            if (threadIdx.x == 0) {
+                *p.loss_sum = tot;
+                *p.ticket = 0u;
+            }
         }
     }
 }
@@ -276,11 +300,21 @@ extern "C" int mmvae_objective_iwae(const float* lpz, const float* lq, const flo
 extern "C" int mmvae_objective_iwae_ptrs(const float* lpz, const float* lq, const float* lpx,
                                          const float* const* lpx_ptrs_host, int M, int L, int K, int64_t B, float beta,
                                          float* lw, float* loss_b, float* w, float* dlq, void* stream) {
+    return mmvae_objective_iwae_fused(lpz, lq, lpx, lpx_ptrs_host, M, L, K, B, beta, lw, loss_b, w, dlq, nullptr, nullptr,
+                                      nullptr, stream);
+}
+
+extern "C" int mmvae_objective_iwae_fused(const float* lpz, const float* lq, const float* lpx,
+                                          const float* const* lpx_ptrs_host, int M, int L, int K, int64_t B, float beta,
+                                          float* lw, float* loss_b, float* w, float* dlq, float* dlpz_unit,
+                                          float* loss_sum, unsigned int* ticket, void* stream) {
     CombParams p{};
     int rc = comb_fill(p, lpz, lq, lpx, lpx_ptrs_host, M, L, K, B);
     if (rc) return rc;
     if (!lw || !loss_b || !w) return MMVAE_E_ARG;
+    if ((loss_sum != nullptr) != (ticket != nullptr)) return MMVAE_E_ARG;
     p.beta = beta; p.lw = lw; p.loss_b = loss_b; p.w = w; p.dlq = dlq;
+    p.dlpz_unit = dlpz_unit; p.loss_sum = loss_sum; p.ticket = ticket;
     const int n = M * K;
     const size_t smem = (size_t)(n * kIwaeBT + 2 * 8 * kIwaeBT) * sizeof(float);
     if (smem > 200 * 1024) return MMVAE_E_LIMIT;

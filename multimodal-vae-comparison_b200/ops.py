@@ -15,6 +15,40 @@ from ._lib import DrawDesc, call
 _P = ctypes.c_void_p
 
 
+# Upstream gradients that are known to be exactly 1 WITHOUT looking at device memory: a caller that starts its backward
+# from a static ones tensor (``loss.backward(one)``) registers it here; a backward node whose incoming gradient has the
+# same address can then skip its "scale by grad_output" launch altogether.  The registry keeps the tensors alive, so a
+# registered address can never be recycled for other data (the owner must not write to it).
+_UNIT_GRADS = {}
+_TICKETS = {}
+
+
+def mark_unit_grad(t: torch.Tensor) -> torch.Tensor:
+    _UNIT_GRADS[t.data_ptr()] = t
+    return t
+
+
+def _is_unit(g: Optional[torch.Tensor]) -> bool:
+    return g is not None and g.numel() == 1 and g.data_ptr() in _UNIT_GRADS
+
+
+def new_ticket(device) -> torch.Tensor:
+    """A zero-initialised counter for kernels that elect their last CTA; the kernel leaves it at zero, so one ticket
+    serves every launch of its owner as long as those launches are stream ordered."""
+    return torch.zeros(1, dtype=torch.int32, device=device)
+
+
+def _ticket(device) -> torch.Tensor:
+    """Default ticket: cached per (device, stream) for eager launches; a fresh one inside a CUDA-graph capture (it then
+    lives in that graph's memory pool -- a cached tensor must not outlive the graph it was captured in)."""
+    if torch.cuda.is_current_stream_capturing():
+        return new_ticket(device)
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    if key not in _TICKETS:
+        _TICKETS[key] = new_ticket(device)
+    return _TICKETS[key]
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return _P(0) if t is None else _P(t.data_ptr())
 
@@ -148,7 +182,8 @@ class _LoglikWeightedSum(torch.autograd.Function):
             raise RuntimeError("mmvae_b200: the fused ELBO gradient buffer is single-use (retain_graph unsupported)")
         g, ctx.g = ctx.g, None
         gs = gS.detach().to(torch.float32).contiguous()
-        call("mmvae_scale_inplace", _ptr(g), _dt(g), g.numel(), _ptr(gs), _stream())
+        if not _is_unit(gS):  # (the kernel itself exits at once when *gs == 1; a registered unit gradient skips the launch)
+            call("mmvae_scale_inplace", _ptr(g), _dt(g), g.numel(), _ptr(gs), _stream())
         gw = (gs * ctx.rows_out) if ctx.w_needs else None
         return g.view(ctx.shape), None, gw, None, None, None, None
 
@@ -249,7 +284,8 @@ class _CatceWeightedSum(torch.autograd.Function):
             raise RuntimeError("mmvae_b200: the fused ELBO gradient buffer is single-use (retain_graph unsupported)")
         g, ctx.g = ctx.g, None
         gs = gS.detach().to(torch.float32).contiguous()
-        call("mmvae_scale_inplace", _ptr(g), _dt(g), g.numel(), _ptr(gs), _stream())
+        if not _is_unit(gS):
+            call("mmvae_scale_inplace", _ptr(g), _dt(g), g.numel(), _ptr(gs), _stream())
         gw = (gs * ctx.rows_out) if ctx.w_needs else None
         return g.view(ctx.shape), None, gw, None, None
 
@@ -529,7 +565,7 @@ class _IwaeRows(torch.autograd.Function):
     (no stack copy); the backward is one launch and hands every row vector of modality r the same gradient -g*w[r]."""
 
     @staticmethod
-    def forward(ctx, lpz, lq, beta, L, *rows):
+    def forward(ctx, lpz, lq, beta, L, ticket, *rows):
         ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(lpz, lq, *rows)
         M, K, B = lpz.shape
@@ -544,11 +580,14 @@ class _IwaeRows(torch.autograd.Function):
         loss_b = torch.empty(B, dtype=torch.float32, device=dev)
         w = torch.empty((M, K, B), dtype=torch.float32, device=dev)
         dlq = torch.empty((M, M, K, B), dtype=torch.float32, device=dev)
-        call("mmvae_objective_iwae_ptrs", _ptr(lpz_c), _ptr(lq_c), _P(0), ptrs, M, L, K, B, float(beta), _ptr(lw),
-             _ptr(loss_b), _ptr(w), _ptr(dlq), _stream())
+        nw = torch.empty((M, K, B), dtype=torch.float32, device=dev)  # -w: the gradients for a unit upstream gradient
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        call("mmvae_reduce_sum", _ptr(loss_b), B, 1.0, _ptr(loss), _stream())
+        # one launch: log-weights, per-sample loss, softmax weights, d/dlq, -w and the batch sum of the loss
+        call("mmvae_objective_iwae_fused", _ptr(lpz_c), _ptr(lq_c), _P(0), ptrs, M, L, K, B, float(beta), _ptr(lw),
+             _ptr(loss_b), _ptr(w), _ptr(dlq), _ptr(nw), _ptr(loss), _ptr(ticket if ticket is not None else _ticket(dev)),
+             _stream())
         ctx.save_for_backward(w, dlq)
+        ctx.nw = nw
         ctx.meta = (M, L, K, B, [r.shape for r in rows])
         ctx.mark_non_differentiable(lw)
         return loss, lw
@@ -558,18 +597,22 @@ class _IwaeRows(torch.autograd.Function):
         w, dlq = ctx.saved_tensors
         M, L, K, B, shapes = ctx.meta
         if g is None:
-            return (None, None, None, None) + (None,) * (M * L)
-        gs = g.detach().float().contiguous()
-        dlpz = torch.empty_like(w)
+            return (None, None, None, None, None) + (None,) * (M * L)
         dlq_out = dlq  # scaled in place by g (single-use buffer, like the fused ELBO gradient)
-        call("mmvae_objective_iwae_bwd", _ptr(gs), _ptr(w), _ptr(dlq_out), _ptr(dlpz), w.numel(), dlq_out.numel(), _stream())
+        if _is_unit(g):  # registered unit gradient: the forward already produced every gradient, nothing to launch
+            dlpz, ctx.nw = ctx.nw, None
+        else:
+            gs = g.detach().float().contiguous()
+            dlpz = torch.empty_like(w)
+            call("mmvae_objective_iwae_bwd", _ptr(gs), _ptr(w), _ptr(dlq_out), _ptr(dlpz), w.numel(), dlq_out.numel(),
+                 _stream())
         row_grads = [dlpz[i // L].reshape(shapes[i]) for i in range(M * L)]
-        return (dlpz, dlq_out, None, None) + tuple(row_grads)
+        return (dlpz, dlq_out, None, None, None) + tuple(row_grads)
 
 
-def iwae_combine_rows(lpz, lq, rows, L, beta):
-    """rows: list of M*L tensors (K*B,), index r*L + l."""
-    return _IwaeRows.apply(lpz, lq, float(beta), int(L), *rows)
+def iwae_combine_rows(lpz, lq, rows, L, beta, ticket=None):
+    """rows: list of M*L tensors (K*B,), index r*L + l.  ticket: optional counter from new_ticket() owned by the caller."""
+    return _IwaeRows.apply(lpz, lq, float(beta), int(L), ticket, *rows)
 
 
 class _PriorScale(torch.autograd.Function):

@@ -130,7 +130,8 @@ class LeafStep:
         else:
             self.eps_stacked = torch.stack(self.noise)  # (M,K,B,D), what mmvae_moe_logdens_* consume
         self._mu0 = torch.zeros(1, self.D, device=dev)
-        self._one = torch.ones((), device=dev)
+        self._ticket = ops.new_ticket(dev) if dev.type == "cuda" else None
+        self._one = ops.mark_unit_grad(torch.ones((), device=dev)) if dev.type == "cuda" else torch.ones(())
         # Stream plan (measured r1 on C2, CUDA-graph replay, ms/step): single stream 0.447; latent kernels on a second
         # stream 0.439; likelihood terms alternating between two streams 0.430; both (the default, `streams = 3`)
         # 0.416.  Two streaming kernels resident at a time cover each other's ramp-up and tail, and the latency-bound
@@ -278,7 +279,7 @@ class LeafStep:
         self._join(lq, lpz, *rows)
         L = len(rows) // M
         if self.obj == "iwae":
-            return ops.iwae_combine_rows(lpz, lq, rows, L, self.beta)[0]
+            return ops.iwae_combine_rows(lpz, lq, rows, L, self.beta, self._ticket)[0]
         lpx = torch.stack(rows).view(M, L, K, B)
         return ops.dreg_combine(lpz, lq, lpx, self.group)[0]
 
