@@ -600,6 +600,8 @@ class _IwaeRows(torch.autograd.Function):
             return (None, None, None, None, None) + (None,) * (M * L)
         dlq_out = dlq  # scaled in place by g (single-use buffer, like the fused ELBO gradient)
         if _is_unit(g):  # registered unit gradient: the forward already produced every gradient, nothing to launch
+            if ctx.nw is None:
+                raise RuntimeError("mmvae_b200: the IWAE gradient buffers are single-use (retain_graph unsupported)")
             dlpz, ctx.nw = ctx.nw, None
         else:
             gs = g.detach().float().contiguous()
