@@ -195,7 +195,7 @@ def cpu_baseline(args):
                 args.cpu_batch, args.workload, cfg["K"], n, dt)}
 
 
-def plugin_e2e(cfg, B, dev, steps, fused_tail=False):
+def plugin_e2e(cfg, B, dev, steps, fused_tail=False, graphed=False):
     import torch
     import mmvae_b200
     import mmvae_b200.synthetic as syn
@@ -213,8 +213,15 @@ def plugin_e2e(cfg, B, dev, steps, fused_tail=False):
     model = mmvae_b200.MODEL_REGISTRY[cfg["model"]](vaes, cfg["D"], {"obj": cfg["obj"], "beta": 1.0, "K": cfg["K"]}, None).to(dev)
     params = [p for p in model.parameters() if p.requires_grad]
 
+    gobj = None
+    if graphed:  # the whole plugin step (encoders, kernels, decoders, backward) as ONE captured graph
+        gobj = mmvae_b200.GraphedObjective(
+            model, {k: {"data": v.to(dev), "masks": None, "categorical": False} for k, v in host.items()})
+
     def step():
         batch = {k: {"data": v.to(dev, non_blocking=True), "masks": None, "categorical": False} for k, v in host.items()}
+        if gobj is not None:
+            return float(gobj.step(batch)["loss"].detach())
         for p in params:
             p.grad = None
         loss = model.objective(batch)["loss"]
@@ -234,8 +241,9 @@ def plugin_e2e(cfg, B, dev, steps, fused_tail=False):
     return {"value": B * steps / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms / steps, "steps": steps,
             "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()), "d2h_bytes_per_step": 4,
             "api": "mmvae_b200.%s(vaes, ...).objective(batch) + backward, linear stand-in encoders/decoders (torch), "
-                   "eager launches%s" % (cfg["model"], "; decoder tail sigmoid+clamp fused into the likelihood kernel "
-                                         "(bce_logits)" if fused_tail else "")}
+                   "%s%s" % (cfg["model"], "mmvae_b200.GraphedObjective (one CUDA-graph replay per step)" if graphed
+                             else "eager launches", "; decoder tail sigmoid+clamp fused into the likelihood kernel "
+                             "(bce_logits)" if fused_tail else "")}
 
 
 _REAL_STDOUT = None
@@ -437,6 +445,11 @@ def main():
             e2e_plugin = plugin_e2e(cfg, B, dev, max(3, min(K_, 10)))
             if any(m["ltype"] == "bce" for m in cfg["mods"]):
                 e2e_plugin["fused_decoder_tail"] = plugin_e2e(cfg, B, dev, max(3, min(K_, 10)), fused_tail=True)
+            try:
+                e2e_plugin["graphed"] = plugin_e2e(cfg, B, dev, max(3, min(K_, 10)), graphed=True,
+                                                   fused_tail=any(m["ltype"] == "bce" for m in cfg["mods"]))
+            except Exception as ex:
+                e2e_plugin["graphed"] = {"error": repr(ex)[:200]}
         except Exception as ex:  # never let the extra leg hide the main numbers
             e2e_plugin = {"error": repr(ex)[:200]}
 

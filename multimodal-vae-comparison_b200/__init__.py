@@ -13,5 +13,6 @@ from .mmvae_models import MoPOE as mopoe  # noqa: E402,F401
 from .objectives import MultimodalObjective, ReconLoss, UnimodalObjective, unimodal_objective  # noqa: E402,F401
 from .output_storage import VAEOutput  # noqa: E402,F401
 from . import utils  # noqa: E402,F401
+from .graphed import GraphedObjective  # noqa: E402,F401
 
 MODEL_REGISTRY = {"moe": moe, "poe": poe, "mopoe": mopoe, "dmvae": dmvae}

@@ -56,13 +56,16 @@ class LinearDecoder(nn.Module):
         self.squash = squash
         # True: hand the pre-sigmoid logits to the likelihood kernel, which applies the tail itself (bce_logits)
         self.returns_logits = bool(returns_logits and squash)
+        # the likelihood scale every reference decoder returns (decoders.py:98 builds it from a host scalar on every
+        # call -- a pageable H2D copy, which a CUDA-graph capture does not allow): a non-persistent buffer instead
+        self.register_buffer("_scale", torch.tensor(0.75), persistent=False)
 
     def forward(self, z):
         z = z["latents"]
         d = self.lin(z)
         if self.squash and not self.returns_logits:
             d = torch.sigmoid(d).clamp(ETA, 1 - ETA)
-        return d.reshape(-1, *self.data_dim), torch.tensor(0.75, device=d.device)
+        return d.reshape(-1, *self.data_dim), self._scale
 
 
 class LeafDecoder(nn.Module):
