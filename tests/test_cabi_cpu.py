@@ -52,6 +52,35 @@ def test_version_and_argument_errors_without_gpu(lib):
     assert L.mmvae_reduce_sum(None, 0, 1.0, None, None) == -1
 
 
+def test_fused_iwae_argument_validation_without_gpu(lib):
+    """mmvae_objective_iwae_fused rejects missing outputs and a loss_sum without its ticket before any launch."""
+    L = lib.load()
+    one = ctypes.c_void_p(16)  # never dereferenced on the host: validation only looks at NULL-ness
+    ptrs = (ctypes.c_void_p * 1)(16)
+    args = dict(lpz=one, lq=one, lpx=None, ptrs=ptrs, M=1, L=1, K=2, B=4, beta=1.0)
+
+    def run(lw, loss_b, w, loss_sum, ticket):
+        return L.mmvae_objective_iwae_fused(args["lpz"], args["lq"], args["lpx"], args["ptrs"], args["M"], args["L"],
+                                            args["K"], args["B"], args["beta"], lw, loss_b, w, None, None, loss_sum,
+                                            ticket, None)
+    assert run(None, one, one, None, None) == -1          # lw missing
+    assert run(one, one, one, one, None) == -1            # loss_sum without ticket
+    assert run(one, one, one, None, one) == -1            # ticket without loss_sum
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py's stdout contract: ONE JSON line, whatever libraries print (fd 1 is pointed at stderr for the run)."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup",
+                        "1", "--cpu-batch", "2"], capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0, r.stderr[-400:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:400]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "objective fwd+bwd samples/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
 def test_draw_desc_layout_matches_header(lib):
     assert ctypes.sizeof(lib.DrawDesc) == 56
 
