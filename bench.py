@@ -114,6 +114,13 @@ class KernelTimer:
 
     def wrap(self, name, fn, args=()):
         a, b = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        # Eager steps are CPU bound around the small kernels: if the stream is idle when `a` is recorded, the host's
+        # launch latency (~5-10 us of Python + ctypes) lands between the two events.  A ~10 us device-side spin keeps
+        # the stream busy while record / launch / record are enqueued, so the events bracket the kernel alone.
+        try:
+            self.torch.cuda._sleep(20000)
+        except Exception:
+            pass
         a.record()
         rc = fn()
         b.record()
