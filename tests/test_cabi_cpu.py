@@ -100,6 +100,19 @@ def test_ops_refuse_cpu_tensors():
                         torch.rand(2, 1, 3, 4), [0, 0])
 
 
+def test_graphed_objective_refuses_cpu_models_and_tracks_batch_signature():
+    import mmvae_b200
+    from mmvae_b200.graphed import _signature
+    lin = torch.nn.Linear(2, 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mmvae_b200.GraphedObjective(lin, {"mod_1": {"data": torch.zeros(2, 2), "masks": None, "categorical": False}})
+    a = {"mod_1": {"data": torch.zeros(4, 3), "masks": None, "categorical": False}}
+    b = {"mod_1": {"data": torch.ones(4, 3), "masks": None, "categorical": False}}
+    c = {"mod_1": {"data": torch.zeros(5, 3), "masks": None, "categorical": False}}
+    d = {"mod_1": {"data": torch.zeros(4, 3), "masks": torch.ones(4, 3, dtype=torch.bool), "categorical": False}}
+    assert _signature(a) == _signature(b) and _signature(a) != _signature(c) and _signature(a) != _signature(d)
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     import mmvae_b200._lib as L
     monkeypatch.setattr(L, "_lib", None)
