@@ -324,9 +324,9 @@ def main():
     step.run()
     launches_per_step = L.launch_count - c0
     runner = step
-    # a collective inside the step (DReG batch sums, optimal_sigma RMS under sharding) keeps the step eager
-    needs_coll = world > 1 and (cfg["obj"] == "dreg" or any(m["ltype"] == "optimal_sigma" for m in cfg["mods"]))
-    if not args.no_graph and not needs_coll:
+    # forward collectives (DReG (M,K) batch sums, optimal_sigma scalar) are issued on the current stream and are
+    # captured in the step graph like the gradient all-reduce
+    if not args.no_graph:
         runner = W.GraphedStep(step)
     sync_mode = "none (1 GPU)"
     if world > 1:
@@ -376,7 +376,7 @@ def main():
     dom = "mmvae_loglik_rowreduce_bwd" if cfg["obj"] != "elbo" else "mmvae_loglik_rowreduce_fused"
     if cfg.get("latent_only"):
         dom = "mmvae_moe_logdens_fwd"
-    kt = KernelTimer([dom, "mmvae_loglik_rowreduce_fwd", "mmvae_moe_logdens_bwd"])
+    kt = KernelTimer([dom, "mmvae_loglik_rowreduce_fwd", "mmvae_moe_logdens_bwd_rk"])
     L.timer = kt
     step.streams = 1  # per-kernel durations: one kernel at a time (the step itself runs two streaming kernels at once)
     for _ in range(min(K_, 10)):
@@ -404,7 +404,7 @@ def main():
     if fms:
         roofline["fwd_kernel"] = {"achieved": fb / (statistics.mean(fms) * 1e-3) / 1e9, "bytes_per_launch": fb,
                                   "avg_ms": statistics.mean(fms)}
-    bms, bb = kt.biggest("mmvae_moe_logdens_bwd")
+    bms, bb = kt.biggest("mmvae_moe_logdens_bwd_rk")
     bms = bms[len(bms) // 5:] if len(bms) >= 5 else bms
     if bms and cfg.get("latent_only"):
         roofline["moe_bwd_kernel"] = {"achieved": bb / (statistics.mean(bms) * 1e-3) / 1e9, "bytes_per_launch": bb,
@@ -420,6 +420,8 @@ def main():
         pairs += list(zip(step.targets, t["targets"])) + list(zip(step.recon, t["recon"]))
         if cfg["model"] == "moe":
             pairs.append((step.eps_stacked, torch.stack(t["noise"])))
+            if step.dz is not None:
+                pairs.append((step.dz, t["dz"]))
         else:  # the draws kernel reads one packed noise buffer
             pairs.append((step.eps_packed, torch.cat([n.reshape(-1) for n in t["noise"]])))
         pairs = [(d, h.contiguous().pin_memory()) for d, h in pairs]

@@ -216,6 +216,18 @@ MMVAE_API int mmvae_moe_logdens_bwd(const float* mu, const float* s, int M, int6
                           const float* mu0, const float* s0, const float* eps,
                           const float* dz_ext, const float* dlq, const float* dlpz, int through_z,
                           float* dmu, float* ds, float* dprior_ws, float* dmu0, float* ds0, void* stream);
+/* same, with the per-(r,k) weights of a DReG-style objective folded into the coefficients instead of being
+ * materialised by the caller as (M,M,K,B) / (M,K,B) gradient tensors (objectives.py:361-387: the weights are a
+ * softmax over K of batch-summed log-weights, constant over b):
+ *   rkc[r,k] = rk_mul * (rk_scale_dev ? *rk_scale_dev : 1) * rk_w[r,k]
+ *   coefficient of log q_j(z[r,k,b]) = rkc[r,k] * dlq[r,j,k,b]   (dlq holds softmax_j(lq), required)
+ *   coefficient of log p(z[r,k,b])   = -rkc[r,k]                 (dlpz must be NULL)
+ * rk_w == NULL: identical to mmvae_moe_logdens_bwd.  Needs D % 4 == 0, D <= 128, M <= 3 and 16-byte aligned buffers (MMVAE_E_LIMIT otherwise). */
+MMVAE_API int mmvae_moe_logdens_bwd_rk(const float* mu, const float* s, int M, int64_t B, int D, int K, const int32_t* dists_host,
+                             const float* mu0, const float* s0, const float* eps,
+                             const float* dz_ext, const float* dlq, const float* dlpz, int through_z,
+                             const float* rk_w, const float* rk_scale_dev, float rk_mul,
+                             float* dmu, float* ds, float* dprior_ws, float* dmu0, float* ds0, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Objective combination (forward value + the per-row weights its backward needs, in one launch):
@@ -261,7 +273,15 @@ MMVAE_API int mmvae_prior_scale_bwd(const float* s0, const float* ds0, int D, fl
 #define MMVAE_DREG_MAX_SPLIT 64
 MMVAE_API int mmvae_objective_dreg_stage1(const float* lpz, const float* lq, const float* lpx, int M, int L, int K, int64_t B,
                                 double* lw_part, float* lq_soft, void* stream);
+/* same, likelihood rows through a HOST array of M*L device pointers (index r*L + l, (K*B) each): no stack copy */
+MMVAE_API int mmvae_objective_dreg_stage1_ptrs(const float* lpz, const float* lq, const float* lpx,
+                                     const float* const* lpx_ptrs_host, int M, int L, int K, int64_t B,
+                                     double* lw_part, float* lq_soft, void* stream);
 MMVAE_API int mmvae_objective_dreg_stage2(const double* lw, int M, int K, float* wt, float* loss, void* stream);
+/* DReG backward for the (M,L,K,B) likelihood rows (and log p(z)): d_rows[r,l,k,b] = -(g/M) * wt[r,k], g = *g_dev
+ * (upstream gradient of the loss; NULL = 1).  The log q gradients are folded into mmvae_moe_logdens_bwd_rk. */
+MMVAE_API int mmvae_objective_dreg_rowgrads(const float* g_dev, const float* wt, int M, int L, int K, int64_t B,
+                                  float* d_rows, void* stream);
 MMVAE_API int mmvae_reduce_sum(const float* x, int64_t n, float scale, float* out, void* stream);
 
 /* in-place scale of a gradient buffer by a DEVICE scalar, skipped entirely (early exit) when the scalar == 1:

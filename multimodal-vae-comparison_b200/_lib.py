@@ -6,7 +6,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmmvae_b200.so")
+# MMVAE_B200_LIB: alternative build of the same library (kernel tuning variants, tools/tune_*.sh); never a fallback
+LIB_PATH = os.environ.get("MMVAE_B200_LIB") or os.path.join(HERE, "libmmvae_b200.so")
 
 c_i, c_i64, c_f, c_d, c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
 
@@ -49,6 +50,8 @@ SIGNATURES = {
     "mmvae_moe_logdens_bwd_ws_floats": (c_i64, [c_i64, c_i, c_i]),
     "mmvae_moe_logdens_bwd": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_i, ctypes.POINTER(ctypes.c_int32), c_p, c_p, c_p,
                                     c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "mmvae_moe_logdens_bwd_rk": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_i, ctypes.POINTER(ctypes.c_int32), c_p, c_p, c_p,
+                                       c_p, c_p, c_p, c_i, c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_p, c_p]),
     "mmvae_objective_iwae": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i64, c_f, c_p, c_p, c_p, c_p, c_p]),
     "mmvae_objective_iwae_ptrs": (c_i, [c_p, c_p, c_p, ctypes.POINTER(c_p), c_i, c_i, c_i, c_i64, c_f, c_p, c_p, c_p,
                                         c_p, c_p]),
@@ -58,7 +61,9 @@ SIGNATURES = {
     "mmvae_prior_scale_fwd": (c_i, [c_p, c_i, c_p, c_p]),
     "mmvae_prior_scale_bwd": (c_i, [c_p, c_p, c_i, c_p, c_p]),
     "mmvae_objective_dreg_stage1": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i64, c_p, c_p, c_p]),
+    "mmvae_objective_dreg_stage1_ptrs": (c_i, [c_p, c_p, c_p, ctypes.POINTER(c_p), c_i, c_i, c_i, c_i64, c_p, c_p, c_p]),
     "mmvae_objective_dreg_stage2": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p]),
+    "mmvae_objective_dreg_rowgrads": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i64, c_p, c_p]),
     "mmvae_reduce_sum": (c_i, [c_p, c_i64, c_f, c_p, c_p]),
     "mmvae_scale_inplace": (c_i, [c_p, c_i, c_i64, c_p, c_p]),
 }
@@ -69,7 +74,7 @@ launch_count = 0
 _LAUNCHES = {"mmvae_loglik_rowreduce_fwd": 1, "mmvae_loglik_rowreduce_bwd": 1, "mmvae_loglik_rowreduce_fused": 1,
              "mmvae_catce_rows": 1, "mmvae_osigma_sumsq": 1, "mmvae_osigma_fwd": 1, "mmvae_osigma_bwd": 2,
              "mmvae_latent_draws_fwd": 1, "mmvae_latent_draws_bwd": 2, "mmvae_moe_logdens_fwd": 1,
-             "mmvae_moe_logdens_bwd": 2, "mmvae_objective_iwae": 1, "mmvae_objective_iwae_fused": 1, "mmvae_objective_dreg_stage1": 2,
+             "mmvae_moe_logdens_bwd": 2, "mmvae_moe_logdens_bwd_rk": 2, "mmvae_objective_iwae": 1, "mmvae_objective_iwae_fused": 1, "mmvae_objective_dreg_stage1": 2, "mmvae_objective_dreg_stage1_ptrs": 2,
              "mmvae_objective_dreg_stage2": 1, "mmvae_reduce_sum": 1, "mmvae_scale_inplace": 1}
 
 

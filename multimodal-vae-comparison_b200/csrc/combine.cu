@@ -137,24 +137,72 @@ __global__ void __launch_bounds__(kIwaeBT * kIwaeSlots) iwae_kernel(const CombPa
 }
 
 // DReG stage 1: one CTA per ((r,k), batch split); writes partial batch sums and softmax_j(lq) for the backward.
+// VEC = 4: a thread takes four consecutive batch rows per step through 128-bit loads / stores (B % 4 == 0, aligned
+// buffers) -- r2 ncu launch list at C4 (B = 16k): 44.6 us for 92 MB with the one-row-per-thread loop (a chain of ten
+// dependent scalar loads per row), the vector form keeps 40 values in flight per thread.
+template <int VEC>
 __global__ void __launch_bounds__(256) dreg_stage1_kernel(const CombParams p, double* __restrict__ part, int nsplit,
                                                           float* __restrict__ lq_soft) {
     __shared__ double red[32];
     const int q = blockIdx.x, sp = blockIdx.y;
     const int r = q / p.K, k = q - r * p.K;
-    const int64_t per = (p.B + nsplit - 1) / nsplit;
+    int64_t per = (p.B + nsplit - 1) / nsplit;
+    per = (per + VEC - 1) / VEC * VEC;
     const int64_t b0 = sp * per, b1 = min(p.B, b0 + per);
-    float vals[MMVAE_MAX_MODS];
     // batch sums feed a softmax over K: |lw| grows with B*P while the softmax needs its ABSOLUTE error small, and
     // the reference carries these sums in fp64 whenever the likelihood is lprob (objectives.py:422) -> double here
     double acc = 0.0;
-    for (int64_t b = b0 + threadIdx.x; b < b1; b += blockDim.x) {
-        float mx, se;
-        acc += (double)lw_value(p, r, k, b, 1.0f, vals, mx, se);  // no beta in _m_dreg_looser (objectives.py:371)
+    const int64_t rk = (int64_t)r * p.K + k;
+    for (int64_t b = b0 + (int64_t)threadIdx.x * VEC; b < b1; b += (int64_t)blockDim.x * VEC) {
+        float lw[VEC], lqv[MMVAE_MAX_MODS][VEC], mx[VEC], se[VEC];
+        if (VEC == 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.lpz + rk * p.B + b));
+            lw[0] = t.x; lw[1] = t.y; lw[2] = t.z; lw[3] = t.w;
+            for (int l = 0; l < p.L; ++l) {
+                const float4 u = __ldg(reinterpret_cast<const float4*>(p.lpx_ptr[r * p.L + l] + (int64_t)k * p.B + b));
+                lw[0] += u.x; lw[1] += u.y; lw[2] += u.z; lw[3] += u.w;
+            }
+#pragma unroll
+            for (int j = 0; j < MMVAE_MAX_MODS; ++j)
+                if (j < p.M) {
+                    const float4 u = __ldg(reinterpret_cast<const float4*>(p.lq + (((int64_t)r * p.M + j) * p.K + k) * p.B + b));
+                    lqv[j][0] = u.x; lqv[j][1] = u.y; lqv[j][2] = u.z; lqv[j][3] = u.w;
+                }
+        } else {
+            lw[0] = __ldg(p.lpz + rk * p.B + b);
+            for (int l = 0; l < p.L; ++l) lw[0] += __ldg(p.lpx_ptr[r * p.L + l] + (int64_t)k * p.B + b);
+#pragma unroll
+            for (int j = 0; j < MMVAE_MAX_MODS; ++j)
+                if (j < p.M) lqv[j][0] = __ldg(p.lq + (((int64_t)r * p.M + j) * p.K + k) * p.B + b);
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            mx[i] = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < MMVAE_MAX_MODS; ++j)
+                if (j < p.M) mx[i] = fmaxf(mx[i], lqv[j][i]);
+            se[i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < MMVAE_MAX_MODS; ++j)
+                if (j < p.M) {
+                    lqv[j][i] = expf(lqv[j][i] - mx[i]);
+                    se[i] += lqv[j][i];
+                }
+            // no beta in _m_dreg_looser (objectives.py:371)
+            acc += (double)(lw[i] - (mx[i] + logf(se[i]) - logf((float)p.M)));
+            se[i] = 1.0f / se[i];
+        }
         if (lq_soft) {
 #pragma unroll
             for (int j = 0; j < MMVAE_MAX_MODS; ++j)
-                if (j < p.M) lq_soft[(((int64_t)r * p.M + j) * p.K + k) * p.B + b] = expf(vals[j] - mx) / se;
+                if (j < p.M) {
+                    float* o = lq_soft + (((int64_t)r * p.M + j) * p.K + k) * p.B + b;
+                    if (VEC == 4)
+                        *reinterpret_cast<float4*>(o) =
+                            make_float4(lqv[j][0] * se[0], lqv[j][1] * se[1], lqv[j][2] * se[2], lqv[j][3] * se[3]);
+                    else
+                        o[0] = lqv[j][0] * se[0];
+                }
         }
     }
     const double tot = block_sum(acc, red);
@@ -199,6 +247,25 @@ __global__ void __launch_bounds__(256) dreg_stage2_kernel(const double* __restri
         double tot = 0.0;
         for (int w = 0; w < 8; ++w) tot += s_part[w];
         *loss = (float)(-tot / (double)M);
+    }
+}
+
+// DReG backward for the likelihood row vectors and log p(z): d loss / d row[r,l,k,b] = -(g/M) wt[r,k] for every b
+// (objectives.py:384-386: loss = -(1/M) sum_r sum_k wt[r,k] lw[r,k], lw a plain batch sum).  One CTA row per (r,l,k);
+// 128-bit stores when the row is aligned.
+__global__ void __launch_bounds__(256) dreg_rowgrad_kernel(const float* __restrict__ g, const float* __restrict__ wt, int M,
+                                                           int L, int K, int64_t B, float* __restrict__ d_rows) {
+    const int q = blockIdx.y;  // (r*L + l)*K + k
+    const int r = q / (L * K), k = q % K;
+    const float v = -(g ? __ldg(g) : 1.0f) / (float)M * __ldg(wt + r * K + k);
+    float* row = d_rows + (int64_t)q * B;
+    if ((B & 3) == 0 && aligned16(d_rows)) {
+        const float4 v4 = make_float4(v, v, v, v);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B / 4; i += (int64_t)gridDim.x * blockDim.x)
+            reinterpret_cast<float4*>(row)[i] = v4;
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x)
+            row[i] = v;
     }
 }
 
@@ -330,9 +397,15 @@ extern "C" int mmvae_objective_iwae_fused(const float* lpz, const float* lq, con
 #define DREG_MAX_SPLIT MMVAE_DREG_MAX_SPLIT
 extern "C" int mmvae_objective_dreg_stage1(const float* lpz, const float* lq, const float* lpx, int M, int L, int K,
                                            int64_t B, double* lw_part, float* lq_soft, void* stream) {
+    return mmvae_objective_dreg_stage1_ptrs(lpz, lq, lpx, nullptr, M, L, K, B, lw_part, lq_soft, stream);
+}
+
+extern "C" int mmvae_objective_dreg_stage1_ptrs(const float* lpz, const float* lq, const float* lpx,
+                                                const float* const* lpx_ptrs_host, int M, int L, int K, int64_t B,
+                                                double* lw_part, float* lq_soft, void* stream) {
     // lw_part: (DREG_MAX_SPLIT + 1, M*K) doubles: [0] receives the local batch sums, [1..] is scratch
     CombParams p{};
-    int rc = comb_fill(p, lpz, lq, lpx, nullptr, M, L, K, B);
+    int rc = comb_fill(p, lpz, lq, lpx, lpx_ptrs_host, M, L, K, B);
     if (rc) return rc;
     if (!lw_part) return MMVAE_E_ARG;
     int nsplit = (int)((B + 2047) / 2048);
@@ -340,7 +413,12 @@ extern "C" int mmvae_objective_dreg_stage1(const float* lpz, const float* lq, co
     if (nsplit > DREG_MAX_SPLIT) nsplit = DREG_MAX_SPLIT;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(M * K, nsplit);
-    dreg_stage1_kernel<<<grid, 256, 0, st>>>(p, lw_part + (size_t)M * K, nsplit, lq_soft);
+    bool vec = (B % 4 == 0) && aligned16(lpz) && aligned16(lq) && (!lq_soft || aligned16(lq_soft));
+    for (int i = 0; i < M * L; ++i) vec = vec && aligned16(p.lpx_ptr[i]);
+    if (vec)
+        dreg_stage1_kernel<4><<<grid, 256, 0, st>>>(p, lw_part + (size_t)M * K, nsplit, lq_soft);
+    else
+        dreg_stage1_kernel<1><<<grid, 256, 0, st>>>(p, lw_part + (size_t)M * K, nsplit, lq_soft);
     MMVAE_LAUNCH_CHECK();
     dreg_partial_sum_kernel<<<(M * K + 127) / 128, 128, 0, st>>>(lw_part + (size_t)M * K, nsplit, M * K, lw_part);
     MMVAE_LAUNCH_CHECK();
@@ -350,6 +428,16 @@ extern "C" int mmvae_objective_dreg_stage1(const float* lpz, const float* lq, co
 extern "C" int mmvae_objective_dreg_stage2(const double* lw, int M, int K, float* wt, float* loss, void* stream) {
     if (!lw || !wt || !loss || M <= 0 || K <= 0) return MMVAE_E_ARG;
     dreg_stage2_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(lw, M, K, wt, loss);
+    MMVAE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mmvae_objective_dreg_rowgrads(const float* g_dev, const float* wt, int M, int L, int K, int64_t B,
+                                             float* d_rows, void* stream) {
+    if (!wt || !d_rows || M <= 0 || L <= 0 || K <= 0 || B <= 0) return MMVAE_E_ARG;
+    const int64_t per = (B + 1023) / 1024;  // 256 threads x 4 elements per CTA
+    dim3 grid((unsigned)(per < 65535 ? per : 65535), (unsigned)(M * L * K));
+    dreg_rowgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g_dev, wt, M, L, K, B, d_rows);
     MMVAE_LAUNCH_CHECK();
     return 0;
 }

@@ -157,6 +157,44 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 }
 __device__ __forceinline__ float exp_shifted(float x, float neg_m_log2e) { return ex2_ftz(fmaf(x, kLog2e, neg_m_log2e)); }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2) -------------------------------------------------------------
+// sm_100 executes fp32 add / mul / fma on TWO values held in an aligned register pair with one instruction
+// (PTX {add,sub,mul,fma}.f32x2).  The FMA pipe needs two cycles for it, so the FLOP rate does not change (r2
+// microbenchmark tools/ffma2_bench.cu: 72 vs 74 TFLOP/s) -- but an issue-bound kernel gets the second issue slot back
+// for its loads, MUFU and integer work.  ptxas folds the sign-bit tricks below (abs / neg) into operand modifiers.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2_bcast(float v) { return f2_pack(v, v); }
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ float f2_lo(f32x2 v) { float a, b; f2_unpack(v, a, b); return a; }
+__device__ __forceinline__ float f2_hi(f32x2 v) { float a, b; f2_unpack(v, a, b); return b; }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2_abs(f32x2 a) { return a & 0x7fffffff7fffffffull; }
+__device__ __forceinline__ f32x2 f2_neg(f32x2 a) { return a ^ 0x8000000080000000ull; }
+
 // ---- TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier ---------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

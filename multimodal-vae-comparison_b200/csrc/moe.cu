@@ -27,6 +27,9 @@ struct MoeParams {
     int64_t B;
     int M, D, K, through_z;
     int dist[MMVAE_MAX_MODS];
+    // "rk" mode of the backward (DReG): per-(r,k) objective weights folded into the coefficients
+    const float *rk_w, *rk_scale;  // (M,K) device weights; optional device scalar
+    float rk_mul;
 };
 
 // -log1p(-a) for a in [0, 1): torch's Laplace.rsample evaluates log1p(-|u|) (laplace.py:84).  The libdevice log1pf
@@ -431,6 +434,545 @@ __global__ void __launch_bounds__(kMoeMaxWarps * 32) moe_bwd_reg_kernel(const Mo
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Flat variants (r2; D % 4 == 0, D <= 128): the lanes of a warp run over the FLATTENED (b, c) plane of one (r, k)
+// slab of eps / z, four consecutive columns per lane -- every global access is one 128-bit request per lane and a
+// warp covers 512 contiguous bytes, whatever D is (the row-per-CTA kernels above move 64 B per warp request at
+// D = 16 and leave half the warp idle).  lpr = lanes per batch row (power of two >= D/4; lanes past D/4 idle), a warp
+// holds 32/lpr batch rows.  A thread owns its (b, 4 columns) for the whole kernel iteration: all per-column constants
+// of the M posteriors and (backward) every gradient accumulator stay in registers over the (k, r) loop; the only
+// cross-lane traffic is the lpr-wide butterfly of the row sums (forward).  r1 ncu on C4 (Laplace, D = 64, K = 50):
+// 239 warp instructions per 64-element row = 120 per element; here ~37 (fwd) / ~45 (bwd) per element:
+//   * Laplace transform through ex2/lg2/rcp.approx.ftz in inline PTX (no denormal / range fix-ups),
+//   * the log normalisers are summed once per row, outside the k loop,
+//   * backward: d/ds accumulates  sum_k c|df|  (Laplace) or  sum_k c df^2  (Normal) and  sum_k c ; the 1/s powers are
+//     applied once per row,
+//   * the next k's eps / dz vectors are requested before the current ones are consumed (software prefetch).
+// K can be split over `ksplit` warps of the CTA (small batches); partial gradients are combined through shared
+// memory in a fixed order (deterministic, no atomics).  The CTAs are persistent (grid-stride over row tiles), so the
+// prior-gradient partials are one (2, D) vector per CTA.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kFlatWarps = 8;
+// depth of the cp.async staging rings (tuning knobs: tools/tune_moe.sh builds variants with -D and times them on the box)
+#ifndef MMVAE_MOE_BWD_STAGES
+#define MMVAE_MOE_BWD_STAGES 3
+#endif
+#ifndef MMVAE_MOE_FWD_STAGES
+#define MMVAE_MOE_FWD_STAGES 4
+#endif
+constexpr int kFlatStages = MMVAE_MOE_BWD_STAGES;
+constexpr int kFwdStages = MMVAE_MOE_FWD_STAGES;
+
+__device__ __forceinline__ void cp_async16_s(uint32_t smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4_s(uint32_t smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds_f(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// sign(u) * -log1p(-|u|) for a PAIR of uniform draws (torch laplace.py:84), packed math:
+//   |u| <  1/4: |u| * P5(|u|), P5 the degree-5 minimax fit of -log1p(-a)/a on [0, 1/4] (1.8e-7 relative in fp32 Horner)
+//   |u| >= 1/4: -ln2 * lg2(fl(1-|u|)) through MUFU.LG2: the subtraction is exact for |u| >= 1/2 and off by at most
+//               2^-25 below, MUFU.LG2 adds 1.7e-7 absolute -- on a value >= 0.288 that is <= 9e-7 relative
+// (r1 used an 8-term Taylor series below 1/8 and a rounding-residual correction d/w through MUFU.RCP above: 1.3e-6
+// relative and 7 more instructions per element).  The branch value is selected per element; its sign never matters
+// because the result takes the sign of u (copysign).
+__device__ __forceinline__ f32x2 laplace_noise2(f32x2 E) {
+    const f32x2 A = f2_abs(E);
+    const f32x2 W = f2_sub(f2_bcast(1.0f), A);
+    float w0, w1, a0, a1, e0, e1, s0, s1, t0, t1;
+    f2_unpack(W, w0, w1);
+    const f32x2 T = f2_mul(f2_pack(lg2_ftz(w0), lg2_ftz(w1)), f2_bcast(0.69314718055994530942f));  // log1p(-a) <= 0
+    f32x2 SM = f2_bcast(0.3392468806299893f);
+    SM = f2_fma(SM, A, f2_bcast(0.14354718845635991f));
+    SM = f2_fma(SM, A, f2_bcast(0.2580779049606482f));
+    SM = f2_fma(SM, A, f2_bcast(0.3328062745954427f));
+    SM = f2_fma(SM, A, f2_bcast(0.5000135657968677f));
+    SM = f2_fma(SM, A, f2_bcast(0.9999999175315916f));
+    SM = f2_mul(SM, A);
+    f2_unpack(A, a0, a1);
+    f2_unpack(E, e0, e1);
+    f2_unpack(SM, s0, s1);
+    f2_unpack(T, t0, t1);
+    return f2_pack(copysignf(a0 < 0.25f ? s0 : t0, e0), copysignf(a1 < 0.25f ? s1 : t1, e1));
+}
+
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
+    const uint4 v = ldg_stream(p);
+    return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
+__device__ __forceinline__ void stg_stream_f4(float* p, const float* v) {
+    stg_stream(p, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
+}
+// sum over the LPR lanes of a row group (compile-time LPR: a run-time bound makes the compiler guard every shuffle
+// with BSSY / WARPSYNC convergence code)
+template <int LPR>
+__device__ __forceinline__ float row_sum(float v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// sum over the lanes of a warp that own the same columns (same lane % LPR)
+template <int LPR>
+__device__ __forceinline__ float col_sum(float v) {
+#pragma unroll
+    for (int o = 16; o >= LPR; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int MT, int LM, int lpr>
+__global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 3 : 2) moe_fwd_flat_kernel(const MoeParams p, const int ksplit) {
+    extern __shared__ float4 ring[];  // per warp: kFwdStages x MT noise vectors x 32 lanes (cp.async staging, see backward)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t ring_base = smem_u32(ring + (size_t)wid * kFwdStages * MT * 32 + lane);
+    constexpr uint32_t kStageBytes = MT * 32 * sizeof(float4);
+    const int pw = wid / ksplit, ks = wid - pw * ksplit, npw = kFlatWarps / ksplit;
+    const int rpw = 32 / lpr, cl = lane & (lpr - 1), c = cl * 4;
+    const bool colok = c < p.D;
+    bool lap[MT];
+#pragma unroll
+    for (int j = 0; j < MT; ++j) lap[j] = LM == 2 ? (p.dist[j] == MMVAE_LAPLACE) : (LM == 1);
+    // prior: u0 = z/s0 - mu0/s0 as one FMA per pair
+    f32x2 PINV[2], PNM[2];
+    float pc = 0.f;
+    {
+        float iv[4], nm[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float sg = colok ? __ldg(p.s0 + c + i) : 1.f;
+            iv[i] = colok ? 1.0f / sg : 0.f;
+            nm[i] = colok ? -__ldg(p.mu0 + c + i) * iv[i] : 0.f;
+            pc += colok ? -logf(sg) - kLogSqrt2Pi : 0.f;
+        }
+        PINV[0] = f2_pack(iv[0], iv[1]); PINV[1] = f2_pack(iv[2], iv[3]);
+        PNM[0] = f2_pack(nm[0], nm[1]); PNM[1] = f2_pack(nm[2], nm[3]);
+    }
+    pc = row_sum<lpr>(pc);
+    const int64_t ntiles = (p.B + rpw - 1) / rpw;
+    const int64_t BD = p.B * p.D;
+    for (int64_t t = (int64_t)blockIdx.x * npw + pw; t < ntiles; t += (int64_t)gridDim.x * npw) {
+        const int64_t b = t * rpw + lane / lpr;
+        const bool ok = colok && b < p.B;
+        // per-column constants of the row's M posteriors, as pairs: mu, sigma, 1/sigma, -mu/sigma
+        f32x2 MU[MT][2], SG[MT][2], INV[MT][2], NM[MT][2];
+        float rc[MT];
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+            const int64_t o = ((int64_t)j * p.B + b) * p.D + c;
+            const float4 m4 = ok ? __ldg(reinterpret_cast<const float4*>(p.mu + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 s4 = ok ? __ldg(reinterpret_cast<const float4*>(p.s + o)) : make_float4(1.f, 1.f, 1.f, 1.f);
+            const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+            float cst = 0.f, sgv[4], iv[4], nm[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                sgv[i] = ok ? ss[i] : 0.f;
+                iv[i] = ok ? 1.0f / ss[i] : 0.f;
+                nm[i] = -mm[i] * iv[i];
+                cst += ok ? (lap[j] ? -logf(2.0f * ss[i]) : -logf(ss[i]) - kLogSqrt2Pi) : 0.f;
+            }
+            MU[j][0] = f2_pack(mm[0], mm[1]); MU[j][1] = f2_pack(mm[2], mm[3]);
+            SG[j][0] = f2_pack(sgv[0], sgv[1]); SG[j][1] = f2_pack(sgv[2], sgv[3]);
+            INV[j][0] = f2_pack(iv[0], iv[1]); INV[j][1] = f2_pack(iv[2], iv[3]);
+            NM[j][0] = f2_pack(nm[0], nm[1]); NM[j][1] = f2_pack(nm[2], nm[3]);
+            rc[j] = row_sum<lpr>(cst);
+        }
+        // running pointers: one 64-bit add per tensor and k step instead of a fresh (r, k, b, c) product per access
+        const int64_t KBD = (int64_t)p.K * BD, KB = (int64_t)p.K * p.B;
+        const int64_t kstepD = (int64_t)ksplit * BD, kstep = (int64_t)ksplit * p.B;
+        const float* ek = p.eps + b * p.D + c + (int64_t)ks * BD;  // issue-side running pointer
+        float* zk = p.z + b * p.D + c + (int64_t)ks * BD;
+        float* lqk = p.lq + b + (int64_t)ks * p.B;
+        float* lpk = p.lpz + b + (int64_t)ks * p.B;
+        // noise vectors of the next kFwdStages-1 k steps in flight through the cp.async ring (r2 ncu: with a one-step
+        // register prefetch 26 % of the stall samples sat on the arrival of the prefetched vector)
+        int k_issue = ks;
+        uint32_t st_issue = ring_base, st_read = ring_base;
+        const uint32_t ring_end = ring_base + kFwdStages * kStageBytes;
+        auto issue = [&]() {
+            if (ok && k_issue < p.K) {
+#pragma unroll
+                for (int r = 0; r < MT; ++r) cp_async16_s(st_issue + r * 32 * sizeof(float4), ek + r * KBD);
+            }
+            cp_async_commit();
+            k_issue += ksplit;
+            ek += kstepD;
+            st_issue += kStageBytes;
+            if (st_issue == ring_end) st_issue = ring_base;
+        };
+#pragma unroll
+        for (int st = 0; st < kFwdStages - 1; ++st) issue();
+        for (int k = ks; k < p.K; k += ksplit) {
+            issue();
+            cp_async_wait<kFwdStages - 1>();
+            float4 e[MT];
+#pragma unroll
+            for (int r = 0; r < MT; ++r) e[r] = ok ? lds_f4(st_read + r * 32 * sizeof(float4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            st_read += kStageBytes;
+            if (st_read == ring_end) st_read = ring_base;
+            float part[MT][MT + 1];  // per-lane partial sums: [r][j] of |u_j| or u_j^2, [r][MT] of the prior's u^2
+#pragma unroll
+            for (int r = 0; r < MT; ++r) {
+                const f32x2 E[2] = {f2_pack(e[r].x, e[r].y), f2_pack(e[r].z, e[r].w)};
+                f32x2 ZZ[2], ACC[MT], AP = 0ull;
+#pragma unroll
+                for (int j = 0; j < MT; ++j) ACC[j] = 0ull;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const f32x2 EF = lap[r] ? laplace_noise2(E[h]) : E[h];
+                    ZZ[h] = f2_fma(EF, SG[r][h], MU[r][h]);
+#pragma unroll
+                    for (int j = 0; j < MT; ++j) {
+                        // own posterior: (z - mu_r)/s_r IS the transformed noise (what an exact evaluation gives; the
+                        // reference recovers it from the rounded z, |difference| <= ulp(z)/s_r).  Others: z/s_j - mu_j/s_j
+                        // as one FMA (error <= ulp(mu_j/s_j), negligible against |u| ~ 1/s_j).
+                        const f32x2 U = j == r ? EF : f2_fma(ZZ[h], INV[j][h], NM[j][h]);
+                        ACC[j] = lap[j] ? f2_add(ACC[j], f2_abs(U)) : f2_fma(U, U, ACC[j]);
+                    }
+                    const f32x2 U0 = f2_fma(ZZ[h], PINV[h], PNM[h]);
+                    AP = f2_fma(U0, U0, AP);
+                }
+                if (ok) {
+                    const float zz[4] = {f2_lo(ZZ[0]), f2_hi(ZZ[0]), f2_lo(ZZ[1]), f2_hi(ZZ[1])};
+                    stg_stream_f4(zk + r * KBD, zz);
+                }
+                part[r][MT] = f2_lo(AP) + f2_hi(AP);
+#pragma unroll
+                for (int j = 0; j < MT; ++j) part[r][j] = f2_lo(ACC[j]) + f2_hi(ACC[j]);
+            }
+            // row sums of the MT*(MT+1) partials.  MT == 2 and >= 2 lanes per row: the first butterfly step TRANSPOSES
+            // (lanes of the lower half of a row group keep the r = 0 partials and send their r = 1 ones, the upper half
+            // the reverse), so the remaining steps run on MT+1 values instead of 2*(MT+1): 30 instead of 48 shuffle /
+            // add instructions per k step.  The lower half then holds the sums of r = 0, the upper half those of r = 1.
+            if (MT == 2 && lpr >= 2) {
+                const bool up = (cl & (lpr / 2)) != 0;
+                float v[MT + 1];
+#pragma unroll
+                for (int q = 0; q <= MT; ++q) {
+                    const float send = up ? part[0][q] : part[1][q], keep = up ? part[1][q] : part[0][q];
+                    v[q] = keep + __shfl_xor_sync(0xffffffffu, send, lpr / 2);
+                }
+#pragma unroll
+                for (int q = 0; q <= MT; ++q) v[q] = row_sum<lpr / 2>(v[q]);
+                // cl == 0 writes r = 0, cl == lpr/2 writes r = 1 (that lane may own no column when D < 2*lpr: row test only)
+                if (b < p.B && (cl & (lpr / 2 - 1)) == 0) {
+                    const int r = up ? 1 : 0;
+#pragma unroll
+                    for (int j = 0; j < MT; ++j) lqk[(r * MT + j) * KB] = rc[j] - (lap[j] ? v[j] : 0.5f * v[j]);
+                    lpk[r * KB] = pc - 0.5f * v[MT];
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < MT; ++r) {
+                    float v[MT + 1];
+#pragma unroll
+                    for (int q = 0; q <= MT; ++q) v[q] = row_sum<lpr>(part[r][q]);
+                    if (ok && cl == 0) {
+#pragma unroll
+                        for (int j = 0; j < MT; ++j) lqk[(r * MT + j) * KB] = rc[j] - (lap[j] ? v[j] : 0.5f * v[j]);
+                        lpk[r * KB] = pc - 0.5f * v[MT];
+                    }
+                }
+            }
+            zk += kstepD;
+            lqk += kstep;
+            lpk += kstep;
+        }
+        cp_async_wait<0>();
+    }
+}
+
+// Backward.  Coefficients of the log-densities: c_j = dlq[r,j,k,b], c_p = dlpz[r,k,b]; in "rk" mode (DReG) the
+// per-(r,k) weights of the objective are folded in here instead of being materialised by the caller:
+//   c_j = rkc[r,k] * dlq[r,j,k,b] (dlq then holds softmax_j(lq)),  c_p = -rkc[r,k],  rkc = rk_mul * (*rk_scale) * rk_w.
+// HOT: the argument pattern of the IWAE / DReG training step is known at compile time (dz_ext and dlq present,
+// through_z set; dlpz present unless rk mode) -- the per-iteration pointer tests of the generic variant go away.
+template <int MT, int LM, int lpr, bool HOT>
+__global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 2 : 1) moe_bwd_flat_kernel(const MoeParams p, const int ksplit) {
+    __shared__ float red[kFlatWarps * 2 * MT * 4 * 32];
+    extern __shared__ float4 ring[];  // per warp: kFlatStages x (2*MT vectors + (MT*MT+MT) scalars) x 32 lanes
+    constexpr int kVecPerStage = 2 * MT * 32, kCofPerStage = (MT * MT + MT) * 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int pw = wid / ksplit, ks = wid - pw * ksplit, npw = kFlatWarps / ksplit;
+    const int rpw = 32 / lpr, cl = lane & (lpr - 1), c = cl * 4;
+    const bool colok = c < p.D;
+    float4* myvec = ring + (size_t)wid * kFlatStages * kVecPerStage + lane;
+    float* mycof = reinterpret_cast<float*>(ring + (size_t)kFlatWarps * kFlatStages * kVecPerStage) +
+                   (size_t)wid * kFlatStages * kCofPerStage + lane;
+    // slots that are never copied into (inactive lanes, absent dz / dlq / dlpz) must read as zero
+    for (int i = 0; i < kFlatStages * 2 * MT; ++i) myvec[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < kFlatStages * (MT * MT + MT); ++i) mycof[i * 32] = 0.f;
+    const uint32_t vec_base = smem_u32(myvec), cof_base = smem_u32(mycof);
+    constexpr uint32_t kVecBytes = kVecPerStage * sizeof(float4), kCofBytes = kCofPerStage * sizeof(float);
+    const bool has_dz = HOT || p.dz_ext != nullptr, has_q = HOT || p.dlq != nullptr, rk = p.rk_w != nullptr;
+    const bool has_l = HOT ? !rk : p.dlpz != nullptr, thru = HOT || p.through_z != 0;
+    bool lap[MT];
+#pragma unroll
+    for (int j = 0; j < MT; ++j) lap[j] = LM == 2 ? (p.dist[j] == MMVAE_LAPLACE) : (LM == 1);
+    // prior N(mu0, s0): d/dmu0 = c_p df/s0^2, d/ds0 = c_p (df^2/s0^3 - 1/s0); the powers of 1/s0 are applied at the end
+    f32x2 PMU[2], NPI2[2], QM[2] = {0ull, 0ull}, QS[2] = {0ull, 0ull};
+    float pinv[4], Cp = 0.f;
+    {
+        float pm[4], np2[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            pm[i] = colok ? __ldg(p.mu0 + c + i) : 0.f;
+            pinv[i] = colok ? 1.0f / __ldg(p.s0 + c + i) : 0.f;
+            np2[i] = -pinv[i] * pinv[i];
+        }
+        PMU[0] = f2_pack(pm[0], pm[1]); PMU[1] = f2_pack(pm[2], pm[3]);
+        NPI2[0] = f2_pack(np2[0], np2[1]); NPI2[1] = f2_pack(np2[2], np2[3]);
+    }
+    const float rk_mul = p.rk_w ? p.rk_mul * (p.rk_scale ? __ldg(p.rk_scale) : 1.0f) : 0.f;
+    const int64_t ntiles = (p.B + rpw - 1) / rpw, ngroups = (ntiles + npw - 1) / npw;
+    const int64_t BD = p.B * p.D;
+    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int64_t b = (g * npw + pw) * rpw + lane / lpr;
+        const bool ok = colok && b < p.B;
+        // constants (pairs): mu, sigma, 1/sigma (Laplace) or 1/sigma^2 (Normal); accumulators: d/dmu, sum c|df| or
+        // sum c df^2, own-sample d/dsigma, sum c
+        f32x2 MU[MT][2], SG[MT][2], IV[MT][2], AM[MT][2], S[MT][2], GS[MT][2];
+        float inv[MT][4], Cs[MT];
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+            const int64_t o = ((int64_t)j * p.B + b) * p.D + c;
+            const float4 m4 = ok ? __ldg(reinterpret_cast<const float4*>(p.mu + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 s4 = ok ? __ldg(reinterpret_cast<const float4*>(p.s + o)) : make_float4(1.f, 1.f, 1.f, 1.f);
+            const float ss[4] = {s4.x, s4.y, s4.z, s4.w};
+            float sgv[4], ivp[4];
+            Cs[j] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                sgv[i] = ok ? ss[i] : 0.f;
+                inv[j][i] = ok ? 1.0f / ss[i] : 0.f;
+                ivp[i] = lap[j] ? inv[j][i] : inv[j][i] * inv[j][i];
+            }
+            MU[j][0] = f2_pack(m4.x, m4.y); MU[j][1] = f2_pack(m4.z, m4.w);
+            SG[j][0] = f2_pack(sgv[0], sgv[1]); SG[j][1] = f2_pack(sgv[2], sgv[3]);
+            IV[j][0] = f2_pack(ivp[0], ivp[1]); IV[j][1] = f2_pack(ivp[2], ivp[3]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) AM[j][h] = S[j][h] = GS[j][h] = 0ull;
+        }
+        // Shared-memory staging ring (cp.async, LDGSTS): every lane copies ITS OWN 16-byte noise / dz vectors and
+        // per-row coefficients of the next kFlatStages-1 k steps into its private slots and reads them back when their
+        // k comes up -- register free prefetch, so no barrier of any kind is needed (a lane only ever reads what it
+        // copied itself, completion is tracked by cp.async groups).  r2 ncu before this: the un-prefetched scalar
+        // coefficient loads stalled every iteration (long scoreboard 5.2 per issue, issue-active 39 % at 16 warps/SM),
+        // and a register double buffer of the same depth spilled at the 128-register budget of two CTAs per SM.
+        const int64_t KBD = (int64_t)p.K * BD, KB = (int64_t)p.K * p.B;
+        const int64_t kstepD = (int64_t)ksplit * BD, kstep = (int64_t)ksplit * p.B;
+        const int64_t off = b * p.D + c + (int64_t)ks * BD, offr = b + (int64_t)ks * p.B;
+        const float* ek = p.eps + off;  // issue-side running pointers
+        const float* dk = has_dz ? p.dz_ext + off : nullptr;
+        const float* qk = has_q ? p.dlq + offr : nullptr;
+        const float* lk = has_l ? p.dlpz + offr : nullptr;
+        int k_issue = ks;
+        uint32_t vi = vec_base, ci = cof_base, vr = vec_base, cr = cof_base;  // issue / read positions in the ring
+        const uint32_t vec_end = vec_base + kFlatStages * kVecBytes;
+        auto issue = [&]() {
+            if (ok && k_issue < p.K) {
+#pragma unroll
+                for (int r = 0; r < MT; ++r) {
+                    cp_async16_s(vi + (2 * r) * 512, ek + r * KBD);
+                    if (has_dz) cp_async16_s(vi + (2 * r + 1) * 512, dk + r * KBD);
+                    if (has_l) cp_async4_s(ci + (MT * MT + r) * 128, lk + r * KB);
+#pragma unroll
+                    for (int j = 0; j < MT; ++j)
+                        if (has_q) cp_async4_s(ci + (r * MT + j) * 128, qk + (r * MT + j) * KB);
+                }
+            }
+            cp_async_commit();  // (possibly empty) group: keeps the group count uniform
+            k_issue += ksplit;
+            ek += kstepD;
+            if (has_dz) dk += kstepD;
+            if (has_q) qk += kstep;
+            if (has_l) lk += kstep;
+            vi += kVecBytes;
+            ci += kCofBytes;
+            if (vi == vec_end) {
+                vi = vec_base;
+                ci = cof_base;
+            }
+        };
+#pragma unroll
+        for (int st = 0; st < kFlatStages - 1; ++st) issue();
+        for (int k = ks; k < p.K; k += ksplit) {
+            issue();
+            cp_async_wait<kFlatStages - 1>();
+#pragma unroll
+            for (int r = 0; r < MT; ++r) {
+                // rk mode: c_j = rkc * softmax_j, c_p = -rkc (inactive lanes: their slots hold zeros, rkc is finite)
+                const float rkc = rk ? rk_mul * __ldg(p.rk_w + r * p.K + k) : 1.0f;
+                float c_[MT];
+#pragma unroll
+                for (int j = 0; j < MT; ++j) {
+                    c_[j] = rkc * lds_f(cr + (r * MT + j) * 128);
+                    Cs[j] += c_[j];
+                }
+                // (a lane that was active for an earlier row group and is past the batch end now still holds that group's
+                // values in its slots: the prior coefficient must read as zero there, it feeds the CTA-wide partials)
+                const float c_p = ok ? (rk ? -rkc : lds_f(cr + (MT * MT + r) * 128)) : 0.f;
+                Cp += c_p;
+                const f32x2 CP2 = f2_bcast(c_p);
+                const float4 e4 = lds_f4(vr + (2 * r) * 512), d4 = lds_f4(vr + (2 * r + 1) * 512);
+                const f32x2 E[2] = {f2_pack(e4.x, e4.y), f2_pack(e4.z, e4.w)};
+                const f32x2 DD[2] = {f2_pack(d4.x, d4.y), f2_pack(d4.z, d4.w)};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const f32x2 EF = lap[r] ? laplace_noise2(E[h]) : E[h];
+                    const f32x2 ZZ = f2_fma(EF, SG[r][h], MU[r][h]);
+                    f32x2 DZL = 0ull;  // d(sum_j c_j log q_j + c_p log p)/dz
+#pragma unroll
+                    for (int j = 0; j < MT; ++j) {
+                        const f32x2 DF = f2_sub(ZZ, MU[j][h]);
+                        if (lap[j]) {
+                            // tt = c sign(df) (torch: sign(0) = 0); d/dmu = tt/s; sum c|df| = sum tt*df; d/dz = -tt/s
+                            float d0, d1;
+                            f2_unpack(DF, d0, d1);
+                            const unsigned cb = __float_as_uint(c_[j]);
+                            const float t0 = d0 == 0.f ? 0.f : __uint_as_float(cb ^ (__float_as_uint(d0) & 0x80000000u));
+                            const float t1 = d1 == 0.f ? 0.f : __uint_as_float(cb ^ (__float_as_uint(d1) & 0x80000000u));
+                            const f32x2 TT = f2_pack(t0, t1);
+                            const f32x2 P = f2_mul(TT, IV[j][h]);
+                            AM[j][h] = f2_add(AM[j][h], P);
+                            S[j][h] = f2_fma(TT, DF, S[j][h]);
+                            DZL = f2_sub(DZL, P);
+                        } else {
+                            // d/dmu = c df/s^2, d/ds = c (df^2/s^3 - 1/s)
+                            const f32x2 H = f2_mul(f2_bcast(c_[j]), DF);
+                            const f32x2 H2 = f2_mul(H, IV[j][h]);
+                            AM[j][h] = f2_add(AM[j][h], H2);
+                            S[j][h] = f2_fma(H, DF, S[j][h]);
+                            DZL = f2_sub(DZL, H2);
+                        }
+                    }
+                    const f32x2 DF0 = f2_sub(ZZ, PMU[h]), H0 = f2_mul(CP2, DF0);
+                    QM[h] = f2_add(QM[h], H0);
+                    QS[h] = f2_fma(H0, DF0, QS[h]);
+                    DZL = f2_fma(H0, NPI2[h], DZL);
+                    const f32x2 DZT = thru ? f2_add(DD[h], DZL) : DD[h];
+                    AM[r][h] = f2_add(AM[r][h], DZT);
+                    GS[r][h] = f2_fma(DZT, EF, GS[r][h]);
+                }
+            }
+            vr += kVecBytes;
+            cr += kCofBytes;
+            if (vr == vec_end) {
+                vr = vec_base;
+                cr = cof_base;
+            }
+        }
+        cp_async_wait<0>();
+        // d/dmu as is; d/ds: apply the powers of 1/s once per row
+        float am[MT][4], fs[MT][4];
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+            const float sv[4] = {f2_lo(S[j][0]), f2_hi(S[j][0]), f2_lo(S[j][1]), f2_hi(S[j][1])};
+            const float gv[4] = {f2_lo(GS[j][0]), f2_hi(GS[j][0]), f2_lo(GS[j][1]), f2_hi(GS[j][1])};
+            am[j][0] = f2_lo(AM[j][0]); am[j][1] = f2_hi(AM[j][0]); am[j][2] = f2_lo(AM[j][1]); am[j][3] = f2_hi(AM[j][1]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float iv = inv[j][i], i2 = iv * iv;
+                fs[j][i] = fmaf(sv[i], lap[j] ? i2 : i2 * iv, fmaf(-Cs[j], iv, gv[i]));
+            }
+        }
+        if (ksplit > 1) {  // fixed-order combine of the K splits through shared memory (uniform branch)
+            __syncthreads();
+            float* mine = red + (size_t)wid * (2 * MT * 4 * 32);
+#pragma unroll
+            for (int j = 0; j < MT; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    mine[((j * 4 + i) * 2 + 0) * 32 + lane] = am[j][i];
+                    mine[((j * 4 + i) * 2 + 1) * 32 + lane] = fs[j][i];
+                }
+            __syncthreads();
+            if (ks == 0) {
+#pragma unroll
+                for (int j = 0; j < MT; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float tm = 0.f, ts = 0.f;
+                        for (int w = 0; w < ksplit; ++w) {
+                            const float* o = red + (size_t)(wid + w) * (2 * MT * 4 * 32);
+                            tm += o[((j * 4 + i) * 2 + 0) * 32 + lane];
+                            ts += o[((j * 4 + i) * 2 + 1) * 32 + lane];
+                        }
+                        am[j][i] = tm;
+                        fs[j][i] = ts;
+                    }
+            }
+        }
+        if (ok && ks == 0) {
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+                const int64_t o = ((int64_t)j * p.B + b) * p.D + c;
+                *reinterpret_cast<float4*>(p.dmu + o) = make_float4(am[j][0], am[j][1], am[j][2], am[j][3]);
+                *reinterpret_cast<float4*>(p.ds + o) = make_float4(fs[j][0], fs[j][1], fs[j][2], fs[j][3]);
+            }
+        }
+    }
+    // prior gradient partials of this CTA: (2, D) into ws
+    __syncthreads();
+    float* mine = red + (size_t)wid * (8 * 32);
+    {
+        const float qmv[4] = {f2_lo(QM[0]), f2_hi(QM[0]), f2_lo(QM[1]), f2_hi(QM[1])};
+        const float qsv[4] = {f2_lo(QS[0]), f2_hi(QS[0]), f2_lo(QS[1]), f2_hi(QS[1])};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float pi2 = pinv[i] * pinv[i];
+            mine[(i * 2 + 0) * 32 + lane] = col_sum<lpr>(qmv[i] * pi2);
+            mine[(i * 2 + 1) * 32 + lane] = col_sum<lpr>(fmaf(qsv[i], pi2 * pinv[i], -Cp * pinv[i]));
+        }
+    }
+    __syncthreads();
+    if (wid == 0 && lane < lpr && colok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float tm = 0.f, ts = 0.f;
+            for (int w = 0; w < kFlatWarps; ++w) {
+                tm += red[(size_t)w * (8 * 32) + (i * 2 + 0) * 32 + lane];
+                ts += red[(size_t)w * (8 * 32) + (i * 2 + 1) * 32 + lane];
+            }
+            p.ws[(size_t)blockIdx.x * 2 * p.D + c + i] = tm;
+            p.ws[(size_t)blockIdx.x * 2 * p.D + p.D + c + i] = ts;
+        }
+    }
+}
+
 typedef void (*moe_kernel_t)(const MoeParams);
 template <bool FWD, int MT_, int NC_>
 static moe_kernel_t pick_variant(int lm, bool full) {
@@ -459,6 +1001,63 @@ static moe_kernel_t pick_reg_kernel(int M, int D, const int* dist, int* nc_out) 
     MOE_PICK(3, 1) MOE_PICK(3, 2)
     MOE_PICK(4, 1) MOE_PICK(4, 2)
 #undef MOE_PICK
+    return nullptr;
+}
+
+struct FlatPlan {
+    int lpr, ksplit;
+    unsigned grid;
+};
+typedef void (*moe_flat_kernel_t)(const MoeParams, int);
+
+template <bool FWD, int MT_, int LPR_>
+static moe_flat_kernel_t pick_flat_lm(int lm, bool hot) {
+#define MOE_F(LM_)                                                        \
+    (FWD ? (moe_flat_kernel_t)moe_fwd_flat_kernel<MT_, LM_, LPR_>         \
+         : (hot && MT_ == 2 && LM_ < 2 ? (moe_flat_kernel_t)moe_bwd_flat_kernel<MT_, LM_, LPR_, (MT_ == 2 && LM_ < 2)> \
+                                       : (moe_flat_kernel_t)moe_bwd_flat_kernel<MT_, LM_, LPR_, false>))
+    return lm == 0 ? MOE_F(0) : (lm == 1 ? MOE_F(1) : MOE_F(2));
+#undef MOE_F
+}
+template <bool FWD, int MT_>
+static moe_flat_kernel_t pick_flat_lpr(int lpr, int lm, bool hot) {
+    switch (lpr) {
+        case 4: return pick_flat_lm<FWD, MT_, 4>(lm, hot);
+        case 8: return pick_flat_lm<FWD, MT_, 8>(lm, hot);
+        case 16: return pick_flat_lm<FWD, MT_, 16>(lm, hot);
+        case 32: return pick_flat_lm<FWD, MT_, 32>(lm, hot);
+    }
+    return nullptr;
+}
+
+// flat kernels need 16-byte aligned (b, c) vectors: D % 4 == 0 and aligned base pointers
+template <bool FWD>
+static moe_flat_kernel_t pick_flat_kernel(const MoeParams& p, FlatPlan* plan) {
+    if (p.D % 4 != 0 || p.D > 128 || p.M > 3) return nullptr;
+    if (!aligned16(p.mu) || !aligned16(p.s) || !aligned16(p.eps)) return nullptr;
+    if (FWD ? !aligned16(p.z) : (!aligned16(p.dmu) || !aligned16(p.ds) || (p.dz_ext && !aligned16(p.dz_ext)))) return nullptr;
+    int lpr = 4;  // narrower rows (D <= 8) run with idle lanes
+    while (lpr * 4 < p.D) lpr <<= 1;
+    const int rpw = 32 / lpr;
+    const int64_t ntiles = (p.B + rpw - 1) / rpw;
+    int ksplit = 1;
+    while (ksplit < kFlatWarps && ntiles * ksplit < (int64_t)kNumSMs * 16 && ksplit * 2 <= p.K) ksplit <<= 1;
+    const int npw = kFlatWarps / ksplit;
+    const int64_t ngroups = (ntiles + npw - 1) / npw;
+    const int64_t cap = (int64_t)kNumSMs * (FWD ? (p.M <= 2 ? 3 : 2) : (p.M <= 2 ? 2 : 1));
+    plan->lpr = lpr;
+    plan->ksplit = ksplit;
+    plan->grid = (unsigned)(ngroups < cap ? ngroups : cap);
+    int nlap = 0;
+    for (int j = 0; j < p.M; ++j) nlap += p.dist[j] == MMVAE_LAPLACE;
+    const int lm = nlap == 0 ? 0 : (nlap == p.M ? 1 : 2);
+    // the training-step argument pattern (IWAE / DReG) gets the variant without per-iteration pointer tests
+    const bool hot = !FWD && p.dz_ext && p.dlq && p.through_z && ((p.rk_w != nullptr) != (p.dlpz != nullptr));
+    switch (p.M) {
+        case 1: return pick_flat_lpr<FWD, 1>(lpr, lm, hot);
+        case 2: return pick_flat_lpr<FWD, 2>(lpr, lm, hot);
+        case 3: return pick_flat_lpr<FWD, 3>(lpr, lm, hot);
+    }
     return nullptr;
 }
 
@@ -492,6 +1091,17 @@ extern "C" int mmvae_moe_logdens_fwd(const float* mu, const float* s, int M, int
     if (rc) return rc;
     if (!z || !lq || !lpz) return MMVAE_E_ARG;
     p.z = z; p.lq = lq; p.lpz = lpz;
+    FlatPlan plan;
+    if (moe_flat_kernel_t kf = pick_flat_kernel<true>(p, &plan)) {
+        const size_t ring = (size_t)kFlatWarps * kFwdStages * M * 32 * sizeof(float4);
+        if (ring > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute((const void*)kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
+            if (e != cudaSuccess) return (int)e;
+        }
+        kf<<<plan.grid, kFlatWarps * 32, ring, (cudaStream_t)stream>>>(p, plan.ksplit);
+        MMVAE_LAUNCH_CHECK();
+        return 0;
+    }
     const size_t smem = (size_t)(4 * M * D + 3 * D) * sizeof(float);
     int nc = 0;
     if (moe_kernel_t kr = pick_reg_kernel<true>(M, D, p.dist, &nc)) {
@@ -515,11 +1125,38 @@ extern "C" int mmvae_moe_logdens_bwd(const float* mu, const float* s, int M, int
                                      const int32_t* dists_host, const float* mu0, const float* s0, const float* eps,
                                      const float* dz_ext, const float* dlq, const float* dlpz, int through_z,
                                      float* dmu, float* ds, float* dprior_ws, float* dmu0, float* ds0, void* stream) {
+    return mmvae_moe_logdens_bwd_rk(mu, s, M, B, D, K, dists_host, mu0, s0, eps, dz_ext, dlq, dlpz, through_z, nullptr,
+                                    nullptr, 1.0f, dmu, ds, dprior_ws, dmu0, ds0, stream);
+}
+
+extern "C" int mmvae_moe_logdens_bwd_rk(const float* mu, const float* s, int M, int64_t B, int D, int K,
+                                        const int32_t* dists_host, const float* mu0, const float* s0, const float* eps,
+                                        const float* dz_ext, const float* dlq, const float* dlpz, int through_z,
+                                        const float* rk_w, const float* rk_scale_dev, float rk_mul,
+                                        float* dmu, float* ds, float* dprior_ws, float* dmu0, float* ds0, void* stream) {
     MoeParams p{};
     int rc = moe_fill(p, mu, s, M, B, D, K, dists_host, mu0, s0, eps);
     if (rc) return rc;
     if (!dmu || !ds || !dprior_ws) return MMVAE_E_ARG;
+    if (rk_w && (dlpz || !dlq)) return MMVAE_E_ARG;  // rk mode: dlq holds softmax_j(lq), dlpz is implied (-rk)
     p.dz_ext = dz_ext; p.dlq = dlq; p.dlpz = dlpz; p.through_z = through_z; p.dmu = dmu; p.ds = ds; p.ws = dprior_ws;
+    p.rk_w = rk_w; p.rk_scale = rk_scale_dev; p.rk_mul = rk_mul;
+    FlatPlan plan;
+    if (moe_flat_kernel_t kf = pick_flat_kernel<false>(p, &plan)) {
+        const size_t ring = (size_t)kFlatWarps * kFlatStages * 32 * (2 * M * sizeof(float4) + (M * M + M) * sizeof(float));
+        if (ring > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute((const void*)kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
+            if (e != cudaSuccess) return (int)e;
+        }
+        kf<<<plan.grid, kFlatWarps * 32, ring, (cudaStream_t)stream>>>(p, plan.ksplit);
+        MMVAE_LAUNCH_CHECK();
+        if (dmu0 && ds0) {
+            partial_sum_kernel<<<2 * D, 128, 0, (cudaStream_t)stream>>>(dprior_ws, (int)plan.grid, 2 * D, D, dmu0, ds0);
+            MMVAE_LAUNCH_CHECK();
+        }
+        return 0;
+    }
+    if (rk_w) return MMVAE_E_LIMIT;  // rk mode exists in the flat kernels only (D % 4 == 0, D <= 128, M <= 3)
     const int nw = moe_warps(K);
     const size_t smem = (size_t)(4 * M * D + 2 * D + nw * (2 * M * D + 2 * D)) * sizeof(float);
     if (smem > 200 * 1024) return MMVAE_E_LIMIT;

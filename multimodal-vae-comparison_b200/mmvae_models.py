@@ -178,11 +178,8 @@ class MOE(TorchMMVAE):
                 rows.append(self.obj_fn.lpx_rows(_first(vae.dec({"latents": z[src], "masks": data[name]["masks"]})),
                                                  data[name], vae.llik_scaling, ltype=_ltype(vae), family=_family(vae),
                                                  out=buf[r, 1]))
-        d = {"lpz": lpz, "lq": lq, "lpx_z": buf.view(M, L, K, B)}
-        if self.obj_fn.obj_name == "iwae":
-            d["lpx_rows"] = rows
-        else:  # DReG combine reads the stacked tensor; route the gradient through a differentiable stack
-            d["lpx_z"] = torch.stack(rows).view(M, L, K, B)
+        # both combines read the row vectors through a pointer table; "lpx_z" is the same memory, for logging
+        d = {"lpz": lpz, "lq": lq, "lpx_z": buf.view(M, L, K, B), "lpx_rows": rows}
         return self.obj_fn.calculate_loss(d)
 
     def modality_mixing(self, mods):

@@ -216,7 +216,11 @@ class MultimodalObjective(BaseObjective):
     def dreg(self, data):
         """objectives.py:361-387 (parity mode: softmax over K of batch-summed log-weights; the reference's gradient
         hook is attached to a tensor that is not on the loss path, so no DReG re-weighting of dz takes place)."""
-        loss, lw = ops.dreg_combine(data["lpz"], data["lq"], data["lpx_z"], self.group)
+        if data.get("lpx_rows") is not None:  # list of M*L row vectors: pointer table, gradients folded into the MoE kernel
+            L = len(data["lpx_rows"]) // data["lpz"].shape[0]
+            loss, lw = ops.dreg_combine_rows(data["lpz"], data["lq"], data["lpx_rows"], L, self.group)
+        else:
+            loss, lw = ops.dreg_combine(data["lpz"], data["lq"], data["lpx_z"], self.group)
         return {"loss": loss, "kld": torch.tensor(0), "reconstruction_loss": data["lpx_z"], "lw": lw}
 
 

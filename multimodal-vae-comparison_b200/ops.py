@@ -505,14 +505,35 @@ class _MoeLogdens(torch.autograd.Function):
         f = lambda t: None if t is None else t.detach().float().contiguous()
         dz, dlq, dlpz = f(dz), f(dlq), f(dlpz)
         dev = mu_c.device
+        # "rk" hand-over from a DReG combine that consumed lq / lpz (ops._DregRows.backward): its gradients are
+        # c[r,k] * softmax_j(lq) and -c[r,k] with c constant over b, so instead of materialising (M,M,K,B) / (M,K,B)
+        # tensors it leaves (wt, g, 1/M, softmax_j) here and the kernel folds them into its coefficients
+        rk, ctx.rk = getattr(ctx, "rk", None), None
+        rk_w = rk_g = None
+        rk_mul = 1.0
+        if rk is not None:
+            wt, g, mul, soft = rk
+            if dlq is None and dlpz is None and moe_rk_supported(M, D):
+                rk_w, rk_g, rk_mul, dlq = wt, g, mul, soft
+            else:  # lq / lpz also feed something else (or an unsupported shape): materialise and add
+                c = wt * mul if g is None else wt * (g * mul)
+                d1, d2 = c.view(M, 1, K, 1) * soft, (-c).view(M, K, 1).expand(M, K, B)
+                dlq = d1 if dlq is None else dlq + d1
+                dlpz = d2.contiguous() if dlpz is None else dlpz + d2
         dmu, ds = torch.empty_like(mu_c), torch.empty_like(s_c)
         nws = _lib.load().mmvae_moe_logdens_bwd_ws_floats(B, D, K)
         ws = torch.empty(nws, dtype=torch.float32, device=dev)
         dprior = torch.empty(2, D, dtype=torch.float32, device=dev)
-        call("mmvae_moe_logdens_bwd", _ptr(mu_c), _ptr(s_c), M, B, D, K, darr, _ptr(mu0_c), _ptr(s0_c), _ptr(eps_c),
-             _ptr(dz), _ptr(dlq), _ptr(dlpz), through_z, _ptr(dmu), _ptr(ds), _ptr(ws), _ptr(dprior[0]),
-             _ptr(dprior[1]), _stream())
+        call("mmvae_moe_logdens_bwd_rk", _ptr(mu_c), _ptr(s_c), M, B, D, K, darr, _ptr(mu0_c), _ptr(s0_c), _ptr(eps_c),
+             _ptr(dz), _ptr(dlq), _ptr(dlpz), through_z, _ptr(rk_w), _ptr(rk_g), float(rk_mul), _ptr(dmu), _ptr(ds),
+             _ptr(ws), _ptr(dprior[0]), _ptr(dprior[1]), _stream())
         return dmu, ds, dprior[0].reshape(sh0), dprior[1].reshape(sh1), None, None, None
+
+
+def moe_rk_supported(M, D):
+    """Shapes the flat MoE kernels (and with them the folded DReG coefficients) cover: include/mmvae_b200.h
+    mmvae_moe_logdens_bwd_rk."""
+    return D % 4 == 0 and D <= 128 and M <= 3
 
 
 def moe_logdens(mu, s, mu0, s0, eps, dists, through_z=True):
@@ -691,6 +712,66 @@ def dreg_combine(lpz, lq, lpx, group=None):
     return _Dreg.apply(lpz, lq, lpx, group)
 
 
+class _DregRows(torch.autograd.Function):
+    """DReG combine over a LIST of likelihood row vectors (index r*L + l, (K*B,) each) read through a pointer table (no
+    stack copy).  Backward: one launch writes the (M,L,K,B) row gradients -(g/M) wt[r,k]; the gradients of lq / lpz
+    are not materialised -- when `node` (the backward node of the ops.moe_logdens call that produced lq and lpz) is
+    given, (wt, g, 1/M, softmax_j lq) is handed to it and folded into the coefficients of its kernel."""
+
+    @staticmethod
+    def forward(ctx, lpz, lq, L, group, node, *rows):
+        ctx.set_materialize_grads(False)
+        _need_cuda(lpz, lq, *rows)
+        M, K, B = lpz.shape
+        f = lambda t: t.detach().float().contiguous()
+        lpz_c, lq_c = f(lpz), f(lq)
+        rows_c = [f(r).reshape(-1) for r in rows]
+        if len(rows_c) != M * L or any(r.numel() != K * B for r in rows_c):
+            raise RuntimeError("mmvae_b200: dreg needs M*L row vectors of K*B elements")
+        ptrs = (ctypes.c_void_p * (M * L))(*[r.data_ptr() for r in rows_c])
+        dev = lpz.device
+        part = torch.empty(((_lib.DREG_MAX_SPLIT + 1), M * K), dtype=torch.float64, device=dev)
+        lq_soft = torch.empty((M, M, K, B), dtype=torch.float32, device=dev)
+        call("mmvae_objective_dreg_stage1_ptrs", _ptr(lpz_c), _ptr(lq_c), _P(0), ptrs, M, L, K, B, _ptr(part),
+             _ptr(lq_soft), _stream())
+        lw = part[0]
+        if group is not None:  # SURVEY 8e (1): the (M,K) batch sums are global; capturable (NCCL on the current stream)
+            import torch.distributed as dist
+            dist.all_reduce(lw, group=group)
+        wt = torch.empty((M, K), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        call("mmvae_objective_dreg_stage2", _ptr(lw), M, K, _ptr(wt), _ptr(loss), _stream())
+        ctx.save_for_backward(wt, lq_soft)
+        ctx.meta = (M, L, K, B, [r.shape for r in rows])
+        ctx.node = node
+        lw_out = lw.clone().view(M, K)
+        ctx.mark_non_differentiable(lw_out)
+        return loss, lw_out
+
+    @staticmethod
+    def backward(ctx, g, _glw):
+        M, L, K, B, shapes = ctx.meta
+        if g is None:
+            return (None,) * (5 + M * L)
+        wt, lq_soft = ctx.saved_tensors
+        gs = None if _is_unit(g) else g.detach().float().contiguous()
+        d_rows = torch.empty((M, L, K, B), dtype=torch.float32, device=wt.device)
+        call("mmvae_objective_dreg_rowgrads", _ptr(gs), _ptr(wt), M, L, K, B, _ptr(d_rows), _stream())
+        row_grads = tuple(d_rows[i // L, i % L].reshape(shapes[i]) for i in range(M * L))
+        if ctx.node is not None:
+            ctx.node.rk = (wt, gs, 1.0 / M, lq_soft)
+            return (None, None, None, None, None) + row_grads
+        c = wt / M if gs is None else wt * (gs / M)
+        return (((-c).view(M, K, 1).expand(M, K, B)), c.view(M, 1, K, 1) * lq_soft, None, None, None) + row_grads
+
+
+def dreg_combine_rows(lpz, lq, rows, L, group=None):
+    """rows: list of M*L tensors (K*B,), index r*L + l.  If lq and lpz are the direct outputs of one ops.moe_logdens
+    call, their gradients are folded into that call's backward kernel (no (M,M,K,B) temporaries)."""
+    node = lq.grad_fn
+    if node is None or node is not lpz.grad_fn or not isinstance(node, _MoeLogdens._backward_cls):
+        node = None
+    return _DregRows.apply(lpz, lq, int(L), group, node, *rows)
 class _KlElementwise(torch.autograd.Function):
     """include/mmvae_b200.h mmvae_kl_elementwise_{fwd,bwd}: (n, D) KL(q || N(loc0, scale0)), prior broadcast over n."""
 

@@ -77,6 +77,10 @@ def make_leaves(name, B=None, seed=1234, recon_dtype=torch.float32):
                       for tm, _ in term_plan(cfg["model"], M)]
     t["noise"] = [syn.make_noise(g, kind, shape)
                   for kind, shape in _noise_plan(cfg["model"], M, K, B, D, pv, [m["dist"] for m in cfg["mods"]])]
+    if cfg.get("latent_only"):
+        # the gradient the (absent) decoders would send back into z: a second root of the backward, so that the latent
+        # backward reads eps AND dz like in a full step (SURVEY 8d counts 4*K*D*e bytes per drawn tensor)
+        t["dz"] = torch.randn(M, K, B, D, generator=g) * 0.1
     return cfg, t
 
 
@@ -117,6 +121,8 @@ class LeafStep:
         self.targets = [x.to(dev) for x in tensors["targets"]]
         self.recon = [x.to(dev).requires_grad_(True) for x in tensors["recon"]]
         self.noise = [x.to(dev) for x in tensors["noise"]]
+        self.dz = tensors["dz"].to(dev) if tensors.get("dz") is not None else None
+        self._z = None
         self.plan = term_plan(self.model, self.M)
         self.codes = [1 if m["dist"] == "laplace" else 0 for m in cfg["mods"]]
         if self.model == "mopoe":
@@ -238,10 +244,19 @@ class LeafStep:
     def loss(self):
         return getattr(self, "_" + self.model)()
 
+    def backward(self, loss):
+        """Backward from the static unit root (no ones_like fill kernel at its head).  Latent-only workloads have a
+        second root: z with the synthetic decoder gradient `dz`."""
+        if self.dz is not None and self._z is not None:
+            torch.autograd.backward([loss, self._z], [self._one, self.dz])
+        else:
+            loss.backward(self._one)
+        self._z = None
+
     def run(self):
         self.zero_grad()
         loss = self.loss()
-        loss.backward(self._one)  # static root gradient: no ones_like fill kernel at the head of the backward
+        self.backward(loss)
         self.finish()
         return loss
 
@@ -276,12 +291,12 @@ class LeafStep:
             return ops.moe_logdens(self.mu, self.s, mu0, s0, eps, self.codes, True)
 
         z, lq, lpz = self._latent(latent)
-        self._join(lq, lpz, *rows)
+        self._join(lq, lpz, z, *rows)
+        self._z = z
         L = len(rows) // M
         if self.obj == "iwae":
             return ops.iwae_combine_rows(lpz, lq, rows, L, self.beta, self._ticket)[0]
-        lpx = torch.stack(rows).view(M, L, K, B)
-        return ops.dreg_combine(lpz, lq, lpx, self.group)[0]
+        return ops.dreg_combine_rows(lpz, lq, rows, L, self.group)[0]
 
     def _poe(self):
         M, D = self.M, self.D
@@ -365,7 +380,7 @@ class GraphedStep:
         step.zero_grad()
         with torch.cuda.graph(self.graph):
             self.loss = step.loss()
-            self.loss.backward(step._one)
+            step.backward(self.loss)
             step.finish()  # joins the side stream of an in-step gradient all-reduce into the capture
         self.grads = [t.grad for t in step.leaves()]
 

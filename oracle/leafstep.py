@@ -22,11 +22,13 @@ def build(cfg, tensors, device="cpu", dtype=torch.float32):
     return dict(mu=mu, s=s, pz_logits=pz, recon=recon), mods, noise
 
 
-def loss_latent_only(cfg, mods, pz, noise, rows, beta=1.0):
+def loss_latent_only(cfg, mods, pz, noise, rows, beta=1.0, zs_out=None):
     """MoE IWAE / DReG with the likelihood row vectors given directly (SURVEY 8d "latent + combine only"):
     objectives.py:342-387 on top of MOE.forward's samples."""
     M, K = len(mods), cfg["K"]
     zs = refmath.moe_forward(mods, noise, K)
+    if zs_out is not None:
+        zs_out.extend(zs)
     mu0 = torch.zeros_like(pz)
     _, s0 = refmath.prior_params(mu0, pz)
     L = len(rows) // M
@@ -65,10 +67,16 @@ def run(cfg, tensors, beta=1.0, device="cpu", dtype=torch.float32):
     """One objective fwd+bwd.  Returns (loss, {name: grad}) with grads for mu, s, pz_logits and recon[i]."""
     leaves, mods, noise = build(cfg, tensors, device, dtype)
     if cfg.get("latent_only"):
-        l = loss_latent_only(cfg, mods, leaves["pz_logits"], noise, leaves["recon"], beta)
+        zs = []
+        l = loss_latent_only(cfg, mods, leaves["pz_logits"], noise, leaves["recon"], beta, zs)
+        if tensors.get("dz") is not None:  # gradient the (absent) decoders would send into z: a second backward root
+            dz = tensors["dz"].to(device=device, dtype=dtype)
+            (l + sum((z * dz[r]).sum() for r, z in enumerate(zs))).backward()
+        else:
+            l.backward()
     else:
         l = loss(cfg, mods, leaves["pz_logits"], noise, beta)
-    l.backward()
+        l.backward()
     grads = {"mu": leaves["mu"].grad, "s": leaves["s"].grad, "pz_logits": leaves["pz_logits"].grad}
     for i, r in enumerate(leaves["recon"]):
         grads["recon%d" % i] = r.grad

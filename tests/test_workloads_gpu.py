@@ -14,34 +14,60 @@ def _rel(a, b):
     return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-12)
 
 
-CASES = [("c1_poe_elbo_cdsprites_l1", 8, 1e-5), ("c2_moe_iwae_cdsprites_l5", 4, 1e-5),
-         ("c3_mopoe_elbo_sprites", 4, 1e-5), ("c4_moe_dreg_mnistsvhn", 6, 2e-5), ("c5_dmvae_elbo_cub", 6, 1e-5),
-         ("c4_moe_dreg_latent_only", 37, 2e-5)]
+TOL = 1e-5  # BASELINE.json north_star: losses, KL and gradients within 1e-5 relative in fp32
+
+CASES = [("c1_poe_elbo_cdsprites_l1", 8), ("c2_moe_iwae_cdsprites_l5", 4), ("c3_mopoe_elbo_sprites", 4),
+         ("c4_moe_dreg_mnistsvhn", 6), ("c5_dmvae_elbo_cub", 6), ("c4_moe_dreg_latent_only", 37)]
+# IWAE / DReG: the gradients carry softmax weights over (r,k) of log-weights |lw| ~ 10^3..10^4 (sums over P of the
+# reconstruction term, for DReG also over the batch).  A softmax weight is as accurate as the ABSOLUTE error of lw, and
+# in fp32 arithmetic -- the reference's own -- that error is ulp(|lw|) ~ 1e-4..1e-3: two correct fp32 evaluations of
+# the reference's formulas differ from each other, and from the exact result, by more than 1e-5.  For these workloads
+# the bound is therefore the larger of 1e-5 and twice the deviation of the REFERENCE arithmetic itself (the fp32 oracle,
+# pinned to the unmodified reference at 4e-7 by oracle/validate_against_reference.py) from the fp64 evaluation on the
+# same tensors, the worst over three seeds for both sides (the floor is set by rounding noise, a single draw of it is not a bound).
+NOISE_FLOOR = {"c2_moe_iwae_cdsprites_l5", "c4_moe_dreg_mnistsvhn", "c4_moe_dreg_latent_only"}
 
 
-@pytest.mark.parametrize("name,B,tol", CASES)
-@pytest.mark.parametrize("graphed", [False, True])
-def test_leafstep_matches_oracle(name, B, tol, graphed):
-    import mmvae_b200.workloads as W
-    cfg, t = W.make_leaves(name, B=B, seed=77)
-    t["pz_logits"] = torch.randn(1, cfg["D"], generator=torch.Generator().manual_seed(5)) * 0.3
-    # the IWAE softmax over (r,k) is conditioned by |lw| ~ sum over P of the reconstruction term; compare in fp64
-    ref_loss, ref_g = leafstep.run(cfg, t, beta=1.3, dtype=torch.float64)
-    step = W.LeafStep(cfg, t, beta=1.3)
-    if graphed:
-        g = W.GraphedStep(step)
-        loss = g.run()
-        loss = g.run()
-    else:
-        loss = step.run()
-    torch.cuda.synchronize()
-    assert _rel(loss, ref_loss) < tol
-    assert _rel(step.mu.grad, ref_g["mu"]) < 5 * tol
-    assert _rel(step.s.grad, ref_g["s"]) < 5 * tol
-    if ref_g["pz_logits"] is not None and float(ref_g["pz_logits"].abs().max()) > 0:
-        assert _rel(step.pz_logits.grad, ref_g["pz_logits"]) < 5 * tol
+def _grads(step):
+    g = {"mu": step.mu.grad, "s": step.s.grad, "pz_logits": step.pz_logits.grad}
     for i, r in enumerate(step.recon):
-        assert _rel(r.grad, ref_g["recon%d" % i]) < 5 * tol, i
+        g["recon%d" % i] = r.grad
+    return g
+
+
+@pytest.mark.parametrize("name,B", CASES)
+@pytest.mark.parametrize("graphed", [False, True])
+def test_leafstep_matches_oracle(name, B, graphed):
+    import mmvae_b200.workloads as W
+    seeds = (77, 78, 79) if name in NOISE_FLOOR else (77,)
+    ours, ref32 = {}, {}
+    for seed in seeds:
+        cfg, t = W.make_leaves(name, B=B, seed=seed)
+        t["pz_logits"] = torch.randn(1, cfg["D"], generator=torch.Generator().manual_seed(5)) * 0.3
+        l64, g64 = leafstep.run(cfg, t, beta=1.3, dtype=torch.float64)
+        step = W.LeafStep(cfg, t, beta=1.3)
+        if graphed:
+            g = W.GraphedStep(step)
+            loss = g.run()
+            loss = g.run()
+        else:
+            loss = step.run()
+        torch.cuda.synchronize()
+        mine = dict(_grads(step), loss=loss)
+        g64 = dict(g64, loss=l64)
+        if name in NOISE_FLOOR:
+            l32, g32 = leafstep.run(cfg, t, beta=1.3, dtype=torch.float32)
+            g32 = dict(g32, loss=l32)
+        for k, exact in g64.items():
+            if exact is None or float(exact.abs().max()) == 0:
+                continue
+            ours[k] = max(ours.get(k, 0.0), _rel(mine[k], exact))
+            if name in NOISE_FLOOR:
+                ref32[k] = max(ref32.get(k, 0.0), _rel(g32[k], exact))
+    for k, err in ours.items():
+        bound = max(TOL, 2.0 * ref32[k]) if name in NOISE_FLOOR else TOL
+        assert err <= bound, "%s %s: deviation from fp64 %.2e > bound %.2e (reference fp32 arithmetic: %.2e)" % (
+            name, k, err, bound, ref32.get(k, float("nan")))
 
 
 @pytest.mark.parametrize("name,B", [("c2_moe_iwae_cdsprites_l5", 16), ("c1_poe_elbo_cdsprites_l1", 64),
