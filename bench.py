@@ -1,20 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- objective fwd+bwd samples/s of the latent + objective hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+                    [--batch B_PER_GPU | --global-batch B] [--dtype fp32|bf16]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-Workload at N=1: BASELINE.json configs[1] -- MMVAE (MoE) IWAE K=30 on CdSprites+ level-5 shapes, batch 256, fp32
-(the configuration the metric is quoted on; it fits one GPU).  N>1 is batch sharded, weak scaling (256 samples per
-GPU), one NCCL all-reduce(SUM) of the replicated prior-logit gradient per step; no data-path collective.
+Workload at N=1: BASELINE.json configs[1] -- MMVAE (MoE) IWAE K=30 on CdSprites+ level-5 shapes, batch 256, fp32 (the
+configuration the metric is quoted on; it fits one GPU).  N>1 is batch sharded: weak scaling by default (the workload's
+batch per GPU), `--global-batch B` splits a fixed batch over the ranks (strong scaling, e.g. configs[1] "batch 256,
+8xB200" = 32 per GPU).  Collectives: one NCCL all-reduce(SUM) of the replicated-parameter gradient per step plus the
+forward exchanges exact parity needs (DReG (M,K) batch sums, optimal_sigma scalar) -- all captured in the step's CUDA
+graph; no data-path collective.
 
-A "step" is one objective fwd+bwd on synthetic leaf tensors (SURVEY.md 8d protocol).  Inputs are resident in HBM for
-`value`; `e2e` repeats the measurement with every input in pinned HOST memory, H2D copies and the loss read-back
-inside the timed region.  Per-step working set (~1.6 GB) is far larger than the 126 MB L2, so no explicit flush.
+A "step" is one objective fwd+bwd on synthetic leaf tensors (SURVEY.md 8d protocol).  `value`: inputs resident in HBM.
+`e2e`: the call a user of the reference makes -- model.objective(batch) + backward through the drop-in plugin (stand-in
+linear encoders / decoders), the batch coming from pinned HOST memory every step, loss read back, gradients of the
+replicated parameters all-reduced at N>1.  `e2e_leaf`: the leaf-tensor step with EVERY input (reconstructions included)
+shipped from pinned host memory.  Timed region: at least K steps and at least 0.3 s of back-to-back steps (the count is in
+`timed_steps`).  Working sets smaller than 4x the 126 MB L2 are timed step by step with an L2 flush in between.
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -26,6 +34,10 @@ sys.path.insert(0, ROOT)
 
 DEFAULT_WORKLOAD = "c2_moe_iwae_cdsprites_l5"
 METRIC = "objective fwd+bwd samples/s"
+MIN_TIMED_S = 0.3
+L2_BYTES = 126 << 20
+# CPU arms: a step of the full workload batch unless its element count exceeds this budget (C2 at B=256: 0.64 G)
+CPU_ELEMS_PER_STEP = 700e6
 
 
 def parse():
@@ -36,6 +48,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default: the workload's batch)")
+    ap.add_argument("--global-batch", type=int, default=None, help="fixed global batch split over the ranks (strong scaling)")
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--streams", type=int, default=3, choices=[1, 3],
@@ -44,7 +57,9 @@ def parse():
                     help="N>1: all-reduce after the step (eager NCCL call) instead of inside it (side stream, captured)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-batch", type=int, default=8, help="samples per step of the bounded CPU sample")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the sharded-vs-unsharded numerical check")
+    ap.add_argument("--cpu-batch", type=int, default=None,
+                    help="opt-in: samples per step of the CPU arms (default: the workload batch, bounded by an element budget)")
     return ap.parse_args()
 
 
@@ -101,8 +116,7 @@ class ClockSampler:
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm),
-                "how": "nvidia-smi -lms 20 from the start of the timed region; the same step loop keeps running "
-                       "(untimed) until >= 0.3 s of load have been sampled"}
+                "how": "nvidia-smi -lms 20 over the timed region (>= 0.3 s of back-to-back steps)"}
 
 
 class KernelTimer:
@@ -124,7 +138,6 @@ class KernelTimer:
         a.record()
         rc = fn()
         b.record()
-        # loglik entry points: (recon, ld, dtype, target, ld, dtype, rows, B, P, ...) -> algorithmic bytes
         nb = None
         if name.startswith("mmvae_moe_logdens") and len(args) > 10:
             # (mu, s, M, B, D, K, dists, mu0, s0, eps, ...): fwd reads eps + writes z; bwd reads eps (+ dz_ext)
@@ -136,121 +149,177 @@ class KernelTimer:
                 has_dz = bool(getattr(args[10], "value", args[10]))
                 nb = big * (2 if has_dz else 1) + rows + 4 * M * B * D * 4
         if name.startswith("mmvae_loglik_rowreduce") and len(args) > 8:
+            # (recon, ld, dtype, target, ld, dtype, rows, B, P, ...) -> algorithmic bytes
             ex, et, rows, B, P = (2 if args[2] else 4), (2 if args[5] else 4), args[6], args[7], args[8]
             R, T = rows * P * ex, B * P * et
             nb = (R + T if name.endswith("_fwd") else 2 * R + T) + rows * 4
+        if name.startswith("mmvae_osigma") and len(args) > 8:
+            ex, et, rows, B, P = (2 if args[2] else 4), (2 if args[5] else 4), args[6], args[7], args[8]
+            R, T = rows * P * ex, B * P * et
+            nb = (2 * R + T) if name.endswith("_bwd") else (R + T)
         self.ev[name].append((a, b, nb))
         return rc
 
-    def times_ms(self, name):
-        return [a.elapsed_time(b) for a, b, _ in self.ev[name]]
-
     def biggest(self, name):
         """(times_ms, bytes) of the launches with the largest algorithmic byte count (the dominant term)."""
-        if not self.ev[name]:
+        if not self.ev.get(name):
             return [], 0
         top = max(nb or 0 for _, _, nb in self.ev[name])
-        return [a.elapsed_time(b) for a, b, nb in self.ev[name] if (nb or 0) == top], top
+        ms = [a.elapsed_time(b) for a, b, nb in self.ev[name] if (nb or 0) == top]
+        return (ms[len(ms) // 5:] if len(ms) >= 5 else ms), top
+
+
+def local_batch(args, cfg_default_B, world):
+    """(samples per GPU, scaling mode)."""
+    if args.global_batch is not None:
+        if args.global_batch % world:
+            raise SystemExit("--global-batch %d is not divisible by %d ranks" % (args.global_batch, world))
+        return args.global_batch // world, "strong"
+    return (args.batch or cfg_default_B), "weak"
+
+
+def flush_needed(step_bytes):
+    """Working set of a step vs the 126 MB L2: big steps stream far more than L2 holds (no flush needed); small ones are
+    timed one by one with a 256 MB write in between so that no step starts with its inputs cached."""
+    return step_bytes < 4 * L2_BYTES
+
+
+def config_dict(args, cfg, B, world, scaling):
+    """The `config` object of the JSON line: identical for the GPU arm and the reference arm of the same invocation
+    (how the GPU arm ran -- launch mode, streams, gradient sync -- is in its `run` object)."""
+    import mmvae_b200.workloads as W
+    import torch
+    step_bytes = W.algorithmic_bytes(dict(cfg, B=B), torch.bfloat16 if args.dtype == "bf16" else torch.float32) * B
+    return {"workload": args.workload, "model": cfg["model"], "objective": cfg["obj"], "K": cfg["K"],
+            "latent_dim": cfg["D"], "batch_per_gpu": B, "global_batch": B * world,
+            "mods": [{"data_dim": list(m["data_dim"]), "ltype": m["ltype"]} for m in cfg["mods"]],
+            "dtype": "bf16" if args.dtype == "bf16" else "f32", "scaling": scaling,
+            "parallelism": "batch-sharded x%d, NCCL all-reduce of replicated grads" % world,
+            "l2": ("per-step working set %.0f MB: 256 MB L2 flush between steps, steps timed one by one" % (step_bytes / 1e6))
+                  if flush_needed(step_bytes) else
+                  ("per-step working set %.2f GB >> 126 MB L2, no flush" % (step_bytes / 1e9))}
+
+
+def cpu_sample_batch(args, cfg, B):
+    """Samples per step of the CPU arms: the workload's own batch (same configuration as the GPU arm) unless one step would
+    exceed the element budget; --cpu-batch overrides (explicit opt-in)."""
+    import mmvae_b200.workloads as W
+    if args.cpu_batch:
+        return args.cpu_batch
+    per_sample = W.algorithmic_bytes(dict(cfg, B=1)) / 4.0
+    return int(max(1, min(B, CPU_ELEMS_PER_STEP // per_sample)))
+
+
+def cpu_steps(cfg, t, n_warm, n_steps=None, budget_s=None):
+    from oracle import leafstep
+    for _ in range(n_warm):
+        leafstep.run(cfg, t)
+    n, t0 = 0, time.perf_counter()
+    while (n_steps is not None and n < n_steps) or \
+            (n_steps is None and (n < 3 or (time.perf_counter() - t0 < budget_s and n < 200))):
+        leafstep.run(cfg, t)
+        n += 1
+    return n, time.perf_counter() - t0
 
 
 def reference_arm(args, rank, world):
-    """The reference's algorithm for this path on the box's host cores: /root/reference (pure Python/torch, nothing
-    to compile) is absent on the GPU box, so this is the oracle port (oracle/refmath.py, pinned to the in-place
-    reference by oracle/validate_against_reference.py) with all host threads, on a bounded sample per step."""
+    """The reference's algorithm for this path on the box's host cores: /root/reference (pure Python/torch, nothing to
+    compile) is absent on the GPU box, so this is the oracle port (oracle/refmath.py, pinned to the in-place reference by
+    oracle/validate_against_reference.py) with all host threads.  Same workload, same batch per step as the GPU arm
+    (bounded by an element budget for the big sweep workloads; the sample is stated)."""
     if rank != 0:
         return
     import torch
+    import mmvae_b200.synthetic as syn
     import mmvae_b200.workloads as W
-    from oracle import leafstep
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg, t = W.make_leaves(args.workload, B=args.cpu_batch, seed=1234)
-    for _ in range(max(args.warmup, 1)):
-        leafstep.run(cfg, t)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        leafstep.run(cfg, t)
-    dt = time.perf_counter() - t0
-    val = args.cpu_batch * args.steps / dt
-    sample = "%d samples/step of %s (same shapes, K=%d), %d steps" % (args.cpu_batch, args.workload, cfg["K"], args.steps)
-    line = {"metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": args.workload, "model": cfg["model"], "objective": cfg["obj"], "K": cfg["K"],
-                       "batch_per_step": args.cpu_batch},
+    B, scaling = local_batch(args, syn.WORKLOADS[args.workload]["B"], world)
+    Bc = cpu_sample_batch(args, syn.WORKLOADS[args.workload], B)
+    cfg, t = W.make_leaves(args.workload, B=Bc, seed=1234)
+    n, dt = cpu_steps(cfg, t, 1, n_steps=args.steps)
+    val = Bc * n / dt
+    sample = "%d of %d samples per step of %s (same shapes, K=%d), %d steps, %.1f s" % (Bc, B, args.workload, cfg["K"], n, dt)
+    line = {"metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": n,
+            "warmup": 1, "ms_per_step": 1e3 * dt / n, "higher_is_better": True,
+            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": config_dict(args, cfg, B, world, scaling),
             "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
 
 
-def cpu_baseline(args):
+def cpu_baseline(args, cfg_full, B):
     import torch
     import mmvae_b200.workloads as W
-    from oracle import leafstep
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg, t = W.make_leaves(args.workload, B=args.cpu_batch, seed=1234)
-    leafstep.run(cfg, t)
-    n, t0 = 0, time.perf_counter()
-    while n < 3 or (time.perf_counter() - t0 < 10 and n < 200):
-        leafstep.run(cfg, t)
-        n += 1
-    dt = time.perf_counter() - t0
-    return {"value": args.cpu_batch * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": "%d samples/step of %s (same shapes, K=%d), %d steps, %.1f s" % (
-                args.cpu_batch, args.workload, cfg["K"], n, dt)}
+    Bc = cpu_sample_batch(args, cfg_full, B)
+    cfg, t = W.make_leaves(args.workload, B=Bc, seed=1234)
+    n, dt = cpu_steps(cfg, t, 1, budget_s=10.0)
+    return {"value": Bc * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": "%d of %d samples per step of %s (same shapes, K=%d), %d steps, %.1f s" % (
+                Bc, B, args.workload, cfg["K"], n, dt)}
 
 
-def plugin_e2e(cfg, B, dev, steps, fused_tail=False, graphed=False):
-    import torch
-    import mmvae_b200
-    import mmvae_b200.synthetic as syn
-    g = syn.gen(4321)
-    vaes, host = {}, {}
-    pv = cfg.get("private")
-    for i, m in enumerate(cfg["mods"]):
-        name = "mod_%d" % (i + 1)
-        dz = cfg["D"] + (pv or 0)
-        enc = syn.LinearEncoder(m["data_dim"], dz)
-        dec = syn.LinearDecoder(dz, m["data_dim"], squash=(m["ltype"] == "bce"), returns_logits=fused_tail)
-        vaes[name] = syn.StubVAE(enc, dec, cfg["D"], m["ltype"], private_latents=pv, llik_scaling=m["lam"],
-                                 prior_dist=m["dist"], id_name=name)
-        host[name] = syn.make_target(g, m["target"], B, m["data_dim"]).pin_memory()
-    model = mmvae_b200.MODEL_REGISTRY[cfg["model"]](vaes, cfg["D"], {"obj": cfg["obj"], "beta": 1.0, "K": cfg["K"]}, None).to(dev)
-    params = [p for p in model.parameters() if p.requires_grad]
+class PluginStep:
+    """The call a user of the reference makes: model.objective(batch) + backward through the drop-in plugin, batch from
+    pinned host memory, replicated-parameter gradients all-reduced (SUM) at N>1, loss read back."""
 
-    gobj = None
-    if graphed:  # the whole plugin step (encoders, kernels, decoders, backward) as ONE captured graph
-        gobj = mmvae_b200.GraphedObjective(
-            model, {k: {"data": v.to(dev), "masks": None, "categorical": False} for k, v in host.items()})
+    def __init__(self, cfg, B, dev, group, world, rank, fused_tail, graphed):
+        import torch
+        import mmvae_b200
+        import mmvae_b200.parallel as par
+        import mmvae_b200.synthetic as syn
+        self.torch = torch
+        torch.manual_seed(99)  # identical replicated parameters on every rank
+        g = syn.gen(4321 + rank)
+        vaes, self.host = {}, {}
+        pv = cfg.get("private")
+        for i, m in enumerate(cfg["mods"]):
+            name = "mod_%d" % (i + 1)
+            dz = cfg["D"] + (pv or 0)
+            enc = syn.LinearEncoder(m["data_dim"], dz)
+            dec = syn.LinearDecoder(dz, m["data_dim"], squash=(m["ltype"] == "bce"), returns_logits=fused_tail)
+            vaes[name] = syn.StubVAE(enc, dec, cfg["D"], m["ltype"], private_latents=pv, llik_scaling=m["lam"],
+                                     prior_dist=m["dist"], id_name=name)
+            self.host[name] = syn.make_target(g, m["target"], B, m["data_dim"]).pin_memory()
+        self.model = mmvae_b200.MODEL_REGISTRY[cfg["model"]](
+            vaes, cfg["D"], {"obj": cfg["obj"], "beta": 1.0, "K": cfg["K"]}, None).to(dev)
+        self.params = [p for p in self.model.parameters() if p.requires_grad]
+        self.dev, self.B, self.world = dev, B, world
+        self.sync = None
+        if world > 1:
+            par.attach(self.model, group, B * world)
+            self.sync = par.GradSync(self.params, group)
+        self.gobj = None
+        if graphed:  # the whole plugin step (encoders, kernels, decoders, backward) as ONE captured graph
+            self.gobj = mmvae_b200.GraphedObjective(
+                self.model, {k: {"data": v.to(dev), "masks": None, "categorical": False} for k, v in self.host.items()})
+        self.h2d = sum(v.numel() * v.element_size() for v in self.host.values())
+        self.api = "mmvae_b200.%s(vaes, ...).objective(batch) + backward, linear stand-in encoders/decoders (torch), %s%s%s" % (
+            cfg["model"], "mmvae_b200.GraphedObjective (one CUDA-graph replay per step)" if graphed else "eager launches",
+            "; decoder tail sigmoid+clamp fused into the likelihood kernel (bce_logits)" if fused_tail else "",
+            "; flat-bucket NCCL all-reduce(SUM) of the parameter gradients" if world > 1 else "")
 
-    def step():
-        batch = {k: {"data": v.to(dev, non_blocking=True), "masks": None, "categorical": False} for k, v in host.items()}
-        if gobj is not None:
-            return float(gobj.step(batch)["loss"].detach())
-        for p in params:
-            p.grad = None
-        loss = model.objective(batch)["loss"]
-        loss.backward()
-        return float(loss.detach())
+    def step(self):
+        dev = self.dev
+        batch = {k: {"data": v.to(dev, non_blocking=True), "masks": None, "categorical": False} for k, v in self.host.items()}
+        if self.gobj is not None:
+            loss = self.gobj.step(batch)["loss"]
+        else:
+            for p in self.params:
+                p.grad = None
+            loss = self.model.objective(batch)["loss"]
+            loss.backward()
+        if self.sync is not None:
+            self.sync.sync()
+        return float(loss.detach())  # device -> host read of the step's result
 
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(steps):
-        step()
-    b.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b)
-    return {"value": B * steps / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms / steps, "steps": steps,
-            "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()), "d2h_bytes_per_step": 4,
-            "api": "mmvae_b200.%s(vaes, ...).objective(batch) + backward, linear stand-in encoders/decoders (torch), "
-                   "%s%s" % (cfg["model"], "mmvae_b200.GraphedObjective (one CUDA-graph replay per step)" if graphed
-                             else "eager launches", "; decoder tail sigmoid+clamp fused into the likelihood kernel "
-                             "(bce_logits)" if fused_tail else "")}
+    def close(self):
+        if self.gobj is not None:
+            self.gobj.close()
 
 
 _REAL_STDOUT = None
@@ -287,6 +356,8 @@ def main():
     import torch
     import torch.distributed as dist
     import mmvae_b200._lib as L
+    import mmvae_b200.parallel as par
+    import mmvae_b200.synthetic as syn
     import mmvae_b200.workloads as W
 
     if not torch.cuda.is_available():
@@ -303,8 +374,8 @@ def main():
         group = dist.group.WORLD
     L.load()
     rdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-    cfg, t = W.make_leaves(args.workload, B=args.batch, seed=1234 + rank, recon_dtype=rdt)
-    B = cfg["B"]
+    B, scaling = local_batch(args, syn.WORKLOADS[args.workload]["B"], world)
+    cfg, t = W.make_leaves(args.workload, B=B, seed=1234 + rank, recon_dtype=rdt)
     # the only replicated parameter on this leaf protocol is the prior logit vector: all-reduce(SUM) its gradient.
     # Default: inside the step (parallel.GradSync hook -> side stream, overlapped with the likelihood backward and
     # captured in the step graph); --eager-sync: one eager NCCL call after the step.
@@ -324,7 +395,7 @@ def main():
     step.run()
     launches_per_step = L.launch_count - c0
     runner = step
-    # forward collectives (DReG (M,K) batch sums, optimal_sigma scalar) are issued on the current stream and are
+    # forward collectives (DReG (M,K) batch sums, optimal_sigma sum + count) are issued on the current stream and are
     # captured in the step graph like the gradient all-reduce
     if not args.no_graph:
         runner = W.GraphedStep(step)
@@ -334,49 +405,72 @@ def main():
                      "backward%s" % (", captured in the step graph" if runner is not step else "")) \
             if step.sync is not None else "eager all-reduce after the step"
 
-    def timed(nsteps, fn):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(nsteps):
-            fn()
-        b.record()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ms = torch.tensor([a.elapsed_time(b)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms)
-
     def one():
         runner.run()
         sync_grads()
 
+    def allmax(x):
+        v = torch.tensor([float(x)], device=dev)
+        if world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v)
+
+    def timed(nsteps, fn, flush=None):
+        """Device time of nsteps back-to-back steps (one event pair), or -- with an L2 flush between the steps -- the sum
+        of per-step event pairs; barrier + synchronize on both sides, MAX over ranks."""
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if flush is None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(nsteps):
+                fn()
+            b.record()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b)
+        else:
+            evs = []
+            for _ in range(nsteps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                evs.append((a, b))
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ms = sum(a.elapsed_time(b) for a, b in evs)
+        return allmax(ms)
+
+    step_bytes = W.algorithmic_bytes(cfg, rdt) * B
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush_needed(step_bytes) else None
     for _ in range(W_):
         one()
+    est_ms = timed(3, one, flush) / 3.0
+    reps = max(1, int(math.ceil(MIN_TIMED_S * 1e3 / max(est_ms, 1e-3) / K_)))
+    if flush is not None:
+        reps = min(reps, max(1, 400 // K_))  # every flushed step costs a 256 MB write as well
+    K_eff = K_ * reps
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    t_load = time.perf_counter()
-    ms = timed(K_, one)
-    # the timed region is only a few milliseconds: keep the identical load running so that the clock / throttle record
-    # covers a representative stretch under load (not timed, not counted)
-    # (the iteration count comes from the all-reduced step time, so every rank runs the same number of collectives)
-    n_extra = int(min(max(0.3 - (time.perf_counter() - t_load), 0.0) if world == 1 else 0.3, 0.3) / (ms / K_ * 1e-3)) + 1
-    for _ in range(n_extra):
-        one()
+    ms = timed(K_eff, one, flush)
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
-    value = B * world * K_ / (ms / 1e3)
+    value = B * world * K_eff / (ms / 1e3)
 
     # roofline of the dominant kernel: CUDA events around every launch of it, eager steps, same inputs
     dom = "mmvae_loglik_rowreduce_bwd" if cfg["obj"] != "elbo" else "mmvae_loglik_rowreduce_fused"
+    if all(m["ltype"] == "optimal_sigma" for m in cfg["mods"]):
+        dom = "mmvae_osigma_bwd"
     if cfg.get("latent_only"):
-        dom = "mmvae_moe_logdens_fwd"
-    kt = KernelTimer([dom, "mmvae_loglik_rowreduce_fwd", "mmvae_moe_logdens_bwd_rk"])
+        dom = "mmvae_moe_logdens_bwd_rk"
+    names = [dom, "mmvae_loglik_rowreduce_fwd", "mmvae_moe_logdens_fwd", "mmvae_moe_logdens_bwd_rk", "mmvae_osigma_fwd"]
+    kt = KernelTimer(names)
     L.timer = kt
     step.streams = 1  # per-kernel durations: one kernel at a time (the step itself runs two streaming kernels at once)
     for _ in range(min(K_, 10)):
@@ -384,38 +478,34 @@ def main():
     torch.cuda.synchronize()
     step.streams = args.streams
     L.timer = None
-    tms, dom_bytes = kt.biggest(dom)  # launches of the largest likelihood term, bytes from the actual arguments
-    tms = tms[len(tms) // 5:] if len(tms) >= 5 else tms
+    tms, dom_bytes = kt.biggest(dom)  # launches of the largest term, bytes from the actual arguments
     peak, peak_src = measured_peak()
     ach = dom_bytes / (statistics.mean(tms) * 1e-3) / 1e9 if tms else None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(dom)
+            traffic = json.load(open(tp)).get(dom if args.workload == DEFAULT_WORKLOAD and B == 256 else "")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": (ach / peak) if ach else None, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_launch": dom_bytes, "avg_ms": statistics.mean(tms) if tms else None,
                 "launches_timed": len(tms)}
-    fms, fb = kt.biggest("mmvae_loglik_rowreduce_fwd")
-    fms = fms[len(fms) // 5:] if len(fms) >= 5 else fms
-    if fms:
-        roofline["fwd_kernel"] = {"achieved": fb / (statistics.mean(fms) * 1e-3) / 1e9, "bytes_per_launch": fb,
-                                  "avg_ms": statistics.mean(fms)}
-    bms, bb = kt.biggest("mmvae_moe_logdens_bwd_rk")
-    bms = bms[len(bms) // 5:] if len(bms) >= 5 else bms
-    if bms and cfg.get("latent_only"):
-        roofline["moe_bwd_kernel"] = {"achieved": bb / (statistics.mean(bms) * 1e-3) / 1e9, "bytes_per_launch": bb,
-                                      "avg_ms": statistics.mean(bms)}
-    step_bytes = W.algorithmic_bytes(cfg, rdt) * B
-    roofline["step"] = {"algorithmic_bytes": step_bytes, "achieved": step_bytes * K_ / (ms * 1e-3) / 1e9,
-                        "frac": step_bytes * K_ / (ms * 1e-3) / 1e9 / peak}
+    for key, nm in (("fwd_kernel", "mmvae_loglik_rowreduce_fwd"), ("moe_fwd_kernel", "mmvae_moe_logdens_fwd"),
+                    ("moe_bwd_kernel", "mmvae_moe_logdens_bwd_rk"), ("osigma_fwd_kernel", "mmvae_osigma_fwd")):
+        kms, kb = kt.biggest(nm)
+        if kms and nm != dom:
+            roofline[key] = {"achieved": kb / (statistics.mean(kms) * 1e-3) / 1e9, "bytes_per_launch": kb,
+                             "avg_ms": statistics.mean(kms)}
+    roofline["step"] = {"algorithmic_bytes": step_bytes, "achieved": step_bytes * K_eff / (ms * 1e-3) / 1e9,
+                        "frac": step_bytes * K_eff / (ms * 1e-3) / 1e9 / peak}
 
-    # end to end: every input of the step lives in pinned host memory; H2D + loss read-back inside the timed region
-    e2e = None
+    # ---- end to end --------------------------------------------------------------------------------------------
+    e2e = e2e_leaf = e2e_variants = None
+    ke = max(3, min(K_, 10))
     if not args.no_e2e:
+        # (a) leaf protocol: every input of the step lives in pinned host memory; H2D + loss read-back in the timed region
         pairs = [(step.mu, t["mu"]), (step.s, t["s"]), (step.pz_logits, t["pz_logits"])]
         pairs += list(zip(step.targets, t["targets"])) + list(zip(step.recon, t["recon"]))
         if cfg["model"] == "moe":
@@ -440,48 +530,70 @@ def main():
 
         for _ in range(3):
             e2e_step()
-        ke = max(3, min(K_, 10))
         ems = timed(ke, e2e_step)
-        e2e = {"value": B * world * ke / (ems / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": 4, "ms_per_step": ems / ke, "steps": ke,
-               "api": "mmvae_b200.workloads.LeafStep / GraphedStep (C-ABI kernels), pinned host inputs"}
+        e2e_leaf = {"value": B * world * ke / (ems / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ems / ke, "steps": ke,
+                    "api": "mmvae_b200.workloads.LeafStep / GraphedStep (C-ABI kernels), every leaf from pinned host memory"}
+        del pairs
+        # (b) plugin level: the call a user of the reference makes, batch from pinned host memory
+        if not cfg.get("latent_only"):
+            e2e_variants = {}
+            fused = any(m["ltype"] == "bce" for m in cfg["mods"])
+            for key, kw in (("graphed", dict(fused_tail=fused, graphed=True)), ("eager", dict(fused_tail=False, graphed=False))):
+                if key == "eager" and world > 1:
+                    continue
+                try:
+                    ps = PluginStep(cfg, B, dev, group, world, rank, **kw)
+                    for _ in range(3):
+                        ps.step()
+                    pms = timed(ke, ps.step)
+                    e2e_variants[key] = {"value": B * world * ke / (pms / 1e3), "unit": "samples/s",
+                                         "h2d_bytes_per_step": ps.h2d, "d2h_bytes_per_step": 4, "ms_per_step": pms / ke,
+                                         "steps": ke, "api": ps.api}
+                    ps.close()
+                    del ps
+                except Exception as ex:  # never let an extra leg hide the main numbers
+                    e2e_variants[key] = {"error": repr(ex)[:300]}
+            if "value" in e2e_variants.get("graphed", {}):
+                e2e = e2e_variants.pop("graphed")
+        if e2e is None:
+            e2e = e2e_leaf
 
-    # plugin level: the call a user of the reference makes -- model.objective(batch) + backward -- with stand-in
-    # linear encoders/decoders (reference ones are dense nets outside this path); batch from pinned host memory
-    e2e_plugin = None
-    if not args.no_e2e and world == 1:
-        try:
-            e2e_plugin = plugin_e2e(cfg, B, dev, max(3, min(K_, 10)))
-            if any(m["ltype"] == "bce" for m in cfg["mods"]):
-                e2e_plugin["fused_decoder_tail"] = plugin_e2e(cfg, B, dev, max(3, min(K_, 10)), fused_tail=True)
+    # ---- multi-GPU numerical parity (outside the timed region) --------------------------------------------------
+    parity_n = None
+    if world > 1 and not args.no_parity:
+        # the benchmarked step's own ingredients on a small global batch that does NOT divide evenly: sharded (graph
+        # captured, in-step gradient all-reduce, forward collectives) vs the full batch on one GPU
+        per = {}
+        for name in dict.fromkeys([args.workload, "c2_moe_iwae_cdsprites_l5", "c4_moe_dreg_mnistsvhn",
+                                   "c3_mopoe_elbo_vilanro"]):
             try:
-                e2e_plugin["graphed"] = plugin_e2e(cfg, B, dev, max(3, min(K_, 10)), graphed=True,
-                                                   fused_tail=any(m["ltype"] == "bce" for m in cfg["mods"]))
+                per[name] = allmax(par.sharded_parity(name, 4 * world + 1, group, dev))
             except Exception as ex:
-                e2e_plugin["graphed"] = {"error": repr(ex)[:200]}
-        except Exception as ex:  # never let the extra leg hide the main numbers
-            e2e_plugin = {"error": repr(ex)[:200]}
+                per[name] = repr(ex)[:200]
+        nums = [v for v in per.values() if isinstance(v, float)]
+        parity_n = {"max_rel": max(nums) if nums else None, "per_workload": per, "global_batch": 4 * world + 1,
+                    "what": "sharded (CUDA graph, in-step NCCL) vs full batch on one GPU: summed loss, all-reduced prior "
+                            "gradient, shard rows of d/dmu, d/ds, d/drecon[0]; max relative deviation over ranks"}
 
-    line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K_, "warmup": W_,
-            "ms_per_step": ms / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    conf = config_dict(args, cfg, B, world, scaling)
+    run = {"grad_sync": sync_mode, "launch_mode": "cuda-graph" if runner is not step else "eager",
+           "streams": "3 (likelihood terms alternate between two streams, latent kernels on a third; "
+                      "forks/joins captured in the graph)" if step.streams == 3 else "single stream"}
+    line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K_, "timed_steps": K_eff,
+            "warmup": W_, "ms_per_step": ms / K_eff, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "bf16" if rdt == torch.bfloat16 else "f32", "data": "synthetic", "impl": "ours",
-            "config": {"workload": args.workload, "model": cfg["model"], "objective": cfg["obj"], "K": cfg["K"],
-                       "latent_dim": cfg["D"], "batch_per_gpu": B, "global_batch": B * world,
-                       "mods": [{"data_dim": list(m["data_dim"]), "ltype": m["ltype"]} for m in cfg["mods"]],
-                       "parallelism": "batch-sharded x%d, NCCL all-reduce of replicated grads" % world,
-                       "grad_sync": sync_mode,
-                       "l2": "per-step working set %.2f GB >> 126 MB L2, no flush" % (step_bytes / 1e9),
-                       "launch_mode": "cuda-graph" if runner is not step else "eager",
-                       "streams": "3 (likelihood terms alternate between two streams, latent kernels on a third; "
-                                  "forks/joins captured in the graph)" if step.streams == 3 else "single stream"},
-            "roofline": roofline, "gpu_launches": launches_per_step * K_, "launches_per_step": launches_per_step,
-            "clocks": clocks}
+            "config": conf, "run": run, "roofline": roofline, "gpu_launches": launches_per_step * K_eff,
+            "launches_per_step": launches_per_step, "clocks": clocks}
     if e2e is not None:
         line["e2e"] = e2e
-    if e2e_plugin is not None:
-        line["e2e_plugin"] = e2e_plugin
+        line["e2e_leaf"] = e2e_leaf
+        if e2e_variants:
+            line["e2e_plugin_variants"] = e2e_variants
+    if parity_n is not None:
+        line["parity_n"] = parity_n
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args)
+        line["cpu_baseline"] = cpu_baseline(args, syn.WORKLOADS[args.workload], B)
     if rank == 0:
         emit(line)
     if world > 1:

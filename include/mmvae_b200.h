@@ -46,7 +46,10 @@ enum { MMVAE_NORMAL = 0, MMVAE_LAPLACE = 1 };
 enum { MMVAE_LT_BCE = 0, MMVAE_LT_LPROB_NORMAL = 1, MMVAE_LT_LPROB_LAPLACE = 2, MMVAE_LT_MSE = 3, MMVAE_LT_L1 = 4,
        /* BCE on decoder LOGITS with the reference decoder tail fused in (decoders.py:96-97):
           x = clamp(sigmoid(y), 1e-6, 1-1e-6); saves one read+write of the (K*B, P) reconstruction per direction */
-       MMVAE_LT_BCE_LOGITS = 5 };
+       MMVAE_LT_BCE_LOGITS = 5,
+       /* lprob with padding masks: the reference overwrites the likelihood's scale with its (cropped) loc
+          (objectives.py:43-45), i.e. log_prob of Normal / Laplace(loc = x, scale = x); NaN (x < 0) -> 0.  Reproduced. */
+       MMVAE_LT_LPROB_NORMAL_SELF = 6, MMVAE_LT_LPROB_LAPLACE_SELF = 7 };
 
 #define MMVAE_MAX_MODS 8    /* modalities per model                       */
 #define MMVAE_MAX_COLS 256  /* latent columns per modality (shared+private) */
@@ -112,7 +115,9 @@ MMVAE_API int mmvae_catce_rows(int mode, const void* recon, int64_t ld_recon, in
  * optimal_sigma (sigma-VAE) rows: replaces ReconLoss.optimal_sigma (objectives.py:502-509) + utils.softclip
  * (utils.py:66-69).  Three stream-ordered stages so that a multi-GPU caller can all-reduce the scalar between
  * stage 1 and 2:
- *   _sumsq : sumsq[0] += sum_all (t - x)^2      (double accumulator, caller zeroes it)
+ *   _sumsq : sumsq[0] += sum_all (t - x)^2, sumsq[1] += rows*P   (TWO doubles, caller zeroes them; a sharded caller
+ *            all-reduces both in one collective).  _fwd / _bwd take the element count from n_total, or from sumsq[1]
+ *            when n_total <= 0 (device-resident global count: uneven shards).
  *   _fwd   : log_sigma = -6 + softplus(log sqrt(sumsq/n_total) + 6);
  *            out_rows[r] = -lam * sum_p [ ((t-x)/sigma)^2 + log_sigma + 0.5 log 2pi ]; stats = {log_sigma, dlogsigma/du}
  *   _bwd   : only log_sigma carries gradient (the squared term is detached):

@@ -14,6 +14,7 @@ c_i, c_i64, c_f, c_d, c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes
 F32, BF16 = 0, 1
 NORMAL, LAPLACE = 0, 1
 LT_BCE, LT_LPROB_NORMAL, LT_LPROB_LAPLACE, LT_MSE, LT_L1, LT_BCE_LOGITS = 0, 1, 2, 3, 4, 5
+LT_LPROB_NORMAL_SELF, LT_LPROB_LAPLACE_SELF = 6, 7
 DRAW_PRIOR, DRAW_DIRECT, DRAW_LAPLACE, DRAW_ROWMASK = 1, 2, 4, 8
 MAX_MODS, MAX_COLS, MAX_DRAWS, DREG_MAX_SPLIT = 8, 256, 64, 64
 

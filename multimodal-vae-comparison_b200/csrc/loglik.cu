@@ -143,6 +143,30 @@ struct LogP {
             const bool bad = (lp != lp);
             if (NEED_V) v = bad ? 0.f : lp;
             if (NEED_D) d = bad ? 0.f : (df > 0.f ? c_inv : (df < 0.f ? -c_inv : 0.f));
+        } else if (LT == MMVAE_LT_LPROB_NORMAL_SELF) {
+            // reference quirk (objectives.py:43-45): with padding masks recon_loss_fn overwrites the likelihood's SCALE
+            // with its (cropped) loc, so lprob evaluates Normal(loc = x, scale = x).log_prob(t).  log(x) of a negative
+            // mean is NaN -> the value is zeroed (:423); the gradient of a zeroed entry is autograd's 0 * (finite local
+            // derivative) = 0 (NaN only where the local derivative itself is not finite, x == 0).
+            const float ix = 1.0f / x, u = (t - x) * ix;
+            const float lp = -0.5f * u * u - logf(x) - 0.91893853320467274178f;
+            const bool bad = (lp != lp);
+            if (NEED_V) v = bad ? 0.f : lp;
+            if (NEED_D) {
+                const float dl = (u * t * ix - 1.0f) * ix;  // d/dloc + d/dscale = (t-x) t / x^3 - 1/x
+                d = bad ? 0.f * dl : dl;
+            }
+        } else if (LT == MMVAE_LT_LPROB_LAPLACE_SELF) {
+            // Laplace(loc = x, scale = x).log_prob(t) = -log(2x) - |t-x|/x (same quirk)
+            const float ix = 1.0f / x, df = t - x;
+            const float lp = -logf(2.0f * x) - fabsf(df) * ix;
+            const bool bad = (lp != lp);
+            if (NEED_V) v = bad ? 0.f : lp;
+            if (NEED_D) {
+                const float sg = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
+                const float dl = (sg - 1.0f + fabsf(df) * ix) * ix;  // sgn(t-x)/x - 1/x + |t-x|/x^2
+                d = bad ? 0.f * dl : dl;
+            }
         } else if (LT == MMVAE_LT_MSE) {
             const float df = t - x;
             if (NEED_V) v = -df * df;
@@ -383,6 +407,8 @@ static int launch2(const LoglikParams& p, int ltype, bool vect, cudaStream_t st)
         case MMVAE_LT_MSE: return launch3<TX, TT, MMVAE_LT_MSE, MODE>(p, vect, st);
         case MMVAE_LT_L1: return launch3<TX, TT, MMVAE_LT_L1, MODE>(p, vect, st);
         case MMVAE_LT_BCE_LOGITS: return launch3<TX, TT, MMVAE_LT_BCE_LOGITS, MODE>(p, vect, st);
+        case MMVAE_LT_LPROB_NORMAL_SELF: return launch3<TX, TT, MMVAE_LT_LPROB_NORMAL_SELF, MODE>(p, vect, st);
+        case MMVAE_LT_LPROB_LAPLACE_SELF: return launch3<TX, TT, MMVAE_LT_LPROB_LAPLACE_SELF, MODE>(p, vect, st);
         default: return MMVAE_E_ENUM;
     }
 }

@@ -23,7 +23,12 @@ __global__ void __launch_bounds__(256) osigma_sumsq_kernel(const TX* __restrict_
         acc += (double)part;
     }
     const double tot = block_sum(acc, red);
-    if (threadIdx.x == 0) atomicAdd(sumsq, tot);
+    if (threadIdx.x == 0) {
+        atomicAdd(sumsq, tot);
+        // element count of this call next to the sum, so that a batch-sharded caller all-reduces both in ONE collective
+        // and uneven shards still get the global mean (n_total was rows*P*world, wrong for B % world != 0)
+        if (blockIdx.x == 0) atomicAdd(sumsq + 1, (double)rows * (double)P);
+    }
 }
 
 __device__ __forceinline__ void osigma_stats(double sumsq, double n_total, float& log_sigma, float& dsoft) {
@@ -42,7 +47,7 @@ __global__ void __launch_bounds__(256) osigma_rows_kernel(const TX* __restrict__
                                                           double n_total, float* out_rows, float* stats2) {
     __shared__ float red[32];
     float log_sigma, dsoft;
-    osigma_stats(*sumsq, n_total, log_sigma, dsoft);
+    osigma_stats(*sumsq, n_total > 0 ? n_total : sumsq[1], log_sigma, dsoft);
     const float inv_sigma = expf(-log_sigma);
     const float cst = log_sigma + 0.91893853320467274178f;  // + 0.5 log(2 pi)
     if (blockIdx.x == 0 && threadIdx.x == 0 && stats2) {
@@ -78,7 +83,7 @@ __global__ void __launch_bounds__(256) osigma_bwd_kernel(const TX* __restrict__ 
                                                          int64_t ldg) {
     float log_sigma, dsoft;
     const double ss = *sumsq;
-    osigma_stats(ss, n_total, log_sigma, dsoft);
+    osigma_stats(ss, n_total > 0 ? n_total : sumsq[1], log_sigma, dsoft);
     // d(sum_r w_r * row_r)/dx_i = -lam * P * wsum * dlog_sigma/dx_i,  dlog_sigma/dx_i = dsoft * (x_i - t_i) / sumsq
     const float coef = (float)(-(double)lam * (double)P * (double)(*wsum) * (double)dsoft / ss);
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
@@ -125,7 +130,7 @@ extern "C" int mmvae_osigma_fwd(const void* recon, int64_t ld_recon, int dtype_r
                                 const double* sumsq, double n_total, float* out_rows, float* stats2, void* workspace,
                                 void* stream) {
     (void)workspace;
-    if (!recon || !target || !sumsq || !out_rows || rows <= 0 || B <= 0 || P <= 0 || n_total <= 0) return MMVAE_E_ARG;
+    if (!recon || !target || !sumsq || !out_rows || rows <= 0 || B <= 0 || P <= 0) return MMVAE_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(TX, TT)                                                                                              \
     osigma_rows_kernel<TX, TT><<<rows_grid(rows), 256, 0, st>>>((const TX*)recon, ld_recon, (const TT*)target,    \

@@ -21,11 +21,19 @@ from typing import Dict
 import torch
 
 
+def _as_static(v):
+    """Batch entries the graph must see through static buffers: tensors, and the reference's list-of-tensors form of
+    ``data`` (objectives._prep stacks it) -- stacked once here so that replays see fresh values."""
+    if isinstance(v, (list, tuple)) and len(v) and all(torch.is_tensor(x) for x in v):
+        return torch.stack(list(v))
+    return v
+
+
 def _signature(batch: Dict[str, dict]):
     sig = []
     for mod in sorted(batch):
         for k in sorted(batch[mod]):
-            v = batch[mod][k]
+            v = _as_static(batch[mod][k])
             sig.append((mod, k, (tuple(v.shape), v.dtype) if torch.is_tensor(v) else v))
     return tuple(sig)
 
@@ -37,8 +45,8 @@ class GraphedObjective:
             raise RuntimeError("GraphedObjective needs a model on a CUDA device (there is no CPU path)")
         self.model, self.backward = model, backward
         self.signature = _signature(batch)
-        self.static = {mod: {k: (v.detach().to(dev).clone() if torch.is_tensor(v) else v) for k, v in entry.items()}
-                       for mod, entry in batch.items()}
+        self.static = {mod: {k: (_as_static(v).detach().to(dev).clone() if torch.is_tensor(_as_static(v)) else v)
+                             for k, v in entry.items()} for mod, entry in batch.items()}
         self.params = [p for p in model.parameters() if p.requires_grad]
         self._one = None
         if backward:
@@ -72,6 +80,7 @@ class GraphedObjective:
                                "capture a new graph for it")
         for mod, entry in batch.items():
             for k, v in entry.items():
+                v = _as_static(v)
                 if torch.is_tensor(v):
                     self.static[mod][k].copy_(v, non_blocking=True)
         self.graph.replay()
@@ -84,3 +93,7 @@ class GraphedObjective:
         if self.graph is not None:
             self.graph.reset()
             self.graph = None
+        if self._one is not None:
+            from . import ops
+            ops.unmark_unit_grad(self._one)  # the registry would keep it (and its address) alive forever otherwise
+            self._one = None

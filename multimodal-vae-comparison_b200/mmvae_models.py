@@ -125,6 +125,11 @@ class MOE(TorchMMVAE):
         self._require_all(data)
         names = list(self.vaes.keys())
         M, K, beta = len(names), self.K, self.obj_fn.beta
+        if M > 2:
+            # reference MOE.forward keeps ONE cross reconstruction per target (cross_px_zs[target] is overwritten by every
+            # source, mmvae_models.py:112-116) and its objective mis-shapes for M = 3: only M <= 2 is defined
+            raise ValueError("MOE.objective is only defined for at most two modalities (the reference's cross-modal "
+                             "bookkeeping, mmvae_models.py:112-116, breaks for M >= 3); got %d" % M)
         enc = self.encode(data)
         obj = self.obj_fn.obj_name
         if obj == "elbo":

@@ -12,7 +12,7 @@ import torch
 
 from . import ops
 
-ELEMENTWISE = ("bce", "lprob", "mse", "l1", "bce_logits")
+ELEMENTWISE = ("bce", "lprob", "mse", "l1", "bce_logits", "lprob_selfscale")
 
 
 class ReconLoss:
@@ -109,22 +109,32 @@ class BaseObjective:
             loc = loc.reshape(rows, *data.shape[1:])
         return loc, data
 
+    @staticmethod
+    def _masked_ltype(ltype, target, loc=None):
+        """Reference quirk, reproduced: with padding masks recon_loss_fn overwrites the likelihood's scale with its
+        cropped loc (objectives.py:43-45) -- only ``lprob`` reads the scale, and then evaluates dist(loc, loc).  If the
+        crop really shortens the decoder output the reference raises: the distribution object keeps the batch_shape it
+        was built with and torch's _validate_sample rejects the (shorter) target."""
+        if ltype == "lprob" and target.get("masks") is not None:
+            if loc is not None and loc.dim() > 1 and loc.shape[1] != target["masks"].shape[1]:
+                raise ValueError("Value is not broadcastable with batch_shape+event_shape: lprob with padding masks "
+                                 "shorter than the decoder output raises in the reference as well (objectives.py:43-45, "
+                                 "torch distribution.py _validate_sample)")
+            return "lprob_selfscale"
+        return ltype
+
     def lpx_rows(self, px_z, target, lam=1.0, ltype=None, family=None, out=None):
         """(recon_loss_fn(px_z, target, K) * lam).sum(-1) of the reference -> (K*B,) rows, k-major.
         out: optional contiguous (K*B,) fp32 slice the kernel writes into (a row of a stacked buffer)."""
-        ltype = ltype or self.ltype
-        if ltype == "lprob" and target.get("masks") is not None:
-            raise NotImplementedError("lprob with padding masks (reference overwrites scale with loc, objectives.py:45)")
         loc, family = _loc_family(px_z, family)
+        ltype = self._masked_ltype(ltype or self.ltype, target, loc)
         loc, data = self._prep(loc, target)
         return ReconLoss._rows(ltype, loc, data, float(lam), family, self.group, out)
 
     def lpx_weighted_sum(self, px_z, target, lam=1.0, w_rows=None, w_const=1.0, ltype=None, family=None):
         """S = sum_r w_r * rows[r] (+ rows for logging) with the gradient produced in the same pass."""
-        ltype = ltype or self.ltype
-        if ltype == "lprob" and target.get("masks") is not None:
-            raise NotImplementedError("lprob with padding masks (reference overwrites scale with loc, objectives.py:45)")
         loc, family = _loc_family(px_z, family)
+        ltype = self._masked_ltype(ltype or self.ltype, target, loc)
         loc, data = self._prep(loc, target)
         if ltype in ELEMENTWISE:
             return ops.loglik_weighted_sum(loc, data, ltype, family, float(lam), w_rows=w_rows, w_const=w_const)

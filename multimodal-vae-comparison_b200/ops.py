@@ -28,6 +28,11 @@ def mark_unit_grad(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def unmark_unit_grad(t: torch.Tensor) -> None:
+    """Drop a tensor registered with mark_unit_grad (its owner is going away)."""
+    _UNIT_GRADS.pop(t.data_ptr(), None)
+
+
 def _is_unit(g: Optional[torch.Tensor]) -> bool:
     return g is not None and g.numel() == 1 and g.data_ptr() in _UNIT_GRADS
 
@@ -100,6 +105,8 @@ LTYPES = {"bce": _lib.LT_BCE, "mse": _lib.LT_MSE, "l1": _lib.LT_L1, "bce_logits"
 def ltype_code(ltype: str, likelihood: str) -> int:
     if ltype == "lprob":
         return _lib.LT_LPROB_LAPLACE if likelihood == "laplace" else _lib.LT_LPROB_NORMAL
+    if ltype == "lprob_selfscale":  # lprob with padding masks: scale := loc (reference objectives.py:43-45)
+        return _lib.LT_LPROB_LAPLACE_SELF if likelihood == "laplace" else _lib.LT_LPROB_NORMAL_SELF
     return LTYPES[ltype]
 
 
@@ -311,13 +318,12 @@ class _OsigmaRows(torch.autograd.Function):
         t, Pt, ldt = _rows2d(target.detach(), B)
         if Pt != P or rows % B != 0:
             raise RuntimeError("mmvae_b200: optimal_sigma shapes %s vs %s" % (tuple(recon.shape), tuple(target.shape)))
-        stat = torch.zeros(2, dtype=torch.float64, device=recon.device)  # [sumsq, n_total]
+        stat = torch.zeros(2, dtype=torch.float64, device=recon.device)  # [sumsq, element count], both device side
         call("mmvae_osigma_sumsq", _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, P, _ptr(stat), _stream())
-        n_total = float(rows * P)
-        if group is not None:  # global RMS over every shard: one tiny all-reduce
-            import torch.distributed as dist
-            dist.all_reduce(stat[:1], group=group)
-            n_total *= dist.get_world_size(group)
+        n_total = 0.0  # <= 0: the kernels read the count from stat[1]
+        if group is not None:  # global RMS over every shard: ONE tiny all-reduce of sum and count,
+            import torch.distributed as dist  # so shards of different sizes (B % world != 0) get the global mean
+            dist.all_reduce(stat, group=group)
         out = torch.empty(rows, dtype=torch.float32, device=recon.device)
         stats2 = torch.empty(2, dtype=torch.float32, device=recon.device)
         call("mmvae_osigma_fwd", _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, P, lam, _ptr(stat), n_total,
@@ -625,6 +631,11 @@ class _IwaeRows(torch.autograd.Function):
                 raise RuntimeError("mmvae_b200: the IWAE gradient buffers are single-use (retain_graph unsupported)")
             dlpz, ctx.nw = ctx.nw, None
         else:
+            # the kernel scales the saved dlq IN PLACE through a raw pointer (autograd sees no version bump): a second
+            # backward would silently return dlq * g^2 -- single-use like the unit path and the fused ELBO buffers
+            if getattr(ctx, "dlq_consumed", False):
+                raise RuntimeError("mmvae_b200: the IWAE gradient buffers are single-use (retain_graph unsupported)")
+            ctx.dlq_consumed = True
             gs = g.detach().float().contiguous()
             dlpz = torch.empty_like(w)
             call("mmvae_objective_iwae_bwd", _ptr(gs), _ptr(w), _ptr(dlq_out), _ptr(dlpz), w.numel(), dlq_out.numel(),

@@ -45,6 +45,57 @@ def shard_batch(batch: dict, rank: int, world: int) -> dict:
     return out
 
 
+def shard_leaves(cfg: dict, tensors: dict, rank: int, world: int):
+    """Rows [lo, hi) of a leaf-tensor set (workloads.make_leaves): encoder outputs (M,B,D), targets (B,..), noise
+    (K,B,D) and the k-major reconstructions (row = k*B + b) / synthetic likelihood rows; the prior logits are replicated.
+    Returns (cfg with the local B, sharded tensors, (lo, hi))."""
+    B = cfg["B"]
+    lo, hi = shard_range(B, rank, world)
+    out = {"mu": tensors["mu"][:, lo:hi].contiguous(), "s": tensors["s"][:, lo:hi].contiguous(),
+           "pz_logits": tensors["pz_logits"], "targets": [x[lo:hi].contiguous() for x in tensors["targets"]]}
+    out["recon"] = [r.view(r.shape[0] // B, B, *r.shape[1:])[:, lo:hi].reshape(-1, *r.shape[1:]).contiguous()
+                    for r in tensors["recon"]]
+    out["noise"] = [n[:, lo:hi].contiguous() for n in tensors["noise"]]
+    if tensors.get("dz") is not None:
+        out["dz"] = tensors["dz"][:, :, lo:hi].contiguous()
+    c = dict(cfg)
+    c["B"] = hi - lo
+    return c, out, (lo, hi)
+
+
+def sharded_parity(name: str, B: int, group, device, seed: int = 11):
+    """Numerical parity of the batch-sharded CUDA path: every rank runs its shard of a small global batch (captured in a
+    CUDA graph together with its collectives, like the benchmarked step) and compares with the same objective on the
+    FULL batch run locally: summed loss, all-reduced prior-logit gradient, the shard's rows of d/dmu, d/ds and of the
+    first reconstruction gradient.  Returns the largest relative deviation seen on this rank."""
+    from . import workloads as W
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    cfg, t = W.make_leaves(name, B=B, seed=seed)
+    t["pz_logits"] = torch.randn(1, cfg["D"], generator=torch.Generator().manual_seed(2)) * 0.3
+    full = W.LeafStep(cfg, t, device=device)
+    full_loss = full.run().detach().clone()
+    c2, t2, (lo, hi) = shard_leaves(cfg, t, rank, world)
+    step = W.LeafStep(c2, t2, device=device, group=group, global_batch=B, sync_grads=True)
+    gs = W.GraphedStep(step)
+    for _ in range(2):
+        loss = gs.run()
+    loss = loss.detach().clone()
+    if cfg["obj"] != "dreg":  # the DReG loss is already a global quantity (computed from all-reduced batch sums)
+        dist.all_reduce(loss, group=group)
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    K = cfg["K"] if cfg["model"] == "moe" else 1
+    errs = [rel(loss, full_loss), rel(step.mu.grad, full.mu.grad[:, lo:hi]), rel(step.s.grad, full.s.grad[:, lo:hi])]
+    if full.pz_logits.grad is not None and float(full.pz_logits.grad.abs().max()) > 0:
+        errs.append(rel(step.pz_logits.grad, full.pz_logits.grad))
+    g_full = full.recon[0].grad
+    g_full = g_full.view(K, B, *g_full.shape[1:])[:, lo:hi].reshape(step.recon[0].grad.shape)
+    errs.append(rel(step.recon[0].grad, g_full))
+    gs.close()  # a graph that captured the communicator must be destroyed before the process group
+    step.sync.disarm()
+    return max(errs)
+
+
 def attach(model, group=None, global_batch: int = None):
     """Tell a drop-in model plugin that it sees one shard of a global batch."""
     model.group = group
@@ -157,7 +208,16 @@ class GradSync:
             return
         if self._inflight:
             if self._side is not None:
-                torch.cuda.current_stream().wait_stream(self._side)
+                cur = torch.cuda.current_stream()
+                cur.wait_stream(self._side)
+                # tensors created on the side stream (the flat bucket, gradients materialised for parameters that got
+                # none) are consumed on this stream from here on: tell the caching allocator, or a later free could hand
+                # their memory back to the side stream while work queued here still reads it
+                if self._flat is not None:
+                    self._flat.record_stream(cur)
+                for p in self.params:
+                    if p.grad is not None:
+                        p.grad.record_stream(cur)
         else:
             self._reduce()
         self._inflight, self._seen = False, 0

@@ -178,6 +178,17 @@ WORKLOADS = {
         dict(data_dim=(8, 64, 64, 3), ltype="bce", target="uniform", dist="normal", lam=1.0),
         dict(data_dim=(9,), ltype="category_ce", target="onehot", dist="normal", lam=1.0),
         dict(data_dim=(4, 6), ltype="category_ce", target="onehot", dist="normal", lam=1.0)]),
+    # C3 / configs[2], VILANRO shapes (reference configs/config_vilanro.yml): language (B,4,V) with V = 27, actions
+    # (B,100,4,1), RGB (B,3,64,64), every likelihood optimal_sigma (objectives.py:502-509), D = 32, B = 64
+    "c3_mopoe_elbo_vilanro": dict(model="mopoe", obj="elbo", K=1, D=32, B=64, mods=[
+        dict(data_dim=(4, 27), ltype="optimal_sigma", target="uniform", dist="normal", lam=1.0),
+        dict(data_dim=(100, 4, 1), ltype="optimal_sigma", target="uniform", dist="normal", lam=1.0),
+        dict(data_dim=(3, 64, 64), ltype="optimal_sigma", target="uniform", dist="normal", lam=1.0)]),
+    # the shipped config_vilanro.yml itself mixes with `poe` (MVAE: all 7 subsets, 21 likelihood terms)
+    "c3_poe_elbo_vilanro": dict(model="poe", obj="elbo", K=1, D=32, B=64, mods=[
+        dict(data_dim=(4, 27), ltype="optimal_sigma", target="uniform", dist="normal", lam=1.0),
+        dict(data_dim=(100, 4, 1), ltype="optimal_sigma", target="uniform", dist="normal", lam=1.0),
+        dict(data_dim=(3, 64, 64), ltype="optimal_sigma", target="uniform", dist="normal", lam=1.0)]),
     # C4: MMVAE DReG K=50, D=64, MNIST/SVHN-shaped Laplace likelihoods
     "c4_moe_dreg_mnistsvhn": dict(model="moe", obj="dreg", K=50, D=64, B=1024, mods=[
         dict(data_dim=(1, 28, 28), ltype="lprob", target="uniform", dist="laplace", lam=1.0),

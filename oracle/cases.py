@@ -54,7 +54,7 @@ def make_case(name, seed, model, obj, B, D, mods, K=1, beta=1.0, private=None, p
         # recon_loss_fn crops the decoder output (objectives.py:43-45)
         dec_dim = tuple(spec.get("dec_dim", spec["data_dim"]))
         P = int(math.prod(dec_dim))
-        squash = spec["ltype"] in ("bce",)
+        squash = spec.get("squash", spec["ltype"] in ("bce",))
         W = torch.randn(P, dz, generator=g) * (0.5 / math.sqrt(dz))
         b = torch.randn(P, generator=g) * 0.1
         target = syn.make_target(g, spec.get("target", "uniform"), B, spec["data_dim"])
@@ -176,6 +176,12 @@ LAP_A = dict(data_dim=(1, 7, 7), ltype="lprob", target="uniform", dist="laplace"
 LAP_B = dict(data_dim=(3, 6, 6), ltype="lprob", target="uniform", dist="laplace", lam=49.0 / 108.0)
 NRM_A = dict(data_dim=(1, 7, 7), ltype="lprob", target="uniform", dist="normal", lam=1.0)
 TXT_MASKED = dict(data_dim=(5, 27), dec_dim=(8, 27), ltype="category_ce", target="onehot")  # decoder pads to T=8
+# lprob + padding masks: recon_loss_fn overwrites the likelihood scale with the cropped loc (objectives.py:43-45);
+# a sigmoid decoder keeps loc (= scale) positive, an unsquashed one produces log(negative) = NaN -> 0 entries
+# (only with mask length == decoder length: a real crop makes the reference raise in torch's _validate_sample, the
+# distribution keeps the batch_shape it was built with)
+LPM_NRM = dict(data_dim=(5, 6), dec_dim=(5, 6), ltype="lprob", target="uniform", dist="normal", squash=True)
+LPM_LAP = dict(data_dim=(4, 7), dec_dim=(4, 7), ltype="lprob", target="uniform", dist="laplace", squash=False, lam=0.5)
 
 
 def case_list():
@@ -197,4 +203,6 @@ def case_list():
     c.append(make_case("poe_elbo_masks", 501, "poe", "elbo", B=6, D=4, mods=[IMG, TXT_MASKED]))
     c.append(make_case("moe_iwae_masks", 502, "moe", "iwae", B=4, D=4, K=3, mods=[IMG, TXT_MASKED]))
     c.append(make_case("mopoe_elbo_masks", 503, "mopoe", "elbo", B=7, D=6, mods=[TXT_MASKED, IMG, ACT]))
+    c.append(make_case("poe_elbo_lprob_masks", 504, "poe", "elbo", B=6, D=4, mods=[IMG, LPM_NRM]))
+    c.append(make_case("mopoe_elbo_lprob_masks", 505, "mopoe", "elbo", B=5, D=4, mods=[LPM_LAP, LPM_NRM]))
     return c

@@ -207,7 +207,8 @@ def recon_logp(ltype, loc, target, K=1, likelihood="normal", scale=0.75, mask_le
     elif ltype == "bce":  # objectives.py:391-406
         loss = F.binary_cross_entropy(loc, target.detach(), reduction="none").reshape(bs, -1)
     elif ltype == "lprob":  # objectives.py:408-424 (fp64 accumulate, NaN -> 0)
-        sc = torch.as_tensor(scale, dtype=loc.dtype, device=loc.device)
+        # objectives.py:43-45: with padding masks the likelihood's scale is overwritten by its (cropped) loc
+        sc = loc if mask_len is not None else torch.as_tensor(scale, dtype=loc.dtype, device=loc.device)
         out = log_prob(likelihood, target, loc, sc).view(bs, -1).double().reshape(bs, -1)
         out = torch.where(torch.isnan(out), torch.zeros_like(out), out)
         loss = -out
