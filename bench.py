@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="N>1: skip the sharded-vs-unsharded numerical check")
+    ap.add_argument("--nccl-only", action="store_true",
+                    help="N>1: every collective through NCCL (default: the small ones fused into our kernels over peer memory)")
     ap.add_argument("--cpu-batch", type=int, default=None,
                     help="opt-in: samples per step of the CPU arms (default: the workload batch, bounded by an element budget)")
     return ap.parse_args()
@@ -292,7 +294,7 @@ class PluginStep:
         self.sync = None
         if world > 1:
             par.attach(self.model, group, B * world)
-            self.sync = par.GradSync(self.params, group)
+            self.sync = par.GradSync(par.nccl_synced_params(self.model), group)
         self.gobj = None
         if graphed:  # the whole plugin step (encoders, kernels, decoders, backward) as ONE captured graph
             self.gobj = mmvae_b200.GraphedObjective(
@@ -373,6 +375,18 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     L.load()
+    # collectives of the step: fused into our kernels over NVLink peer memory (parallel.PeerGroup, csrc/peer.cuh) unless
+    # --nccl-only or the symmetric-memory allocation is unavailable; NCCL stays for the plugin's parameter buckets
+    coll, coll_note = group, "none (1 GPU)"
+    if world > 1:
+        coll_note = "NCCL (in-graph all-reduce on a side stream)"
+        if not args.nccl_only:
+            try:
+                coll = par.PeerGroup(group, dev)
+                coll_note = ("fused into the kernels over NVLink peer memory (prior-logit gradient sync inside the prior-scale "
+                             "backward, DReG (M,K) batch sums inside stage 2, optimal_sigma sum+count): no NCCL call in the step")
+            except Exception as ex:
+                coll_note = "NCCL (peer memory unavailable: %s)" % repr(ex)[:160]
     rdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     B, scaling = local_batch(args, syn.WORKLOADS[args.workload]["B"], world)
     cfg, t = W.make_leaves(args.workload, B=B, seed=1234 + rank, recon_dtype=rdt)
@@ -380,12 +394,12 @@ def main():
     # Default: inside the step (parallel.GradSync hook -> side stream, overlapped with the likelihood backward and
     # captured in the step graph); --eager-sync: one eager NCCL call after the step.
     in_step_sync = world > 1 and not args.eager_sync
-    step = W.LeafStep(cfg, t, device=dev, group=group, global_batch=B * world, sync_grads=in_step_sync)
+    step = W.LeafStep(cfg, t, device=dev, group=coll, global_batch=B * world, sync_grads=in_step_sync)
     step.streams = args.streams
     W_, K_ = max(args.warmup, 3), args.steps
 
     def sync_grads():
-        if world > 1 and step.sync is None and step.pz_logits.grad is not None:
+        if world > 1 and step.sync is None and step.peer is None and step.pz_logits.grad is not None:
             dist.all_reduce(step.pz_logits.grad, group=group)
 
     # launches of our kernels per step, counted on one eager step
@@ -401,9 +415,14 @@ def main():
         runner = W.GraphedStep(step)
     sync_mode = "none (1 GPU)"
     if world > 1:
-        sync_mode = ("in-step all-reduce on a side stream behind the latent backward, overlapped with the likelihood "
-                     "backward%s" % (", captured in the step graph" if runner is not step else "")) \
-            if step.sync is not None else "eager all-reduce after the step"
+        if step.peer is not None:
+            sync_mode = "fused into the prior-scale backward kernel (peer memory)%s" % (
+                ", captured in the step graph" if runner is not step else "")
+        elif step.sync is not None:
+            sync_mode = ("in-step NCCL all-reduce on a side stream behind the latent backward, overlapped with the likelihood "
+                         "backward%s" % (", captured in the step graph" if runner is not step else ""))
+        else:
+            sync_mode = "eager NCCL all-reduce after the step"
 
     def one():
         runner.run()
@@ -543,7 +562,7 @@ def main():
                 if key == "eager" and world > 1:
                     continue
                 try:
-                    ps = PluginStep(cfg, B, dev, group, world, rank, **kw)
+                    ps = PluginStep(cfg, B, dev, coll, world, rank, **kw)
                     for _ in range(3):
                         ps.step()
                     pms = timed(ke, ps.step)
@@ -568,16 +587,18 @@ def main():
         for name in dict.fromkeys([args.workload, "c2_moe_iwae_cdsprites_l5", "c4_moe_dreg_mnistsvhn",
                                    "c3_mopoe_elbo_vilanro"]):
             try:
-                per[name] = allmax(par.sharded_parity(name, 4 * world + 1, group, dev))
+                per[name] = allmax(par.sharded_parity(name, 4 * world + 1, coll, dev))
             except Exception as ex:
                 per[name] = repr(ex)[:200]
         nums = [v for v in per.values() if isinstance(v, float)]
         parity_n = {"max_rel": max(nums) if nums else None, "per_workload": per, "global_batch": 4 * world + 1,
-                    "what": "sharded (CUDA graph, in-step NCCL) vs full batch on one GPU: summed loss, all-reduced prior "
-                            "gradient, shard rows of d/dmu, d/ds, d/drecon[0]; max relative deviation over ranks"}
+                    "peer_timeouts": bool(coll.error()) if isinstance(coll, par.PeerGroup) else None,
+                    "what": "sharded (CUDA graph, collectives inside the step) vs full batch on one GPU: summed loss, "
+                            "all-reduced prior gradient, shard rows of d/dmu, d/ds, d/drecon[0]; max relative deviation "
+                            "over ranks"}
 
     conf = config_dict(args, cfg, B, world, scaling)
-    run = {"grad_sync": sync_mode, "launch_mode": "cuda-graph" if runner is not step else "eager",
+    run = {"grad_sync": sync_mode, "collectives": coll_note, "launch_mode": "cuda-graph" if runner is not step else "eager",
            "streams": "3 (likelihood terms alternate between two streams, latent kernels on a third; "
                       "forks/joins captured in the graph)" if step.streams == 3 else "single stream"}
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K_, "timed_steps": K_eff,

@@ -51,6 +51,11 @@ enum { MMVAE_LT_BCE = 0, MMVAE_LT_LPROB_NORMAL = 1, MMVAE_LT_LPROB_LAPLACE = 2, 
           (objectives.py:43-45), i.e. log_prob of Normal / Laplace(loc = x, scale = x); NaN (x < 0) -> 0.  Reproduced. */
        MMVAE_LT_LPROB_NORMAL_SELF = 6, MMVAE_LT_LPROB_LAPLACE_SELF = 7 };
 
+/* peer-memory all-reduce (mmvae_*_peer entry points): layout constants of the per-rank symmetric buffer */
+#define MMVAE_PEER_CHANNELS 8        /* independent call sites / streams                       */
+#define MMVAE_PEER_MAX_WORLD 32      /* ranks of one NVLink domain                             */
+#define MMVAE_PEER_BUFFER_BYTES (72 * 1024) /* bytes to allocate (zeroed) per rank             */
+
 #define MMVAE_MAX_MODS 8    /* modalities per model                       */
 #define MMVAE_MAX_COLS 256  /* latent columns per modality (shared+private) */
 
@@ -202,6 +207,14 @@ MMVAE_API int mmvae_kl_elementwise_bwd(const float* loc, const float* scale, con
                              int dist, int64_t n, int D, const float* upstream, float* dloc, float* dscale,
                              float* ws, float* dloc0, float* dscale0, void* stream);
 
+/* Per-dimension KL tables of the analysis hooks: replaces utils.make_kl_df (utils.py:130-162; called by
+ * trainer.analyse_data trainer.py:242-272), which moves every posterior to the CPU and evaluates M + 2*C(M,2) separate
+ * torch kl_divergence calls.  loc, scale (M, n, D); prior row (D); out (T, n, D), T = M + M(M-1)/2:
+ *   out[i] = KL(q_i || N(loc0, scale0)), then for pairs i < j (itertools.combinations order)
+ *   out[M + pair] = 0.5 (KL(q_i || q_j) + KL(q_j || q_i)).  All M posteriors share one family (Normal or Laplace). */
+MMVAE_API int mmvae_kl_table(const float* loc, const float* scale, int M, const int32_t* dists_host, const float* loc0,
+                   const float* scale0, int64_t n, int D, float* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * MoE sample + log-densities (fused): replaces MOE.forward's rsample (mmvae_models.py:99), the importance
  * terms of the ELBO branch (:56-62) and the log p(z) / log-mean q_j(z) terms of MultimodalObjective.iwae /
@@ -288,6 +301,30 @@ MMVAE_API int mmvae_objective_dreg_stage2(const double* lw, int M, int K, float*
 MMVAE_API int mmvae_objective_dreg_rowgrads(const float* g_dev, const float* wt, int M, int L, int K, int64_t B,
                                   float* d_rows, void* stream);
 MMVAE_API int mmvae_reduce_sum(const float* x, int64_t n, float scale, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused compute + collective over NVLink peer memory (multi-GPU): the three reductions of this path whose
+ * result every rank needs run as ONE kernel each -- local math, exchange through peer-mapped symmetric buffers
+ * (P2P stores / loads over NVSwitch, flags with system-scope release / acquire), the math that consumes the sum --
+ * instead of kernel -> NCCL all-reduce -> kernel.  Sums are taken in rank order: bit-identical on every rank.
+ *   peer_bufs_dev: DEVICE array of `world` pointers, entry q = rank q's symmetric buffer of MMVAE_PEER_BUFFER_BYTES
+ *   bytes (zero-initialised once, before the first call, followed by a barrier) mapped into this rank's address
+ *   space; `channel` < MMVAE_PEER_CHANNELS separates call sites that may be in flight at the same time.  Every rank
+ *   must issue the same calls in the same order per channel.  CUDA-graph capturable (sequence numbers live in the
+ *   buffer).  A wait that exceeds ~2 s sets the error word (mmvae_peer_error_offset()) instead of hanging.
+ *   _prior_scale_bwd_peer : dlogits = all-reduce( D p (ds0 - <ds0, p>) )   (mmvae_prior_scale_bwd + gradient sync of
+ *                           the replicated prior logits _pz_params[1], reference mmvae_models.py:28-30)
+ *   _dreg_stage2_peer     : lw <- all-reduce(lw) (global batch sums, objectives.py:361-387), then stage 2 as above;
+ *                           lw is updated in place with the global sums
+ *   _peer_allreduce_f64   : in-place sum of n <= 512 doubles (optimal_sigma sum of squares + element count)
+ * ------------------------------------------------------------------------------------------------------- */
+MMVAE_API int64_t mmvae_peer_error_offset(void);
+MMVAE_API int mmvae_prior_scale_bwd_peer(const float* s0, const float* ds0, int D, float* dlogits,
+                               void* const* peer_bufs_dev, int rank, int world, int channel, void* stream);
+MMVAE_API int mmvae_objective_dreg_stage2_peer(double* lw_inout, int M, int K, float* wt, float* loss,
+                                     void* const* peer_bufs_dev, int rank, int world, int channel, void* stream);
+MMVAE_API int mmvae_peer_allreduce_f64(double* data_inout, int n, void* const* peer_bufs_dev, int rank, int world,
+                             int channel, void* stream);
 
 /* in-place scale of a gradient buffer by a DEVICE scalar, skipped entirely (early exit) when the scalar == 1:
  * lets the fused ELBO path keep autograd semantics for loss.backward(gradient=g) at zero cost when g == 1. */

@@ -17,6 +17,7 @@ LT_BCE, LT_LPROB_NORMAL, LT_LPROB_LAPLACE, LT_MSE, LT_L1, LT_BCE_LOGITS = 0, 1, 
 LT_LPROB_NORMAL_SELF, LT_LPROB_LAPLACE_SELF = 6, 7
 DRAW_PRIOR, DRAW_DIRECT, DRAW_LAPLACE, DRAW_ROWMASK = 1, 2, 4, 8
 MAX_MODS, MAX_COLS, MAX_DRAWS, DREG_MAX_SPLIT = 8, 256, 64, 64
+PEER_CHANNELS, PEER_MAX_WORLD, PEER_BUFFER_BYTES = 8, 32, 72 * 1024
 
 
 class DrawDesc(ctypes.Structure):
@@ -46,6 +47,7 @@ SIGNATURES = {
     "mmvae_kl_elementwise_fwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i64, c_i, c_p, c_p]),
     "mmvae_kl_elementwise_ws_floats": (c_i64, [c_i64, c_i]),
     "mmvae_kl_elementwise_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i64, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "mmvae_kl_table": (c_i, [c_p, c_p, c_i, ctypes.POINTER(ctypes.c_int32), c_p, c_p, c_i64, c_i, c_p, c_p]),
     "mmvae_moe_logdens_fwd": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_i, ctypes.POINTER(ctypes.c_int32), c_p, c_p, c_p,
                                     c_p, c_p, c_p, c_p]),
     "mmvae_moe_logdens_bwd_ws_floats": (c_i64, [c_i64, c_i, c_i]),
@@ -66,6 +68,10 @@ SIGNATURES = {
     "mmvae_objective_dreg_stage2": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p]),
     "mmvae_objective_dreg_rowgrads": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i64, c_p, c_p]),
     "mmvae_reduce_sum": (c_i, [c_p, c_i64, c_f, c_p, c_p]),
+    "mmvae_peer_error_offset": (c_i64, []),
+    "mmvae_prior_scale_bwd_peer": (c_i, [c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_p]),
+    "mmvae_objective_dreg_stage2_peer": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_p]),
+    "mmvae_peer_allreduce_f64": (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_p]),
     "mmvae_scale_inplace": (c_i, [c_p, c_i, c_i64, c_p, c_p]),
 }
 

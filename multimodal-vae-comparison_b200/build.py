@@ -21,7 +21,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 def _digest():
     h = hashlib.sha256()
-    files = [os.path.join(CSRC, f) for f in SOURCES] + [os.path.join(CSRC, "common.cuh"),
+    files = [os.path.join(CSRC, f) for f in SOURCES] + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "peer.cuh"),
                                                          os.path.join(ROOT, "include", "mmvae_b200.h")]
     for f in files:
         h.update(open(f, "rb").read())

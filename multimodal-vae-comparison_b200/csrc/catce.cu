@@ -337,6 +337,231 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
 
 
 // ---------------------------------------------------------------------------------------------------------------
+// bf16 pair kernel (r2): long class axes in bf16 (CUB captions, C = 246, d = 27 -- BASELINE configs[4]).
+//
+// ncu r1 on the staged kernel above at that shape: instruction-latency bound (issue-active 45 %), 2.2 TB/s.  A lane
+// there owns one column and pays, per element, a 2-byte LDS per tensor, a conversion per tensor and scalar math.  Here a
+// lane owns one 32-bit WORD position of the class-row period, i.e. TWO element streams, and everything is done on pairs:
+// one LDS.32 per tensor and pair, the two bf16 -> fp32 conversions are a shift and a mask into an aligned register pair,
+// exp arguments / running sums / gradient are packed f32x2 operations (common.cuh), the gradient leaves as one packed
+// cvt.rn.bf16x2 + STS.32.
+//   d even: a period is one class row (d/2 words); a lane's streams are the columns (2p, 2p+1), every class row.
+//   d odd : a period is TWO class rows (d words; needs C even); the streams are (parity, column) pairs -- columns 2p, 2p+1
+//           of the even rows for p < (d-1)/2, the straddling word (even row, d-1 | odd row, 0), then columns of the odd
+//           rows.  The two parities of a column are merged like the W class-axis slices of the warps.
+// W warps per row split the periods; partial (max, sum exp, sum t, sum t*x) per (warp, parity, column) go through
+// shared memory, ONE barrier, every warp merges the statistics of all columns itself and proceeds to the gradient of
+// its own slice (written in place over the staged x, one TMA bulk store per CTA).  Targets are staged next to x or read
+// straight from global memory (STAGE_T = 0: half the shared memory per CTA, more resident warps).
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef MMVAE_CATCE_PAIRS
+#define MMVAE_CATCE_PAIRS 1
+#endif
+#ifndef MMVAE_CATCE_PAIRS_W
+#define MMVAE_CATCE_PAIRS_W 4
+#endif
+#ifndef MMVAE_CATCE_PAIRS_R
+#define MMVAE_CATCE_PAIRS_R 4
+#endif
+#ifndef MMVAE_CATCE_PAIRS_STAGE_T
+#define MMVAE_CATCE_PAIRS_STAGE_T 0
+#endif
+constexpr int kPairCh = 8;  // periods per register chunk: 8 words per tensor in flight per lane
+
+__device__ __forceinline__ f32x2 bf2_to_f2(uint32_t w) { return f2_pack(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+__device__ __forceinline__ uint32_t f2_to_bf2(f32x2 v) {
+    uint32_t r;
+    float lo, hi;
+    f2_unpack(v, lo, hi);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+template <int MODE, bool STAGE_T>  // MODE 0: forward (+ statistics), 2: fused value + gradient
+__global__ void __launch_bounds__(512) catce_pairs_kernel(const CatceParams p) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const int n = p.C * p.d, R = p.R, W = p.W, d = p.d;
+    const bool odd = (d & 1) != 0;
+    const int Pw = odd ? d : d / 2;        // words per period
+    const int NP = odd ? p.C / 2 : p.C;    // periods per row
+    const int NPAR = odd ? 2 : 1;
+    uint32_t* sx = reinterpret_cast<uint32_t*>(smraw);
+    size_t off = up16((size_t)R * n * 2);
+    uint32_t* stg = reinterpret_cast<uint32_t*>(smraw + off);
+    if (STAGE_T) off += up16((size_t)R * n * 2);
+    float* s_lse = reinterpret_cast<float*>(smraw + off);  // R*d merged logsumexp
+    float* s_ts = s_lse + R * d;                            // R*d merged sum t
+    float4* part = reinterpret_cast<float4*>(smraw + up16(off + (size_t)2 * R * d * 4));  // R*W*NPAR*d
+    uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(part) + (size_t)R * W * NPAR * d * 16);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rl = warp / W, w = warp - rl * W;
+    const int64_t row0 = (int64_t)blockIdx.x * R;
+    const __nv_bfloat16* xg = reinterpret_cast<const __nv_bfloat16*>(p.x);
+    const __nv_bfloat16* tg = reinterpret_cast<const __nv_bfloat16*>(p.t);
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bx = (uint32_t)((size_t)R * n * 2);
+        mbar_expect_tx(bar, STAGE_T ? 2 * bx : bx);
+        bulk_g2s(sx, xg + row0 * p.ldx, bx, bar);
+        if (STAGE_T) bulk_g2s(stg, tg + (row0 % p.B) * p.ldt, bx, bar);
+    }
+    // this lane's two streams: (parity, column) of the low and the high half of its word
+    const bool lane_ok = lane < Pw;
+    int parL = 0, colL = 2 * lane, parH = 0, colH = 2 * lane + 1;
+    if (odd) {
+        const int h = (d - 1) / 2;
+        if (lane == h) { colL = d - 1; parH = 1; colH = 0; }
+        else if (lane > h) { parL = parH = 1; colL = 2 * lane - d; colH = colL + 1; }
+    }
+    const int NPw = (NP + W - 1) / W, q_lo = w * NPw, q_hi = min(NP, q_lo + NPw);
+    const uint32_t* rx = sx + (size_t)rl * (n / 2) + lane;
+    const uint32_t* rt = STAGE_T ? stg + (size_t)rl * (n / 2) + lane
+                                 : reinterpret_cast<const uint32_t*>(tg + ((row0 + rl) % p.B) * p.ldt) + lane;
+    if (warp == 0) mbar_wait(bar, 0);
+    __syncthreads();
+
+    // ---- pass 1: online softmax statistics of the two streams over this warp's periods ------------------------------
+    float mL = -INFINITY, mH = -INFINITY;
+    f32x2 SE = 0ull, TS = 0ull, TX = 0ull;
+    const f32x2 L2E = f2_bcast(kLog2e);
+    if (lane_ok) {
+        for (int q0 = q_lo; q0 < q_hi; q0 += kPairCh) {
+            uint32_t xw[kPairCh], tw[kPairCh];
+#pragma unroll
+            for (int u = 0; u < kPairCh; ++u) xw[u] = q0 + u < q_hi ? rx[(q0 + u) * Pw] : 0xff80ff80u;  // -inf pairs
+#pragma unroll
+            for (int u = 0; u < kPairCh; ++u) tw[u] = q0 + u < q_hi ? (STAGE_T ? rt[(q0 + u) * Pw] : __ldg(rt + (q0 + u) * Pw)) : 0u;
+            float cL = -INFINITY, cH = -INFINITY;
+#pragma unroll
+            for (int u = 0; u < kPairCh; ++u) {
+                cL = fmaxf(cL, __uint_as_float(xw[u] << 16));
+                cH = fmaxf(cH, __uint_as_float(xw[u] & 0xffff0000u));
+            }
+            const float nL = fmaxf(mL, cL), nH = fmaxf(mH, cH);
+            const float kL = nL == -INFINITY ? 0.f : -nL * kLog2e, kH = nH == -INFINITY ? 0.f : -nH * kLog2e;
+            SE = f2_mul(SE, f2_pack(ex2_ftz(fmaf(mL, kLog2e, kL)), ex2_ftz(fmaf(mH, kLog2e, kH))));  // rescale to the new max
+            const f32x2 NM = f2_pack(kL, kH);
+#pragma unroll
+            for (int u = 0; u < kPairCh; ++u) {
+                const f32x2 X = bf2_to_f2(xw[u]), T = bf2_to_f2(tw[u]);
+                float a0, a1;
+                f2_unpack(f2_fma(X, L2E, NM), a0, a1);
+                SE = f2_add(SE, f2_pack(ex2_ftz(a0), ex2_ftz(a1)));
+                TS = f2_add(TS, T);
+                if (q0 + u < q_hi) TX = f2_fma(T, X, TX);  // (-inf padding: t = 0 but 0 * -inf is NaN)
+            }
+            mL = nL;
+            mH = nH;
+        }
+        part[((size_t)(rl * W + w) * NPAR + parL) * d + colL] = make_float4(mL, f2_lo(SE), f2_lo(TS), f2_lo(TX));
+        if (colH < d) part[((size_t)(rl * W + w) * NPAR + parH) * d + colH] = make_float4(mH, f2_hi(SE), f2_hi(TS), f2_hi(TX));
+    }
+    __syncthreads();
+    // ---- merge: every warp merges the W x NPAR partials of all columns of its row (lane j <-> column j) -------------
+    float lse_j = 0.f, ts_j = 0.f, acc = 0.f;
+    for (int j = lane; j < d; j += 32) {
+        float mm = -INFINITY;
+        for (int q = 0; q < W * NPAR; ++q) mm = fmaxf(mm, part[((size_t)rl * W * NPAR + q) * d + j].x);
+        const float nm = mm == -INFINITY ? 0.f : -mm * kLog2e;
+        float se = 0.f, ts = 0.f, txs = 0.f;
+        for (int q = 0; q < W * NPAR; ++q) {
+            const float4 v = part[((size_t)rl * W * NPAR + q) * d + j];
+            se = fmaf(v.y, ex2_ftz(fmaf(v.x, kLog2e, nm)), se);
+            ts += v.z;
+            txs += v.w;
+        }
+        const float lse = mm + logf(se);
+        acc += txs - lse * ts;
+        if (d <= 32) { lse_j = lse; ts_j = ts; }
+        else { s_lse[rl * d + j] = lse; s_ts[rl * d + j] = ts; }
+        if (w == 0 && p.stats) {
+            p.stats[(row0 + rl) * 2 * d + j] = lse;
+            p.stats[(row0 + rl) * 2 * d + d + j] = ts;
+        }
+    }
+    if (w == 0) {
+        acc = warp_sum(acc);
+        if (lane == 0) p.out_rows[row0 + rl] = p.lam * acc;
+    }
+    if (MODE == 2) {
+        // statistics of this lane's two streams' columns: held by lanes colL / colH (d <= 32) or in shared memory
+        float lseL, lseH, tsL, tsH;
+        if (d <= 32) {
+            lseL = __shfl_sync(0xffffffffu, lse_j, colL & 31); tsL = __shfl_sync(0xffffffffu, ts_j, colL & 31);
+            lseH = __shfl_sync(0xffffffffu, lse_j, colH & 31); tsH = __shfl_sync(0xffffffffu, ts_j, colH & 31);
+        } else {
+            __syncwarp();
+            lseL = s_lse[rl * d + colL]; tsL = s_ts[rl * d + colL];
+            lseH = s_lse[rl * d + min(colH, d - 1)]; tsH = s_ts[rl * d + min(colH, d - 1)];
+        }
+        if (lane_ok) {
+            const float wl = (p.w_rows ? __ldg(p.w_rows + row0 + rl) : p.w_const) * p.lam;
+            const f32x2 NL = f2_pack(-lseL * kLog2e, -lseH * kLog2e), WTS = f2_pack(-wl * tsL, -wl * tsH), WL = f2_bcast(wl);
+            uint32_t* gx = sx + (size_t)rl * (n / 2) + lane;  // in place over the staged x
+            for (int q0 = q_lo; q0 < q_hi; q0 += kPairCh) {
+                uint32_t xw[kPairCh], tw[kPairCh];
+#pragma unroll
+                for (int u = 0; u < kPairCh; ++u) xw[u] = q0 + u < q_hi ? rx[(q0 + u) * Pw] : 0u;
+#pragma unroll
+                for (int u = 0; u < kPairCh; ++u) tw[u] = q0 + u < q_hi ? (STAGE_T ? rt[(q0 + u) * Pw] : __ldg(rt + (q0 + u) * Pw)) : 0u;
+#pragma unroll
+                for (int u = 0; u < kPairCh; ++u) {
+                    float a0, a1;
+                    f2_unpack(f2_fma(bf2_to_f2(xw[u]), L2E, NL), a0, a1);
+                    const f32x2 G = f2_fma(f2_pack(ex2_ftz(a0), ex2_ftz(a1)), WTS, f2_mul(WL, bf2_to_f2(tw[u])));
+                    if (q0 + u < q_hi) gx[(q0 + u) * Pw] = f2_to_bf2(G);
+                }
+            }
+        }
+        fence_async_smem();  // generic-proxy smem writes -> visible to the async (TMA) proxy
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_s2g(reinterpret_cast<__nv_bfloat16*>(p.g) + row0 * p.ldg, sx, (uint32_t)((size_t)R * n * 2));
+            bulk_wait_read();  // smem must stay alive until the bulk store has read it
+        }
+    }
+}
+
+static size_t pairs_smem(int R, int W, int n, int d, bool stage_t) {
+    const int npar = (d & 1) ? 2 : 1;
+    size_t off = up16((size_t)R * n * 2) * (stage_t ? 2 : 1);
+    off = up16(off + (size_t)2 * R * d * 4);
+    return off + (size_t)R * W * npar * d * 16 + 16;
+}
+
+// bf16 / bf16, forward or fused, dense TMA-able slabs, d odd (<= 31, C even) or d even (<= 64); false otherwise
+static bool launch_catce_pairs(int mode, CatceParams p, cudaStream_t st, int* rc) {
+#if MMVAE_CATCE_PAIRS
+    const int n = p.C * p.d, d = p.d;
+    if (mode == 1 || p.C < 64) return false;  // long class axes only: short rows stay on the tuned r1 kernels
+    if ((d & 1) ? (d > 31 || (p.C & 1)) : d > 64) return false;
+    int R = MMVAE_CATCE_PAIRS_R, W = MMVAE_CATCE_PAIRS_W;
+    while (R > 1 && (pairs_smem(R, W, n, d, MMVAE_CATCE_PAIRS_STAGE_T) > 100 * 1024 || R * W > 16)) R >>= 1;
+    const bool dense = p.ldx == n && p.ldt == n && (mode == 0 || p.ldg == n);
+    const bool ok = dense && aligned16(p.x) && aligned16(p.t) && (mode == 0 || aligned16(p.g)) && p.rows % R == 0 &&
+                    p.B % R == 0 && ((size_t)R * n * 2) % 16 == 0 && (n % 2) == 0;
+    if (!ok) return false;
+    p.R = R;
+    p.W = W;
+    const size_t smem = pairs_smem(R, W, n, d, MMVAE_CATCE_PAIRS_STAGE_T);
+    auto k = mode == 0 ? catce_pairs_kernel<0, MMVAE_CATCE_PAIRS_STAGE_T != 0> : catce_pairs_kernel<2, MMVAE_CATCE_PAIRS_STAGE_T != 0>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { *rc = (int)e; return true; }
+    }
+    k<<<(unsigned)(p.rows / R), R * W * 32, smem, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    *rc = e == cudaSuccess ? 0 : (int)e;
+    return true;
+#else
+    (void)mode; (void)p; (void)st; (void)rc;
+    return false;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // v2 (default): no shared-memory staging.
 //
 // ncu r1 on the TMA-staged kernel above (C2 text term, 7680 x 45 x 27 fp32): 18.7 us forward / 21.7 us backward for
@@ -844,8 +1069,11 @@ extern "C" int mmvae_catce_rows(int mode, const void* recon, int64_t ld_recon, i
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype_recon == MMVAE_F32 && dtype_target == MMVAE_F32) return launch_catce<float, float>(mode, p, st);
     if (dtype_recon == MMVAE_BF16 && dtype_target == MMVAE_F32) return launch_catce<__nv_bfloat16, float>(mode, p, st);
-    if (dtype_recon == MMVAE_BF16 && dtype_target == MMVAE_BF16)
+    if (dtype_recon == MMVAE_BF16 && dtype_target == MMVAE_BF16) {
+        int rc = 0;
+        if (launch_catce_pairs(mode, p, st, &rc)) return rc;
         return launch_catce<__nv_bfloat16, __nv_bfloat16>(mode, p, st);
+    }
     if (dtype_recon == MMVAE_F32 && dtype_target == MMVAE_BF16) return launch_catce<float, __nv_bfloat16>(mode, p, st);
     return MMVAE_E_ENUM;
 }

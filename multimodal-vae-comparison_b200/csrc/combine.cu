@@ -5,6 +5,7 @@
 // lanes run over b (coalesced) and the (r,k) logsumexp is an online-softmax merge across warps through shared
 // memory; batch sums are warp-shuffle + smem block reductions.
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace mmvae {
 
@@ -218,9 +219,18 @@ __global__ void dreg_partial_sum_kernel(const double* __restrict__ ws, int parts
 }
 
 // DReG stage 2 (single CTA, one warp per modality row): wt = softmax_k(lw[r,:]); loss = -(1/M) sum wt*lw
-__global__ void __launch_bounds__(256) dreg_stage2_kernel(const double* __restrict__ lw, int M, int K,
-                                                          float* __restrict__ wt, float* __restrict__ loss) {
+template <bool PEER>
+__global__ void __launch_bounds__(256) dreg_stage2_kernel(double* __restrict__ lw, int M, int K,
+                                                          float* __restrict__ wt, float* __restrict__ loss, PeerCtx pc) {
     __shared__ double s_part[8];
+    if (PEER) {  // global batch sums: exchange the (M,K) local sums through peer memory, rank-ordered sum
+        __shared__ double s_lw[kPeerSlotBytes / sizeof(double)];
+        for (int i = threadIdx.x; i < M * K; i += blockDim.x) s_lw[i] = lw[i];
+        __syncthreads();
+        peer_allreduce_smem<double>(s_lw, M * K, pc);
+        for (int i = threadIdx.x; i < M * K; i += blockDim.x) lw[i] = s_lw[i];
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double mine = 0.0;
     for (int r = wid; r < M; r += 8) {
@@ -318,9 +328,10 @@ __global__ void __launch_bounds__(256) prior_scale_fwd_kernel(const float* __res
     for (int i = threadIdx.x; i < D; i += blockDim.x) s0[i] = expf(logits[i] - mx) / se * (float)D;
 }
 
+template <bool PEER>
 __global__ void __launch_bounds__(256) prior_scale_bwd_kernel(const float* __restrict__ s0,
                                                               const float* __restrict__ ds0, int D,
-                                                              float* __restrict__ dlogits) {
+                                                              float* __restrict__ dlogits, PeerCtx pc) {
     __shared__ float red[32];
     __shared__ float bc;
     float dot = 0.f;  // sum_d ds0_d * p_d with p = s0 / D
@@ -329,7 +340,23 @@ __global__ void __launch_bounds__(256) prior_scale_bwd_kernel(const float* __res
     if (threadIdx.x == 0) bc = dot / (float)D;
     __syncthreads();
     dot = bc;
-    for (int i = threadIdx.x; i < D; i += blockDim.x) dlogits[i] = s0[i] * (ds0[i] - dot);
+    if (!PEER) {
+        for (int i = threadIdx.x; i < D; i += blockDim.x) dlogits[i] = s0[i] * (ds0[i] - dot);
+    } else {  // gradient sync of the replicated prior logits fused in: all-reduce(SUM) over peer memory
+        __shared__ float s_g[kPeerSlotBytes / sizeof(float)];
+        for (int i = threadIdx.x; i < D; i += blockDim.x) s_g[i] = s0[i] * (ds0[i] - dot);
+        __syncthreads();
+        peer_allreduce_smem<float>(s_g, D, pc);
+        for (int i = threadIdx.x; i < D; i += blockDim.x) dlogits[i] = s_g[i];
+    }
+}
+
+__global__ void __launch_bounds__(256) peer_allreduce_f64_kernel(double* __restrict__ data, int n, PeerCtx pc) {
+    __shared__ double s_v[kPeerSlotBytes / sizeof(double)];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_v[i] = data[i];
+    __syncthreads();
+    peer_allreduce_smem<double>(s_v, n, pc);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) data[i] = s_v[i];
 }
 
 template <typename T>
@@ -427,7 +454,42 @@ extern "C" int mmvae_objective_dreg_stage1_ptrs(const float* lpz, const float* l
 
 extern "C" int mmvae_objective_dreg_stage2(const double* lw, int M, int K, float* wt, float* loss, void* stream) {
     if (!lw || !wt || !loss || M <= 0 || K <= 0) return MMVAE_E_ARG;
-    dreg_stage2_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(lw, M, K, wt, loss);
+    dreg_stage2_kernel<false><<<1, 256, 0, (cudaStream_t)stream>>>(const_cast<double*>(lw), M, K, wt, loss, PeerCtx{});
+    MMVAE_LAUNCH_CHECK();
+    return 0;
+}
+
+static int peer_fill(PeerCtx& pc, void* const* peer_bufs_dev, int rank, int world, int channel) {
+    if (!peer_bufs_dev || world <= 0 || rank < 0 || rank >= world || channel < 0) return MMVAE_E_ARG;
+    if (world > kPeerMaxWorld || channel >= kPeerChannels) return MMVAE_E_LIMIT;
+    pc.bufs = reinterpret_cast<unsigned char* const*>(peer_bufs_dev);
+    pc.rank = rank; pc.world = world; pc.channel = channel;
+    return 0;
+}
+
+extern "C" int64_t mmvae_peer_error_offset(void) { return (int64_t)kPeerErrOff; }
+
+extern "C" int mmvae_objective_dreg_stage2_peer(double* lw_inout, int M, int K, float* wt, float* loss,
+                                                void* const* peer_bufs_dev, int rank, int world, int channel,
+                                                void* stream) {
+    if (!lw_inout || !wt || !loss || M <= 0 || K <= 0) return MMVAE_E_ARG;
+    if ((size_t)M * K * sizeof(double) > kPeerSlotBytes) return MMVAE_E_LIMIT;
+    PeerCtx pc{};
+    int rc = peer_fill(pc, peer_bufs_dev, rank, world, channel);
+    if (rc) return rc;
+    dreg_stage2_kernel<true><<<1, 256, 0, (cudaStream_t)stream>>>(lw_inout, M, K, wt, loss, pc);
+    MMVAE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mmvae_peer_allreduce_f64(double* data_inout, int n, void* const* peer_bufs_dev, int rank, int world,
+                                        int channel, void* stream) {
+    if (!data_inout || n <= 0) return MMVAE_E_ARG;
+    if ((size_t)n * sizeof(double) > kPeerSlotBytes) return MMVAE_E_LIMIT;
+    PeerCtx pc{};
+    int rc = peer_fill(pc, peer_bufs_dev, rank, world, channel);
+    if (rc) return rc;
+    peer_allreduce_f64_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(data_inout, n, pc);
     MMVAE_LAUNCH_CHECK();
     return 0;
 }
@@ -484,7 +546,19 @@ extern "C" int mmvae_prior_scale_fwd(const float* logits, int D, float* s0, void
 
 extern "C" int mmvae_prior_scale_bwd(const float* s0, const float* ds0, int D, float* dlogits, void* stream) {
     if (!s0 || !ds0 || !dlogits || D <= 0) return MMVAE_E_ARG;
-    prior_scale_bwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(s0, ds0, D, dlogits);
+    prior_scale_bwd_kernel<false><<<1, 256, 0, (cudaStream_t)stream>>>(s0, ds0, D, dlogits, PeerCtx{});
+    MMVAE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mmvae_prior_scale_bwd_peer(const float* s0, const float* ds0, int D, float* dlogits,
+                                          void* const* peer_bufs_dev, int rank, int world, int channel, void* stream) {
+    if (!s0 || !ds0 || !dlogits || D <= 0) return MMVAE_E_ARG;
+    if ((size_t)D * sizeof(float) > kPeerSlotBytes) return MMVAE_E_LIMIT;
+    PeerCtx pc{};
+    int rc = peer_fill(pc, peer_bufs_dev, rank, world, channel);
+    if (rc) return rc;
+    prior_scale_bwd_kernel<true><<<1, 256, 0, (cudaStream_t)stream>>>(s0, ds0, D, dlogits, pc);
     MMVAE_LAUNCH_CHECK();
     return 0;
 }

@@ -261,6 +261,49 @@ __global__ void __launch_bounds__(256) kl_elem_kernel(const float* __restrict__ 
     }
 }
 
+// KL between two posteriors of the same family (torch kl.py _kl_normal_normal / _kl_laplace_laplace)
+__device__ __forceinline__ float kl_pair(bool laplace, float lp, float sp, float lq, float sq) {
+    if (!laplace) return kl_value(false, lp, sp, lq, sq);
+    const float ratio = sp / sq, ad = fabsf(lp - lq);
+    return -logf(ratio) + ad / sq + ratio * expf(-ad / sp) - 1.0f;
+}
+
+// Per-dimension KL tables of the analysis hooks (reference utils.py:130-162 make_kl_df, called from
+// trainer.py:242-272 analyse_data): for M posteriors (M, n, D) and the prior row (D), ONE pass writes
+//   out[i]           = KL(q_i || p)                                  i < M
+//   out[M + pair]    = 0.5 (KL(q_i || q_j) + KL(q_j || q_i))         pairs (i < j) in itertools.combinations order
+// as (T, n, D), T = M + M(M-1)/2.  The reference moves every distribution to the CPU and evaluates M + 2*C(M,2)
+// separate torch.distributions.kl_divergence calls there.  Every thread reads the 2M parameters of its (row, column)
+// once and produces all T values from registers.
+__global__ void __launch_bounds__(256) kl_table_kernel(const float* __restrict__ loc, const float* __restrict__ scale,
+                                                       const float* __restrict__ loc0, const float* __restrict__ scale0,
+                                                       int M, int lap_mask, int64_t n, int D, float* __restrict__ out) {
+    const int64_t total = n * D;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % D);
+        const float m0 = __ldg(loc0 + c), s0 = __ldg(scale0 + c);
+        float l[MMVAE_MAX_MODS], sg[MMVAE_MAX_MODS];
+#pragma unroll
+        for (int m = 0; m < MMVAE_MAX_MODS; ++m)
+            if (m < M) {
+                l[m] = loc[(int64_t)m * total + i];
+                sg[m] = scale[(int64_t)m * total + i];
+                out[(int64_t)m * total + i] = kl_value((lap_mask >> m) & 1, l[m], sg[m], m0, s0);
+            }
+        int t = M;
+#pragma unroll
+        for (int a = 0; a < MMVAE_MAX_MODS; ++a)
+#pragma unroll
+            for (int b = a + 1; b < MMVAE_MAX_MODS; ++b)
+                if (b < M) {
+                    const bool lap = (lap_mask >> a) & 1;  // host guarantees equal families inside a pair
+                    out[(int64_t)t * total + i] =
+                        0.5f * (kl_pair(lap, l[a], sg[a], l[b], sg[b]) + kl_pair(lap, l[b], sg[b], l[a], sg[a]));
+                    ++t;
+                }
+    }
+}
+
 static unsigned draws_grid(int64_t B) {
     int64_t g = (B + kWarps - 1) / kWarps;
     const int64_t cap = (int64_t)kNumSMs * 4;
@@ -348,6 +391,21 @@ static unsigned kl_grid(int64_t total) {
     int64_t g = (total + 255) / 256;
     const int64_t cap = (int64_t)kNumSMs * 4;
     return (unsigned)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+extern "C" int mmvae_kl_table(const float* loc, const float* scale, int M, const int32_t* dists_host, const float* loc0,
+                              const float* scale0, int64_t n, int D, float* out, void* stream) {
+    if (!loc || !scale || !dists_host || !loc0 || !scale0 || !out || M <= 0 || n <= 0 || D <= 0) return MMVAE_E_ARG;
+    if (M > MMVAE_MAX_MODS) return MMVAE_E_LIMIT;
+    int mask = 0;
+    for (int m = 0; m < M; ++m) {
+        if (dists_host[m] != MMVAE_NORMAL && dists_host[m] != MMVAE_LAPLACE) return MMVAE_E_ENUM;
+        if (dists_host[m] != dists_host[0]) return MMVAE_E_ENUM;  // symmetric J needs both directions in closed form
+        mask |= (dists_host[m] == MMVAE_LAPLACE) << m;
+    }
+    kl_table_kernel<<<kl_grid(n * D), 256, 0, (cudaStream_t)stream>>>(loc, scale, loc0, scale0, M, mask, n, D, out);
+    MMVAE_LAUNCH_CHECK();
+    return 0;
 }
 
 extern "C" int64_t mmvae_kl_elementwise_ws_floats(int64_t n, int D) { return (int64_t)kl_grid(n * D) * 2 * D; }

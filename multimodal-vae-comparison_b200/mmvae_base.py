@@ -68,7 +68,8 @@ class TorchMMVAE(nn.Module):
         """pz_params for the kernels: same values as the `pz_params` property, the softmax*D evaluated by one tiny
         kernel each way (ops.prior_scale) instead of four eager ones."""
         if self._pz_params[1].is_cuda:
-            return self._pz_params[0], ops.prior_scale(self._pz_params[1])
+            peer = self.group if hasattr(self.group, "bufs_dev") else None  # parallel.PeerGroup: fused gradient sync
+            return self._pz_params[0], ops.prior_scale(self._pz_params[1], peer)
         return self.pz_params
 
     @property

@@ -62,6 +62,13 @@ def _stream():
     return _P(torch.cuda.current_stream().cuda_stream)
 
 
+def _peer(group):
+    """(peer, process_group): `group` may be a parallel.PeerGroup (fused peer-memory kernels) or a torch process group."""
+    if group is not None and hasattr(group, "bufs_dev"):
+        return group, group.pg
+    return None, group
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -310,7 +317,7 @@ def catce_weighted_sum(recon, target, lam=1.0, w_rows=None, w_const=1.0):
 # ----------------------------------------------------------------------------------------------------------
 class _OsigmaRows(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, recon, target, lam, group):
+    def forward(ctx, recon, target, lam, group, channel):
         ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(recon, target)
         rows, B = recon.shape[0], target.shape[0]
@@ -321,39 +328,50 @@ class _OsigmaRows(torch.autograd.Function):
         stat = torch.zeros(2, dtype=torch.float64, device=recon.device)  # [sumsq, element count], both device side
         call("mmvae_osigma_sumsq", _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, P, _ptr(stat), _stream())
         n_total = 0.0  # <= 0: the kernels read the count from stat[1]
-        if group is not None:  # global RMS over every shard: ONE tiny all-reduce of sum and count,
-            import torch.distributed as dist  # so shards of different sizes (B % world != 0) get the global mean
-            dist.all_reduce(stat, group=group)
+        peer, pgroup = _peer(group)
+        if peer is not None:  # global RMS over every shard: sum AND count through peer memory
+            call("mmvae_peer_allreduce_f64", _ptr(stat), 2, peer.bufs_dev, peer.rank, peer.world,
+                 peer.CH_OSIGMA + (channel & 1), _stream())
+        elif pgroup is not None:  # ... or ONE tiny NCCL all-reduce of both, so uneven shards get the global mean
+            import torch.distributed as dist
+            dist.all_reduce(stat, group=pgroup)
         out = torch.empty(rows, dtype=torch.float32, device=recon.device)
         stats2 = torch.empty(2, dtype=torch.float32, device=recon.device)
         call("mmvae_osigma_fwd", _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, P, lam, _ptr(stat), n_total,
              _ptr(out), _ptr(stats2), _P(0), _stream())
         ctx.save_for_backward(x, t, stat)
-        ctx.meta = (rows, B, P, ldx, ldt, lam, n_total, recon.shape, group)
+        ctx.meta = (rows, B, P, ldx, ldt, lam, n_total, recon.shape, group, channel)
         return out
 
     @staticmethod
     def backward(ctx, g_rows):
         if g_rows is None:
-            return None, None, None, None
+            return None, None, None, None, None
         x, t, stat = ctx.saved_tensors
-        rows, B, P, ldx, ldt, lam, n_total, shape, group = ctx.meta
+        rows, B, P, ldx, ldt, lam, n_total, shape, group, channel = ctx.meta
         w = g_rows.detach().to(torch.float32).contiguous()
         wsum = torch.empty(1, dtype=torch.float32, device=x.device)
         g = torch.empty((rows, P), dtype=x.dtype, device=x.device)
-        if group is not None:
+        peer, pgroup = _peer(group)
+        if peer is not None or pgroup is not None:
             # the shards' rows all depend on every shard's x through the global sigma: sum_r w_r must be global too
-            import torch.distributed as dist
-            wtot = w.sum().reshape(1)
-            dist.all_reduce(wtot, group=group)
-            w = wtot / rows * torch.ones_like(w)  # same row-weight sum, fed through the unchanged kernel
+            wtot = w.sum(dtype=torch.float64).reshape(1)
+            if peer is not None:
+                call("mmvae_peer_allreduce_f64", _ptr(wtot), 1, peer.bufs_dev, peer.rank, peer.world,
+                     peer.CH_OSIGMA_BWD + (channel & 1), _stream())
+            else:
+                import torch.distributed as dist
+                dist.all_reduce(wtot, group=pgroup)
+            w = (wtot / rows).float() * torch.ones_like(w)  # same row-weight sum, fed through the unchanged kernel
         call("mmvae_osigma_bwd", _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, P, lam, _ptr(stat), n_total,
              _ptr(w), _ptr(wsum), _ptr(g), P, _stream())
-        return g.view(shape), None, None, None
+        return g.view(shape), None, None, None, None
 
 
-def osigma_rows(recon, target, lam=1.0, group=None):
-    return _OsigmaRows.apply(recon, target, float(lam), group)
+def osigma_rows(recon, target, lam=1.0, group=None, channel=0):
+    """group: torch process group or parallel.PeerGroup of a batch-sharded run; channel: distinguishes optimal_sigma terms
+    that may be in flight at the same time on different streams (peer mode)."""
+    return _OsigmaRows.apply(recon, target, float(lam), group, int(channel))
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -653,7 +671,7 @@ class _PriorScale(torch.autograd.Function):
     """s0 = softmax(logits, 1) * D of the learnable prior (reference mmvae_models.py:28-30), one tiny kernel each way."""
 
     @staticmethod
-    def forward(ctx, logits):
+    def forward(ctx, logits, peer):
         ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(logits)
         lg = logits.detach().float().contiguous()
@@ -661,21 +679,29 @@ class _PriorScale(torch.autograd.Function):
         s0 = torch.empty_like(lg)
         call("mmvae_prior_scale_fwd", _ptr(lg), D, _ptr(s0), _stream())
         ctx.save_for_backward(s0)
+        ctx.peer = peer
         return s0
 
     @staticmethod
     def backward(ctx, ds0):
         if ds0 is None:
-            return None
+            return None, None
         (s0,) = ctx.saved_tensors
         d = ds0.detach().float().contiguous()
         out = torch.empty_like(s0)
-        call("mmvae_prior_scale_bwd", _ptr(s0), _ptr(d), s0.shape[-1], _ptr(out), _stream())
-        return out
+        if ctx.peer is not None:  # gradient sync of the replicated logits fused into this kernel (peer memory)
+            pg = ctx.peer
+            call("mmvae_prior_scale_bwd_peer", _ptr(s0), _ptr(d), s0.shape[-1], _ptr(out), pg.bufs_dev, pg.rank, pg.world,
+                 pg.CH_PRIOR_GRAD, _stream())
+        else:
+            call("mmvae_prior_scale_bwd", _ptr(s0), _ptr(d), s0.shape[-1], _ptr(out), _stream())
+        return out, None
 
 
-def prior_scale(logits):
-    return _PriorScale.apply(logits)
+def prior_scale(logits, peer=None):
+    """s0 = softmax(logits, 1) * D.  peer: a parallel.PeerGroup -- the backward then returns the gradient already
+    all-reduced (SUM) over its ranks (one fused kernel, no NCCL); every rank must run this backward once per step."""
+    return _PriorScale.apply(logits, peer)
 
 
 class _Dreg(torch.autograd.Function):
@@ -696,9 +722,10 @@ class _Dreg(torch.autograd.Function):
         call("mmvae_objective_dreg_stage1", _ptr(lpz_c), _ptr(lq_c), _ptr(lpx_c), M, L, K, B, _ptr(part),
              _ptr(lq_soft), _stream())
         lw = part[0]
-        if group is not None:
+        _, pgroup = _peer(group)
+        if pgroup is not None:
             import torch.distributed as dist
-            dist.all_reduce(lw, group=group)
+            dist.all_reduce(lw, group=pgroup)
         wt = torch.empty((M, K), dtype=torch.float32, device=dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
         call("mmvae_objective_dreg_stage2", _ptr(lw), M, K, _ptr(wt), _ptr(loss), _stream())
@@ -746,12 +773,18 @@ class _DregRows(torch.autograd.Function):
         call("mmvae_objective_dreg_stage1_ptrs", _ptr(lpz_c), _ptr(lq_c), _P(0), ptrs, M, L, K, B, _ptr(part),
              _ptr(lq_soft), _stream())
         lw = part[0]
-        if group is not None:  # the (M,K) batch sums are global; capturable (NCCL on the current stream)
-            import torch.distributed as dist
-            dist.all_reduce(lw, group=group)
+        peer, pgroup = _peer(group)
         wt = torch.empty((M, K), dtype=torch.float32, device=dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        call("mmvae_objective_dreg_stage2", _ptr(lw), M, K, _ptr(wt), _ptr(loss), _stream())
+        if peer is not None and M * K * 8 <= 4096:
+            # the (M,K) batch sums are global -- exchanged through peer memory INSIDE stage 2
+            call("mmvae_objective_dreg_stage2_peer", _ptr(lw), M, K, _ptr(wt), _ptr(loss), peer.bufs_dev, peer.rank,
+                 peer.world, peer.CH_DREG, _stream())
+        else:
+            if pgroup is not None:  # NCCL on the current stream (capturable)
+                import torch.distributed as dist
+                dist.all_reduce(lw, group=pgroup)
+            call("mmvae_objective_dreg_stage2", _ptr(lw), M, K, _ptr(wt), _ptr(loss), _stream())
         ctx.save_for_backward(wt, lq_soft)
         ctx.meta = (M, L, K, B, [r.shape for r in rows])
         ctx.node = node
@@ -823,6 +856,23 @@ class _KlElementwise(torch.autograd.Function):
 
 def kl_elementwise(loc, scale, loc0, scale0, laplace=False):
     return _KlElementwise.apply(loc, scale, loc0, scale0, 1 if laplace else 0)
+
+
+def kl_table(loc, scale, loc0, scale0, laplace=False):
+    """include/mmvae_b200.h mmvae_kl_table (forward only: analysis).  loc, scale (M, n, D); prior (D) ->
+    (M + M(M-1)/2, n, D): KL(q_i || prior) rows, then the symmetric J divergences of the pairs i < j."""
+    _need_cuda(loc, scale, loc0, scale0)
+    M, n, D = loc.shape
+    f = lambda t: t.detach().float().contiguous()
+    l, sg = f(loc), f(scale)
+    l0 = f(loc0).reshape(-1).expand(D).contiguous() if loc0.numel() == 1 else f(loc0).reshape(-1)
+    s0 = f(scale0).reshape(-1).expand(D).contiguous() if scale0.numel() == 1 else f(scale0).reshape(-1)
+    if l0.numel() != D or s0.numel() != D:
+        raise RuntimeError("mmvae_b200: the prior must broadcast as a single (D) row")
+    out = torch.empty((M + M * (M - 1) // 2, n, D), dtype=torch.float32, device=loc.device)
+    darr = (ctypes.c_int32 * M)(*([1 if laplace else 0] * M))
+    call("mmvae_kl_table", _ptr(l), _ptr(sg), M, darr, _ptr(l0), _ptr(s0), n, D, _ptr(out), _stream())
+    return out
 
 
 def reduce_sum(x, scale=1.0):

@@ -19,6 +19,43 @@ import torch
 import torch.distributed as dist
 
 
+class PeerGroup:
+    """One NVLink / NVSwitch domain seen through peer-mapped symmetric buffers: the handle the fused
+    compute + collective kernels (include/mmvae_b200.h mmvae_*_peer) exchange their small reductions through, instead
+    of going kernel -> NCCL all-reduce -> kernel.  PyTorch only provides the memory: the buffer comes from
+    torch.distributed._symmetric_memory (CUDA VMM allocation exported to the peers of `group`), the protocol and the
+    kernels are ours (csrc/peer.cuh).  Wherever this package takes a process `group`, a PeerGroup may be passed
+    instead; NCCL (``.pg``) stays in use for what does not fit a 4 KB slot (encoder / decoder gradient buckets)."""
+
+    CH_PRIOR_GRAD, CH_DREG, CH_OSIGMA, CH_OSIGMA_BWD = 0, 1, 2, 4  # channels (osigma: + term parity)
+
+    def __init__(self, group=None, device=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self.pg = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.pg), dist.get_world_size(self.pg)
+        if self.world > _lib.PEER_MAX_WORLD:
+            raise RuntimeError("mmvae_b200: PeerGroup supports up to %d ranks" % _lib.PEER_MAX_WORLD)
+        device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm.empty(_lib.PEER_BUFFER_BYTES, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, self.pg.group_name)
+        torch.cuda.synchronize(device)
+        dist.barrier(self.pg)  # every rank's buffer is zeroed before anyone publishes into it
+        self.bufs_dev = ctypes.c_void_p(int(self.hdl.buffer_ptrs_dev))
+        self._err_off = int(_lib.load().mmvae_peer_error_offset())
+
+    def error(self) -> bool:
+        """True if a wait of any fused collective on this rank ever timed out (a peer did not show up within ~2 s)."""
+        return bool(self.buf[self._err_off:self._err_off + 4].view(torch.int32).item())
+
+
+def process_group(group):
+    """The torch process group behind `group` (a PeerGroup or a process group / None)."""
+    return group.pg if isinstance(group, PeerGroup) else group
+
+
 def shard_range(n_global: int, rank: int, world: int):
     """Contiguous global-row range [lo, hi) of `rank`: rows [g*B/G, (g+1)*B/G), remainder to the first ranks."""
     base, rem = divmod(n_global, world)
@@ -69,7 +106,8 @@ def sharded_parity(name: str, B: int, group, device, seed: int = 11):
     FULL batch run locally: summed loss, all-reduced prior-logit gradient, the shard's rows of d/dmu, d/ds and of the
     first reconstruction gradient.  Returns the largest relative deviation seen on this rank."""
     from . import workloads as W
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    pg = process_group(group)
+    rank, world = dist.get_rank(pg), dist.get_world_size(pg)
     cfg, t = W.make_leaves(name, B=B, seed=seed)
     t["pz_logits"] = torch.randn(1, cfg["D"], generator=torch.Generator().manual_seed(2)) * 0.3
     full = W.LeafStep(cfg, t, device=device)
@@ -81,7 +119,7 @@ def sharded_parity(name: str, B: int, group, device, seed: int = 11):
         loss = gs.run()
     loss = loss.detach().clone()
     if cfg["obj"] != "dreg":  # the DReG loss is already a global quantity (computed from all-reduced batch sums)
-        dist.all_reduce(loss, group=group)
+        dist.all_reduce(loss, group=pg)
     torch.cuda.synchronize()
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
     K = cfg["K"] if cfg["model"] == "moe" else 1
@@ -92,16 +130,26 @@ def sharded_parity(name: str, B: int, group, device, seed: int = 11):
     g_full = g_full.view(K, B, *g_full.shape[1:])[:, lo:hi].reshape(step.recon[0].grad.shape)
     errs.append(rel(step.recon[0].grad, g_full))
     gs.close()  # a graph that captured the communicator must be destroyed before the process group
-    step.sync.disarm()
+    if step.sync is not None:
+        step.sync.disarm()
     return max(errs)
 
 
 def attach(model, group=None, global_batch: int = None):
-    """Tell a drop-in model plugin that it sees one shard of a global batch."""
+    """Tell a drop-in model plugin that it sees one shard of a global batch.  With a PeerGroup the forward exchanges AND
+    the gradient sync of the replicated prior logits run inside the fused peer-memory kernels."""
     model.group = group
     model.obj_fn.group = group
     model.global_batch = global_batch
     return model
+
+
+def nccl_synced_params(model):
+    """Parameters whose gradients still need the flat-bucket NCCL all-reduce (GradSync): everything trainable, except
+    the prior logits when the model is attached to a PeerGroup (their gradient leaves prior_scale's backward kernel
+    already summed over the ranks)."""
+    skip = id(model._pz_params[1]) if isinstance(getattr(model, "group", None), PeerGroup) else None
+    return [p for p in model.parameters() if p.requires_grad and id(p) != skip]
 
 
 class GradSync:
@@ -121,7 +169,7 @@ class GradSync:
 
     def __init__(self, params: Iterable[torch.nn.Parameter], group=None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
-        self.group = group
+        self.group = process_group(group)
         self._flat = None
         self._side = None
         self._handles = []

@@ -1,6 +1,7 @@
 """Hot-path helpers with the reference's names (reference utils.py: log_mean_exp :395-396, kl_divergence :399-405,
 subsample_input_modalities :86-112, find_out_batch_size :72-78, softclip :66-69, Constants :253-259, combinatorial
-:595-601), written for this package."""
+:595-601) and the analysis consumers of the same math (make_kl_df :130-162, trainer.eval_forward / analyse_data
+trainer.py:242-279), written for this package."""
 import itertools
 import math
 
@@ -72,3 +73,92 @@ def subsample_input_modalities(mods, forbidden=()):
                     entry[k] = {kk: (None if kk in ("data", "masks") else vv) for kk, vv in mods[k].items()}
             out.append(entry)
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# analysis / evaluation consumers
+# ----------------------------------------------------------------------------------------------------------
+KL_AX_NAMES = ["Dimensions", r"KL$(q\,||\,p)$"]
+
+
+def _tensors_to_df(tensors, head, keys, ax_names):
+    """Long-format table of reference visualization.py:106-122 (tensor_to_df / tensors_to_df): one row per
+    (tensor, sample, dimension), columns [head, ax_names[0], ax_names[1]], sample-major inside a dimension."""
+    import numpy as np
+    import pandas as pd
+    dfs = []
+    for t in tensors:
+        assert t.ndim == 2, "Can only currently convert 2D tensors to dataframes"
+        df = pd.DataFrame(data=np.asarray(t), columns=np.arange(t.shape[1]))
+        dfs.append(df.melt(value_vars=df.columns, var_name=ax_names[0], value_name=ax_names[1]))
+    df = pd.concat(dfs, keys=keys)
+    df.reset_index(level=0, inplace=True)
+    df.rename(columns={"level_0": head}, inplace=True)
+    return df
+
+
+def kl_tables(qz_xs, pz):
+    """(T, n, D) tensor of per-dimension divergences: KL(q_i || p) for every posterior, then the symmetric
+    J(q_i, q_j) = 0.5 (KL(q_i||q_j) + KL(q_j||q_i)) of every pair i < j -- one kernel launch (ops.kl_table) for Normal
+    or Laplace posteriors on the GPU; everything stays on the device."""
+    if not isinstance(qz_xs, (list, tuple)):
+        qz_xs = [qz_xs]
+    fam = type(qz_xs[0])
+    if fam not in (dist.Normal, dist.Laplace) or any(type(q) is not fam for q in qz_xs) or not isinstance(pz, dist.Normal):
+        raise NotImplementedError("kl_tables: Normal or Laplace posteriors of one family against a Normal prior")
+    D = qz_xs[0].loc.shape[-1]
+    loc = torch.stack([q.loc.reshape(-1, D) for q in qz_xs])
+    scale = torch.stack([q.scale.reshape(-1, D) for q in qz_xs])
+    return ops.kl_table(loc, scale, pz.loc, pz.scale, laplace=fam is dist.Laplace)
+
+
+def make_kl_df(qz_xs, pz):
+    """Reference utils.py:130-162: the per-dimension KL table the analysis hook plots -- KL(q(z|x_i) || p(z)) for every
+    modality and the symmetric J divergence of every pair, as the same long-format pandas DataFrame (same keys, column
+    names and row order).  The divergences come from one kernel launch on the device; only the finished (T, n, D) table
+    is copied to the host (the reference moves every distribution to the CPU first and calls kl_divergence M + 2 C(M,2)
+    times there)."""
+    if isinstance(qz_xs, (list, tuple)) and len(qz_xs) == 1:
+        qz_xs = qz_xs[0]
+    if isinstance(qz_xs, (list, tuple)):
+        M = len(qz_xs)
+        table = kl_tables(list(qz_xs), pz).cpu()
+        keys = [r"KL$(q(z|x_{})\,||\,p(z))$".format(i) for i in range(M)] + \
+               [r"J$(q(z|x_{})\,||\,q(z|x_{}))$".format(i, j) for i, j in itertools.combinations(range(M), 2)]
+        return _tensors_to_df([table[i] for i in range(table.shape[0])], "KL", keys, KL_AX_NAMES)
+    table = kl_tables([qz_xs], pz).cpu()
+    return _tensors_to_df([table[0]], "KL", [r"KL$(q(z|x)\,||\,p(z))$"], KL_AX_NAMES)
+
+
+def check_input_unpacked(mods):
+    """reference utils.py:80-84."""
+    if len(mods.keys()) == 1:
+        mods = mods[list(mods.keys())[0]]
+    return mods
+
+
+def data_to_device(data, device):
+    """reference utils.py:114-118 (returns a new dict instead of mutating the caller's)."""
+    return {key: {k: v.to(device=device, non_blocking=True) if hasattr(v, "to") else v for k, v in entry.items()}
+            for key, entry in data.items()}
+
+
+def eval_forward(model, data):
+    """reference trainer.py:274-279 (MultimodalVAE.eval_forward): forward pass outside training -> unpacked VAEOutput."""
+    device = next(model.parameters()).device
+    with torch.no_grad():
+        output = model.forward(check_input_unpacked(data_to_device(data, device)))
+    return output.unpack_values()
+
+
+def analyse_data(model, data, num_samples=250):
+    """The numerical part of reference trainer.py:242-272 (analyse_data): encode `data`, build the per-dimension KL table
+    and collect the latent samples the T-SNE plot embeds (prior samples first, then one entry per modality).  Plotting
+    (seaborn / matplotlib) is outside this path.  Returns {"kl_df", "latent_samples", "output"}."""
+    out = eval_forward(model, data)
+    pz = model.pz(*model.pz_params)
+    with torch.no_grad():
+        zss = [pz.sample(torch.Size([1, num_samples])).view(-1, pz.batch_shape[-1])] + \
+              [zs["latents"].view(-1, zs["latents"].size(-1)) for zs in out["latent_samples"]]
+        kl_df = make_kl_df([q for q in out["encoder_dist"] if q is not None], pz)
+    return {"kl_df": kl_df, "latent_samples": zss, "output": out}

@@ -154,8 +154,11 @@ class LeafStep:
         # IWAE / DReG branch creates the latent nodes after the likelihood nodes, so autograd (highest sequence number
         # first) runs the latent backward -- which produces that gradient -- before the long likelihood backward
         # kernels, and the collective hides behind them.
+        # With a parallel.PeerGroup as `group` the same all-reduce is FUSED into the backward kernel of the prior scale
+        # (peer memory over NVLink, csrc/peer.cuh): no NCCL call, no side stream, nothing to join.
         self.sync = None
-        if sync_grads and group is not None:
+        self.peer = group if (sync_grads and hasattr(group, "bufs_dev")) else None
+        if sync_grads and group is not None and self.peer is None:
             from .parallel import GradSync
             self.sync = GradSync([self.pz_logits], group).arm()
 
@@ -222,7 +225,7 @@ class LeafStep:
         if m["ltype"] == "category_ce":
             return ops.catce_rows(self.recon[i], self.targets[tm], m["lam"])
         if m["ltype"] == "optimal_sigma":
-            return ops.osigma_rows(self.recon[i], self.targets[tm], m["lam"], self.group)
+            return ops.osigma_rows(self.recon[i], self.targets[tm], m["lam"], self.group, i)
         return ops.loglik_rows(self.recon[i], self.targets[tm], m["ltype"], fam, m["lam"])
 
     def _wsum(self, i, w_const=1.0, w_rows=None):
@@ -232,13 +235,13 @@ class LeafStep:
         if m["ltype"] == "category_ce":
             return ops.catce_weighted_sum(self.recon[i], self.targets[tm], m["lam"], w_rows=w_rows, w_const=w_const)
         if m["ltype"] == "optimal_sigma":
-            rows = ops.osigma_rows(self.recon[i], self.targets[tm], m["lam"], self.group)
+            rows = ops.osigma_rows(self.recon[i], self.targets[tm], m["lam"], self.group, i)
             return (torch.dot(rows, w_rows) if w_rows is not None else w_const * rows.sum()), rows.detach()
         return ops.loglik_weighted_sum(self.recon[i], self.targets[tm], m["ltype"], fam, m["lam"], w_rows=w_rows,
                                        w_const=w_const)
 
     def _prior(self):
-        return self._mu0, ops.prior_scale(self.pz_logits)
+        return self._mu0, ops.prior_scale(self.pz_logits, self.peer)
 
     # -- objectives -----------------------------------------------------------------------------------------
     def loss(self):

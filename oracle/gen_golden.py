@@ -16,7 +16,8 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, _ROOT)
 
 from oracle import cases, ref_inplace, refmath  # noqa: E402
-from oracle.validate_against_reference import run_reference, run_reference_unimodal, unimodal_cases  # noqa: E402
+from oracle.validate_against_reference import (kl_df_cases, run_reference, run_reference_kl_df,  # noqa: E402
+                                               run_reference_unimodal, unimodal_cases)
 
 OUT = os.path.join(_ROOT, "tests", "golden")
 
@@ -49,6 +50,7 @@ def main():
         blob["cases"].append({"case": case, "reference": ref})
         print("froze", case["name"], float(ref["loss"]))
     blob["unimodal"] = [{"case": c, "reference": run_reference_unimodal(c)} for c in unimodal_cases()]
+    blob["kl_df"] = [{"case": c, "reference": run_reference_kl_df(c)} for c in kl_df_cases()]
     blob["chunk_ends"] = chunk_maps()
     path = os.path.join(OUT, "reference_cases.pt")
     torch.save(blob, path)

@@ -501,3 +501,19 @@ def unimodal_elbo(mu, s, dist_name, noise, dec, target, ltype, beta=1.0, K=1, ma
     kld = kl_to_normal(dist_name, mu, s, torch.zeros_like(mu[:1]), torch.ones_like(mu[:1]))
     loss = elbo(lpx_z, kld, beta)
     return {"loss": loss, "kld": kld, "reconstruction_loss": lpx_z, "z": z}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# f3: per-dimension KL tables of the analysis hook (utils.py:130-162 make_kl_df)
+# ----------------------------------------------------------------------------------------------------------
+def kl_table(family, locs, scales, loc0, scale0):
+    """[KL(q_i || p) for i] + [0.5 (KL(q_i||q_j) + KL(q_j||q_i)) for i < j] through torch.distributions.kl_divergence
+    (utils.py:399-405 -> torch kl.py closed forms), stacked (T, n, D)."""
+    import itertools
+    import torch.distributions as dist
+    cls = dist.Laplace if family == "laplace" else dist.Normal
+    qs = [cls(l, s) for l, s in zip(locs, scales)]
+    pz = dist.Normal(loc0, scale0)
+    rows = [dist.kl_divergence(q, pz) for q in qs]
+    rows += [0.5 * (dist.kl_divergence(p, q) + dist.kl_divergence(q, p)) for p, q in itertools.combinations(qs, 2)]
+    return torch.stack(rows)

@@ -201,8 +201,46 @@ def run_oracle_unimodal(c, dtype=torch.float32):
             "grad.mu": mu.grad.double(), "grad.s": s.grad.double(), "grad.W": W.grad.double(), "grad.b": b.grad.double()}
 
 
+def kl_df_cases():
+    """Inputs of the analysis hook utils.make_kl_df (utils.py:130-162): M posteriors (n, D) + the Normal prior row."""
+    import mmvae_b200.synthetic as syn
+    g = torch.Generator().manual_seed(91)
+    out = []
+    for name, fam, M, n, D in (("kl_df_normal_m2", "normal", 2, 7, 6), ("kl_df_laplace_m3", "laplace", 3, 5, 4),
+                               ("kl_df_normal_m1", "normal", 1, 4, 8)):
+        post = [syn.make_posterior(g, n, D) for _ in range(M)]
+        out.append(dict(name=name, family=fam, locs=[p[0] for p in post], scales=[p[1] for p in post],
+                        loc0=torch.randn(1, D, generator=g) * 0.2, scale0=torch.softmax(torch.randn(1, D, generator=g), 1) * D))
+    return out
+
+
+def run_reference_kl_df(c):
+    """The reference's make_kl_df on torch.distributions objects; returns the DataFrame as plain python / tensors."""
+    import torch.distributions as dist
+    models, objectives, utils = ref_inplace.load()
+    cls = dist.Laplace if c["family"] == "laplace" else dist.Normal
+    qs = [cls(l.clone(), s.clone()) for l, s in zip(c["locs"], c["scales"])]
+    df = utils.make_kl_df(qs, dist.Normal(c["loc0"].clone(), c["scale0"].clone()))
+    return {"columns": list(df.columns), "keys": [str(k) for k in df[df.columns[0]].tolist()],
+            "dims": torch.tensor(df[df.columns[1]].to_numpy().astype("int64")),
+            "values": torch.tensor(df[df.columns[2]].to_numpy().astype("float64"))}
+
+
+def oracle_kl_df_values(c, dtype=torch.float32):
+    """refmath.kl_table laid out like the DataFrame's value column (table-major, then dimension, then sample)."""
+    t = refmath.kl_table(c["family"], [l.to(dtype) for l in c["locs"]], [s.to(dtype) for s in c["scales"]],
+                         c["loc0"].to(dtype), c["scale0"].to(dtype))
+    return t.permute(0, 2, 1).reshape(-1).double()
+
+
 def main():
     assert ref_inplace.available(), "needs /root/reference"
+    for c in kl_df_cases():
+        ref = run_reference_kl_df(c)
+        mine = oracle_kl_df_values(c)
+        worst = float((mine - ref["values"]).abs().max() / ref["values"].abs().max())
+        assert worst < 1e-6, (c["name"], worst)
+        print("%-22s make_kl_df worst rel diff vs reference %.2e (%d rows)" % (c["name"], worst, mine.numel()))
     for c in unimodal_cases():
         worst = compare(run_reference_unimodal(c), run_oracle_unimodal(c), c["name"])
         print("%-22s unimodal worst rel diff vs reference %.2e" % (c["name"], worst))

@@ -451,6 +451,40 @@ def test_dreg_combine(ops, M, L, K, B):
         assert rel(x, y) < 5e-5  # batch sums of O(B) terms in fp32 feed a softmax
 
 
+@pytest.mark.parametrize("lik", ["normal", "laplace"])
+def test_lprob_selfscale(ops, lik):
+    """lprob with padding masks: the reference overwrites the likelihood scale with the cropped loc (objectives.py:43-45),
+    i.e. dist(loc = x, scale = x).log_prob(t); a negative mean gives log(negative) = NaN -> value 0 (:423) and, through
+    autograd's zeroed upstream gradient, gradient 0."""
+    import torch.distributions as dist
+    g = torch.Generator().manual_seed(19)
+    K, B, shape = 2, 5, (6, 8)
+    x = torch.randn(K * B, *shape, generator=g)
+    x = torch.where(x.abs() < 0.05, torch.full_like(x, 0.3), x)  # keep 1/x^2 gradients well conditioned
+    t = torch.rand(B, *shape, generator=g)
+    w = torch.randn(K * B, generator=g)
+    xo = x.double().clone().requires_grad_(True)
+    d = (dist.Laplace if lik == "laplace" else dist.Normal)(xo, torch.tensor(0.75, dtype=torch.float64), validate_args=False)
+    d.scale = xo
+    out = d.log_prob(t.double().repeat(K, 1, 1)).view(K * B, -1)
+    assert torch.isnan(out).any()
+    out = out.clone()
+    out[torch.isnan(out)] = 0
+    ref = 0.37 * out.sum(-1)
+    (ref * w.double()).sum().backward()
+    xc = x.cuda().requires_grad_(True)
+    rows = ops.loglik_rows(xc, t.cuda(), "lprob_selfscale", lik, 0.37)
+    (rows * w.cuda()).sum().backward()
+    assert rel(rows, ref) < FP32_TOL
+    assert not torch.isnan(xc.grad).any()
+    assert rel(xc.grad, xo.grad) < FP32_TOL
+    # fused (ELBO) pass gives the same rows and gradient
+    xf = x.cuda().requires_grad_(True)
+    S, rows_f = ops.loglik_weighted_sum(xf, t.cuda(), "lprob_selfscale", lik, 0.37, w_rows=w.cuda())
+    S.backward()
+    assert rel(rows_f, ref) < FP32_TOL and rel(xf.grad, xo.grad) < FP32_TOL
+
+
 def test_ops_refuse_cpu_tensors(ops):
     with pytest.raises(RuntimeError):
         ops.loglik_rows(torch.rand(4, 8), torch.rand(4, 8), "bce")

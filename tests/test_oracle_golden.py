@@ -53,3 +53,14 @@ def test_unimodal_restatement_matches_reference(golden):
     assert len(golden["unimodal"]) == 3
     for entry in golden["unimodal"]:
         _cmp(entry["reference"], run_oracle_unimodal(entry["case"]), entry["case"]["name"])
+
+
+def test_kl_table_restatement_matches_reference_make_kl_df(golden):
+    """refmath.kl_table against the frozen DataFrame values of the reference's utils.make_kl_df (utils.py:130-162)."""
+    assert len(golden["kl_df"]) == 3
+    for entry in golden["kl_df"]:
+        c, ref = entry["case"], entry["reference"]
+        t = refmath.kl_table(c["family"], c["locs"], c["scales"], c["loc0"], c["scale0"])
+        mine = t.permute(0, 2, 1).reshape(-1).double()
+        assert mine.shape == ref["values"].shape
+        assert float((mine - ref["values"]).abs().max() / ref["values"].abs().max()) <= RTOL, c["name"]

@@ -29,11 +29,14 @@ def _worker(rank, world, port, q):
     try:
         import mmvae_b200.parallel as par
         res = {}
-        for name, B in (("c2_moe_iwae_cdsprites_l5", 6), ("c4_moe_dreg_mnistsvhn", 9), ("c3_mopoe_elbo_sprites", 6),
-                        ("c1_poe_elbo_cdsprites_l1", 7), ("c3_mopoe_elbo_vilanro", 7), ("c4_moe_dreg_latent_only", 11)):
-            err = torch.tensor([par.sharded_parity(name, B, dist.group.WORLD, dev)], device=dev)
-            dist.all_reduce(err, op=dist.ReduceOp.MAX)
-            res[name] = float(err)
+        peer = par.PeerGroup(dist.group.WORLD, dev)  # collectives fused into our kernels over NVLink peer memory
+        for mode, coll in (("nccl", dist.group.WORLD), ("peer", peer)):
+            for name, B in (("c2_moe_iwae_cdsprites_l5", 6), ("c4_moe_dreg_mnistsvhn", 9), ("c3_mopoe_elbo_sprites", 6),
+                            ("c1_poe_elbo_cdsprites_l1", 7), ("c3_mopoe_elbo_vilanro", 7), ("c4_moe_dreg_latent_only", 11)):
+                err = torch.tensor([par.sharded_parity(name, B, coll, dev)], device=dev)
+                dist.all_reduce(err, op=dist.ReduceOp.MAX)
+                res[mode + ":" + name] = float(err)
+        assert not peer.error(), "a peer-memory wait timed out"
         if rank == 0:
             q.put(res)
     finally:

@@ -25,6 +25,12 @@ done
 # weak scaling of the sweep's largest per-GPU point and the C2 strong split, with the sharded-parity record
 run --workload c4_moe_dreg_latent_only --batch 16384 --steps 20 --warmup 5 --no-cpu-baseline --no-e2e
 run --workload c2_moe_iwae_cdsprites_l5 --global-batch 256 --steps 20 --warmup 5 --no-cpu-baseline --no-e2e --no-parity
+if [ "$N" -gt 1 ]; then
+  # headline workload, weak scaling: collectives fused over peer memory (default) vs NCCL, with the plugin-level e2e
+  run --workload c2_moe_iwae_cdsprites_l5 --steps 20 --warmup 5 --no-cpu-baseline
+  run --workload c2_moe_iwae_cdsprites_l5 --steps 20 --warmup 5 --no-cpu-baseline --no-e2e --no-parity --nccl-only
+  run --workload c4_moe_dreg_latent_only --batch 16384 --steps 20 --warmup 5 --no-cpu-baseline --no-e2e --no-parity --nccl-only
+fi
 python - "$OUT" <<'PY'
 import json, sys
 for l in open(sys.argv[1]):
@@ -33,7 +39,8 @@ for l in open(sys.argv[1]):
         continue
     d = json.loads(l)
     c, r = d['config'], d['roofline']
-    print("%-26s N=%d global B=%-6d (%5d/GPU) %-6s %12.0f samples/s  %8.3f ms/step  step %5.1f%% of HBM peak/GPU  parity_n %s" % (
+    print("%-26s N=%d global B=%-6d (%5d/GPU) %-6s %12.0f samples/s  %8.3f ms/step  step %5.1f%% of HBM peak/GPU  parity_n %s  e2e %s  [%s]" % (
         c['workload'], d['n_gpus'], c['global_batch'], c['batch_per_gpu'], d['scaling'], d['value'], d['ms_per_step'],
-        100 * r['step']['frac'], (d.get('parity_n') or {}).get('max_rel')))
+        100 * r['step']['frac'], (d.get('parity_n') or {}).get('max_rel'), ('%.0f' % d['e2e']['value']) if 'e2e' in d else '-',
+        d['run']['grad_sync'][:28]))
 PY

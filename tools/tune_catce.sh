@@ -7,10 +7,11 @@ cd "$(dirname "$0")/.."
 SRC=multimodal-vae-comparison_b200/csrc
 OUT=gpurun_out/tune_catce; mkdir -p $OUT; rm -f $OUT/lib_*.so
 declare -A V
-V[cur_w2]=""
-V[w4]="-DMMVAE_CATCE_W_LONG=4"
-V[w1]="-DMMVAE_CATCE_W_LONG=1"
-V[v2_cols]="-DMMVAE_CATCE_IMPL=2"
+V[r1_staged]="-DMMVAE_CATCE_PAIRS=0"
+V[pairs_w4_t0]=""
+V[pairs_w2_t0]="-DMMVAE_CATCE_PAIRS_W=2"
+V[pairs_w4_t1]="-DMMVAE_CATCE_PAIRS_STAGE_T=1"
+V[pairs_w2_t1]="-DMMVAE_CATCE_PAIRS_W=2 -DMMVAE_CATCE_PAIRS_STAGE_T=1"
 for k in "${!V[@]}"; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -Iinclude ${V[$k]} -shared $SRC/catce.cu -o $OUT/lib_$k.so -lcudart > $OUT/build_$k.log 2>&1 &
 done
@@ -20,10 +21,9 @@ import ctypes, glob, os, torch
 c_p, c_i, c_i64, c_f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 flush = torch.empty(64 << 20, device="cuda")
 # (name, rows, B, C, d, recon dtype)
-SHAPES = [("c2_text", 7680, 256, 45, 27, torch.float32), ("c5_text_bf16", 4096, 4096, 246, 27, torch.bfloat16),
-          ("c5_text_f32", 4096, 4096, 246, 27, torch.float32), ("mid_c128", 4096, 4096, 128, 27, torch.float32),
-          ("c1_text", 4096, 4096, 7, 27, torch.float32), ("c3_actions", 4096, 4096, 9, 1, torch.float32),
-          ("c3_attrs", 4096, 4096, 4, 6, torch.float32), ("wide_d", 2048, 256, 12, 80, torch.float32)]
+SHAPES = [("c5_text_bf16", 4096, 4096, 246, 27, torch.bfloat16), ("bf16_c128_d27", 4096, 4096, 128, 27, torch.bfloat16),
+          ("bf16_c100_d40", 4096, 1024, 100, 40, torch.bfloat16), ("bf16_c64_d6", 8192, 4096, 64, 6, torch.bfloat16),
+          ("c2_text", 7680, 256, 45, 27, torch.float32), ("c5_text_f32", 4096, 4096, 246, 27, torch.float32)]
 def ref(x, t, rows, B, C, d, w):
     xd = x.double().view(rows, C, d).requires_grad_(True)
     td = t.double().view(B, C, d).repeat(rows // B, 1, 1)
@@ -78,3 +78,4 @@ for name, rows, B, C, d, dt in SHAPES:
 open("gpurun_out/tune_catce/results.txt", "w").write("\n".join(lines) + "\n")
 PY
 grep -l error $OUT/build_*.log | head
+rm -f $OUT/lib_*.so
