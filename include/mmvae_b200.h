@@ -52,6 +52,7 @@ enum { MMVAE_LT_BCE = 0, MMVAE_LT_LPROB_NORMAL = 1, MMVAE_LT_LPROB_LAPLACE = 2, 
        MMVAE_LT_LPROB_NORMAL_SELF = 6, MMVAE_LT_LPROB_LAPLACE_SELF = 7 };
 
 /* peer-memory all-reduce (mmvae_*_peer entry points): layout constants of the per-rank symmetric buffer */
+#define MMVAE_ELBO_MAX_TERMS 48     /* likelihood terms / KL segments of one mmvae_objective_elbo call */
 #define MMVAE_PEER_CHANNELS 8        /* independent call sites / streams                       */
 #define MMVAE_PEER_MAX_WORLD 32      /* ranks of one NVLink domain                             */
 #define MMVAE_PEER_BUFFER_BYTES (72 * 1024) /* bytes to allocate (zeroed) per rank             */
@@ -240,11 +241,13 @@ MMVAE_API int mmvae_moe_logdens_bwd(const float* mu, const float* s, int M, int6
  *   rkc[r,k] = rk_mul * (rk_scale_dev ? *rk_scale_dev : 1) * rk_w[r,k]
  *   coefficient of log q_j(z[r,k,b]) = rkc[r,k] * dlq[r,j,k,b]   (dlq holds softmax_j(lq), required)
  *   coefficient of log p(z[r,k,b])   = -rkc[r,k]                 (dlpz must be NULL)
- * rk_w == NULL: identical to mmvae_moe_logdens_bwd.  Needs D % 4 == 0, D <= 128, M <= 3 and 16-byte aligned buffers (MMVAE_E_LIMIT otherwise). */
+ * rk_w == NULL: identical to mmvae_moe_logdens_bwd.  Needs D % 4 == 0, D <= 128, M <= 3 and 16-byte aligned buffers (MMVAE_E_LIMIT otherwise).
+ * dlq_packed != 0 (rk mode, M == 2, dz_ext given, through_z set): dlq is the (K, B, 4) layout [r*2 + j] written by
+ * mmvae_objective_dreg_stage1_ptrs(soft_packed = 1). */
 MMVAE_API int mmvae_moe_logdens_bwd_rk(const float* mu, const float* s, int M, int64_t B, int D, int K, const int32_t* dists_host,
                              const float* mu0, const float* s0, const float* eps,
                              const float* dz_ext, const float* dlq, const float* dlpz, int through_z,
-                             const float* rk_w, const float* rk_scale_dev, float rk_mul,
+                             const float* rk_w, const float* rk_scale_dev, float rk_mul, int dlq_packed,
                              float* dmu, float* ds, float* dprior_ws, float* dmu0, float* ds0, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -291,15 +294,30 @@ MMVAE_API int mmvae_prior_scale_bwd(const float* s0, const float* ds0, int D, fl
 #define MMVAE_DREG_MAX_SPLIT 64
 MMVAE_API int mmvae_objective_dreg_stage1(const float* lpz, const float* lq, const float* lpx, int M, int L, int K, int64_t B,
                                 double* lw_part, float* lq_soft, void* stream);
-/* same, likelihood rows through a HOST array of M*L device pointers (index r*L + l, (K*B) each): no stack copy */
+/* same, likelihood rows through a HOST array of M*L device pointers (index r*L + l, (K*B) each): no stack copy.
+ * soft_packed != 0 (M == 2 only): lq_soft is written as (K, B, 4) vectors [r*2 + j] -- the layout
+ * mmvae_moe_logdens_bwd_rk reads with one 16-byte copy per (k, b) when its dlq_packed flag is set. */
 MMVAE_API int mmvae_objective_dreg_stage1_ptrs(const float* lpz, const float* lq, const float* lpx,
                                      const float* const* lpx_ptrs_host, int M, int L, int K, int64_t B,
-                                     double* lw_part, float* lq_soft, void* stream);
+                                     double* lw_part, float* lq_soft, int soft_packed, void* stream);
 MMVAE_API int mmvae_objective_dreg_stage2(const double* lw, int M, int K, float* wt, float* loss, void* stream);
 /* DReG backward for the (M,L,K,B) likelihood rows (and log p(z)): d_rows[r,l,k,b] = -(g/M) * wt[r,k], g = *g_dev
  * (upstream gradient of the loss; NULL = 1).  The log q gradients are folded into mmvae_moe_logdens_bwd_rk. */
 MMVAE_API int mmvae_objective_dreg_rowgrads(const float* g_dev, const float* wt, int M, int L, int K, int64_t B,
                                   float* d_rows, void* stream);
+/* ELBO combination -- replaces reference objectives.py:54-67 (BaseObjective.elbo), :316-340 (calculate_loss) and the
+ * model-level sums of mmvae_models.py:181-187 (POE.objective), :314-320 (MoPOE.objective), :455-465 (DMVAE.objective):
+ *   loss = sum_{i<n_terms} coef[i] * sum_{r<n[i]} term_i[r]  +  sum_{j<n_kl} kl_coef[j] * sum_{b<B} kl[j*B + b]
+ *   kld  = sum_j kl_log_coef[j] * sum_b kl[j*B + b]              (the logged "kld"; kld and kl_log_coef may be NULL)
+ *   dkl_unit[j*B + b] = kl_coef[j]   (gradient of the packed KL rows for a unit upstream gradient; may be NULL)
+ * term_ptrs_host / term_n_host / term_coef_host / kl_coef_host / kl_log_coef_host are HOST arrays (copied into the
+ * kernel parameters; at most MMVAE_ELBO_MAX_TERMS entries each); term_i: device fp32 vectors (likelihood row vectors,
+ * or already reduced scalars with n = 1); kl: the packed (n_kl, B) KL rows of mmvae_latent_draws_fwd.  One single-CTA
+ * launch, fixed summation order (deterministic). */
+MMVAE_API int mmvae_objective_elbo(const float* const* term_ptrs_host, const int64_t* term_n_host,
+                         const float* term_coef_host, int n_terms, const float* kl, int64_t B,
+                         const float* kl_coef_host, const float* kl_log_coef_host, int n_kl, float* loss, float* kld,
+                         float* dkl_unit, void* stream);
 MMVAE_API int mmvae_reduce_sum(const float* x, int64_t n, float scale, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -18,6 +18,7 @@ LT_LPROB_NORMAL_SELF, LT_LPROB_LAPLACE_SELF = 6, 7
 DRAW_PRIOR, DRAW_DIRECT, DRAW_LAPLACE, DRAW_ROWMASK = 1, 2, 4, 8
 MAX_MODS, MAX_COLS, MAX_DRAWS, DREG_MAX_SPLIT = 8, 256, 64, 64
 PEER_CHANNELS, PEER_MAX_WORLD, PEER_BUFFER_BYTES = 8, 32, 72 * 1024
+ELBO_MAX_TERMS = 48
 
 
 class DrawDesc(ctypes.Structure):
@@ -54,7 +55,7 @@ SIGNATURES = {
     "mmvae_moe_logdens_bwd": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_i, ctypes.POINTER(ctypes.c_int32), c_p, c_p, c_p,
                                     c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     "mmvae_moe_logdens_bwd_rk": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_i, ctypes.POINTER(ctypes.c_int32), c_p, c_p, c_p,
-                                       c_p, c_p, c_p, c_i, c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_p, c_p]),
+                                       c_p, c_p, c_p, c_i, c_p, c_p, c_f, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     "mmvae_objective_iwae": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i64, c_f, c_p, c_p, c_p, c_p, c_p]),
     "mmvae_objective_iwae_ptrs": (c_i, [c_p, c_p, c_p, ctypes.POINTER(c_p), c_i, c_i, c_i, c_i64, c_f, c_p, c_p, c_p,
                                         c_p, c_p]),
@@ -64,10 +65,13 @@ SIGNATURES = {
     "mmvae_prior_scale_fwd": (c_i, [c_p, c_i, c_p, c_p]),
     "mmvae_prior_scale_bwd": (c_i, [c_p, c_p, c_i, c_p, c_p]),
     "mmvae_objective_dreg_stage1": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i64, c_p, c_p, c_p]),
-    "mmvae_objective_dreg_stage1_ptrs": (c_i, [c_p, c_p, c_p, ctypes.POINTER(c_p), c_i, c_i, c_i, c_i64, c_p, c_p, c_p]),
+    "mmvae_objective_dreg_stage1_ptrs": (c_i, [c_p, c_p, c_p, ctypes.POINTER(c_p), c_i, c_i, c_i, c_i64, c_p, c_p, c_i,
+                                               c_p]),
     "mmvae_objective_dreg_stage2": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p]),
     "mmvae_objective_dreg_rowgrads": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i64, c_p, c_p]),
     "mmvae_reduce_sum": (c_i, [c_p, c_i64, c_f, c_p, c_p]),
+    "mmvae_objective_elbo": (c_i, [ctypes.POINTER(c_p), ctypes.POINTER(c_i64), ctypes.POINTER(c_f), c_i, c_p, c_i64,
+                                   ctypes.POINTER(c_f), ctypes.POINTER(c_f), c_i, c_p, c_p, c_p, c_p]),
     "mmvae_peer_error_offset": (c_i64, []),
     "mmvae_prior_scale_bwd_peer": (c_i, [c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_p]),
     "mmvae_objective_dreg_stage2_peer": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_p]),

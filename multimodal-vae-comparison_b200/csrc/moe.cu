@@ -30,6 +30,7 @@ struct MoeParams {
     // "rk" mode of the backward (DReG): per-(r,k) objective weights folded into the coefficients
     const float *rk_w, *rk_scale;  // (M,K) device weights; optional device scalar
     float rk_mul;
+    int dlq_packed;                // rk mode, M == 2: dlq is (K, B, 4) [r*2 + j] (one 16-byte vector per (k, b))
 };
 
 // -log1p(-a) for a in [0, 1): torch's Laplace.rsample evaluates log1p(-|u|) (laplace.py:84).  The libdevice log1pf
@@ -720,11 +721,15 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 3 : 2) moe_fwd_flat
 //   c_j = rkc[r,k] * dlq[r,j,k,b] (dlq then holds softmax_j(lq)),  c_p = -rkc[r,k],  rkc = rk_mul * (*rk_scale) * rk_w.
 // HOT: the argument pattern of the IWAE / DReG training step is known at compile time (dz_ext and dlq present,
 // through_z set; dlpz present unless rk mode) -- the per-iteration pointer tests of the generic variant go away.
-template <int MT, int LM, int lpr, bool HOT>
+template <int MT, int LM, int lpr, bool HOT, bool PK = false>
 __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 2 : 1) moe_bwd_flat_kernel(const MoeParams p, const int ksplit) {
     __shared__ float red[kFlatWarps * 2 * MT * 4 * 32];
     extern __shared__ float4 ring[];  // per warp: kFlatStages x (2*MT vectors + (MT*MT+MT) scalars) x 32 lanes
-    constexpr int kVecPerStage = 2 * MT * 32, kCofPerStage = (MT * MT + MT) * 32;
+    // packed coefficients (PK: DReG, M == 2, compile time): the four softmax_j(lq) values of a (k, b) arrive as ONE
+    // 16-byte vector, staged as a fifth vector slot of the stage -- one LDGSTS + one LDS.128 at an immediate offset of
+    // the vector ring pointer instead of four 4-byte copies from planes K*B apart through a second ring pointer
+    constexpr bool packed = HOT && MT == 2 && PK;
+    constexpr int kVecPerStage = (2 * MT + (packed ? 1 : 0)) * 32, kCofPerStage = (MT * MT + MT) * 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int pw = wid / ksplit, ks = wid - pw * ksplit, npw = kFlatWarps / ksplit;
     const int rpw = 32 / lpr, cl = lane & (lpr - 1), c = cl * 4;
@@ -733,25 +738,27 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 2 : 1) moe_bwd_flat
     float* mycof = reinterpret_cast<float*>(ring + (size_t)kFlatWarps * kFlatStages * kVecPerStage) +
                    (size_t)wid * kFlatStages * kCofPerStage + lane;
     // slots that are never copied into (inactive lanes, absent dz / dlq / dlpz) must read as zero
-    for (int i = 0; i < kFlatStages * 2 * MT; ++i) myvec[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = 0; i < kFlatStages * (MT * MT + MT); ++i) mycof[i * 32] = 0.f;
+    for (int i = 0; i < kFlatStages * (kVecPerStage / 32); ++i) myvec[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!packed)
+        for (int i = 0; i < kFlatStages * (MT * MT + MT); ++i) mycof[i * 32] = 0.f;
     const uint32_t vec_base = smem_u32(myvec), cof_base = smem_u32(mycof);
     constexpr uint32_t kVecBytes = kVecPerStage * sizeof(float4), kCofBytes = kCofPerStage * sizeof(float);
-    const bool has_dz = HOT || p.dz_ext != nullptr, has_q = HOT || p.dlq != nullptr, rk = p.rk_w != nullptr;
+    const bool has_dz = HOT || p.dz_ext != nullptr, has_q = HOT || p.dlq != nullptr;
+    const bool rk = packed || p.rk_w != nullptr;  // (packed implies rk mode: no dlpz stream at all)
     const bool has_l = HOT ? !rk : p.dlpz != nullptr, thru = HOT || p.through_z != 0;
     bool lap[MT];
 #pragma unroll
     for (int j = 0; j < MT; ++j) lap[j] = LM == 2 ? (p.dist[j] == MMVAE_LAPLACE) : (LM == 1);
     // prior N(mu0, s0): d/dmu0 = c_p df/s0^2, d/ds0 = c_p (df^2/s0^3 - 1/s0); the powers of 1/s0 are applied at the end
     f32x2 PMU[2], NPI2[2], QM[2] = {0ull, 0ull}, QS[2] = {0ull, 0ull};
-    float pinv[4], Cp = 0.f;
+    float Cp = 0.f;
     {
         float pm[4], np2[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             pm[i] = colok ? __ldg(p.mu0 + c + i) : 0.f;
-            pinv[i] = colok ? 1.0f / __ldg(p.s0 + c + i) : 0.f;
-            np2[i] = -pinv[i] * pinv[i];
+            const float pinv = colok ? 1.0f / __ldg(p.s0 + c + i) : 0.f;  // (re-derived at the end: not kept live)
+            np2[i] = -pinv * pinv;
         }
         PMU[0] = f2_pack(pm[0], pm[1]); PMU[1] = f2_pack(pm[2], pm[3]);
         NPI2[0] = f2_pack(np2[0], np2[1]); NPI2[1] = f2_pack(np2[2], np2[3]);
@@ -765,7 +772,7 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 2 : 1) moe_bwd_flat
         // constants (pairs): mu, sigma, 1/sigma (Laplace) or 1/sigma^2 (Normal); accumulators: d/dmu, sum c|df| or
         // sum c df^2, own-sample d/dsigma, sum c
         f32x2 MU[MT][2], SG[MT][2], IV[MT][2], AM[MT][2], S[MT][2], GS[MT][2];
-        float inv[MT][4], Cs[MT];
+        float Cs[MT];
 #pragma unroll
         for (int j = 0; j < MT; ++j) {
             const int64_t o = ((int64_t)j * p.B + b) * p.D + c;
@@ -777,8 +784,8 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 2 : 1) moe_bwd_flat
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 sgv[i] = ok ? ss[i] : 0.f;
-                inv[j][i] = ok ? 1.0f / ss[i] : 0.f;
-                ivp[i] = lap[j] ? inv[j][i] : inv[j][i] * inv[j][i];
+                const float iv = ok ? 1.0f / ss[i] : 0.f;  // (1/s is re-derived from SG after the loop: 8 registers less)
+                ivp[i] = lap[j] ? iv : iv * iv;
             }
             MU[j][0] = f2_pack(m4.x, m4.y); MU[j][1] = f2_pack(m4.z, m4.w);
             SG[j][0] = f2_pack(sgv[0], sgv[1]); SG[j][1] = f2_pack(sgv[2], sgv[3]);
@@ -797,8 +804,9 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 2 : 1) moe_bwd_flat
         const int64_t off = b * p.D + c + (int64_t)ks * BD, offr = b + (int64_t)ks * p.B;
         const float* ek = p.eps + off;  // issue-side running pointers
         const float* dk = has_dz ? p.dz_ext + off : nullptr;
-        const float* qk = has_q ? p.dlq + offr : nullptr;
+        const float* qk = has_q ? (packed ? p.dlq + ((int64_t)ks * p.B + b) * 4 : p.dlq + offr) : nullptr;
         const float* lk = has_l ? p.dlpz + offr : nullptr;
+        const int64_t qstep = packed ? kstep * 4 : kstep;
         int k_issue = ks;
         uint32_t vi = vec_base, ci = cof_base, vr = vec_base, cr = cof_base;  // issue / read positions in the ring
         const uint32_t vec_end = vec_base + kFlatStages * kVecBytes;
@@ -811,20 +819,21 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 2 : 1) moe_bwd_flat
                     if (has_l) cp_async4_s(ci + (MT * MT + r) * 128, lk + r * KB);
 #pragma unroll
                     for (int j = 0; j < MT; ++j)
-                        if (has_q) cp_async4_s(ci + (r * MT + j) * 128, qk + (r * MT + j) * KB);
+                        if (has_q && !packed) cp_async4_s(ci + (r * MT + j) * 128, qk + (r * MT + j) * KB);
                 }
+                if (packed) cp_async16_s(vi + (2 * MT) * 512, qk);
             }
             cp_async_commit();  // (possibly empty) group: keeps the group count uniform
             k_issue += ksplit;
             ek += kstepD;
             if (has_dz) dk += kstepD;
-            if (has_q) qk += kstep;
+            if (has_q) qk += qstep;
             if (has_l) lk += kstep;
             vi += kVecBytes;
-            ci += kCofBytes;
+            if (!packed) ci += kCofBytes;
             if (vi == vec_end) {
                 vi = vec_base;
-                ci = cof_base;
+                if (!packed) ci = cof_base;
             }
         };
 #pragma unroll
@@ -832,6 +841,8 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 2 : 1) moe_bwd_flat
         for (int k = ks; k < p.K; k += ksplit) {
             issue();
             cp_async_wait<kFlatStages - 1>();
+            float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (packed) q4 = lds_f4(vr + (2 * MT) * 512);
 #pragma unroll
             for (int r = 0; r < MT; ++r) {
                 // rk mode: c_j = rkc * softmax_j, c_p = -rkc (inactive lanes: their slots hold zeros, rkc is finite)
@@ -839,7 +850,9 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 2 : 1) moe_bwd_flat
                 float c_[MT];
 #pragma unroll
                 for (int j = 0; j < MT; ++j) {
-                    c_[j] = rkc * lds_f(cr + (r * MT + j) * 128);
+                    const float qv = packed ? (r == 0 ? (j == 0 ? q4.x : q4.y) : (j == 0 ? q4.z : q4.w))
+                                            : lds_f(cr + (r * MT + j) * 128);
+                    c_[j] = rkc * qv;
                     Cs[j] += c_[j];
                 }
                 // (a lane that was active for an earlier row group and is past the batch end now still holds that group's
@@ -857,6 +870,12 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 2 : 1) moe_bwd_flat
                     f32x2 DZL = 0ull;  // d(sum_j c_j log q_j + c_p log p)/dz
 #pragma unroll
                     for (int j = 0; j < MT; ++j) {
+                        // Own posterior with the gradient flowing through z (every IWAE / DReG step): z_r - mu_r =
+                        // s_r * noise, so log q_r(z_r) = -|noise| (or -noise^2/2) - log(norm * s_r) depends on (mu_r,
+                        // s_r) only through -log s_r.  The d/dmu, sum c|df| and d/dz contributions of this term cancel
+                        // EXACTLY in the totals below (P - P; S/s^2 - P*noise): skip them, Cs[j] carries the -c/s part.
+                        // (The generic variant keeps them: with z detached -- MoE-ELBO -- they do not cancel.)
+                        if (HOT && j == r) continue;
                         const f32x2 DF = f2_sub(ZZ, MU[j][h]);
                         if (lap[j]) {
                             // tt = c sign(df) (torch: sign(0) = 0); d/dmu = tt/s; sum c|df| = sum tt*df; d/dz = -tt/s
@@ -889,10 +908,10 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 2 : 1) moe_bwd_flat
                 }
             }
             vr += kVecBytes;
-            cr += kCofBytes;
+            if (!packed) cr += kCofBytes;
             if (vr == vec_end) {
                 vr = vec_base;
-                cr = cof_base;
+                if (!packed) cr = cof_base;
             }
         }
         cp_async_wait<0>();
@@ -902,10 +921,11 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 2 : 1) moe_bwd_flat
         for (int j = 0; j < MT; ++j) {
             const float sv[4] = {f2_lo(S[j][0]), f2_hi(S[j][0]), f2_lo(S[j][1]), f2_hi(S[j][1])};
             const float gv[4] = {f2_lo(GS[j][0]), f2_hi(GS[j][0]), f2_lo(GS[j][1]), f2_hi(GS[j][1])};
+            const float sg4[4] = {f2_lo(SG[j][0]), f2_hi(SG[j][0]), f2_lo(SG[j][1]), f2_hi(SG[j][1])};
             am[j][0] = f2_lo(AM[j][0]); am[j][1] = f2_hi(AM[j][0]); am[j][2] = f2_lo(AM[j][1]); am[j][3] = f2_hi(AM[j][1]);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float iv = inv[j][i], i2 = iv * iv;
+                const float iv = ok ? 1.0f / sg4[i] : 0.f, i2 = iv * iv;
                 fs[j][i] = fmaf(sv[i], lap[j] ? i2 : i2 * iv, fmaf(-Cs[j], iv, gv[i]));
             }
         }
@@ -953,9 +973,9 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 2 : 1) moe_bwd_flat
         const float qsv[4] = {f2_lo(QS[0]), f2_hi(QS[0]), f2_lo(QS[1]), f2_hi(QS[1])};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float pi2 = pinv[i] * pinv[i];
+            const float pinv = colok ? 1.0f / __ldg(p.s0 + c + i) : 0.f, pi2 = pinv * pinv;
             mine[(i * 2 + 0) * 32 + lane] = col_sum<lpr>(qmv[i] * pi2);
-            mine[(i * 2 + 1) * 32 + lane] = col_sum<lpr>(fmaf(qsv[i], pi2 * pinv[i], -Cp * pinv[i]));
+            mine[(i * 2 + 1) * 32 + lane] = col_sum<lpr>(fmaf(qsv[i], pi2 * pinv, -Cp * pinv));
         }
     }
     __syncthreads();
@@ -1011,21 +1031,23 @@ struct FlatPlan {
 typedef void (*moe_flat_kernel_t)(const MoeParams, int);
 
 template <bool FWD, int MT_, int LPR_>
-static moe_flat_kernel_t pick_flat_lm(int lm, bool hot) {
+static moe_flat_kernel_t pick_flat_lm(int lm, bool hot, bool pk) {
 #define MOE_F(LM_)                                                        \
     (FWD ? (moe_flat_kernel_t)moe_fwd_flat_kernel<MT_, LM_, LPR_>         \
-         : (hot && MT_ == 2 && LM_ < 2 ? (moe_flat_kernel_t)moe_bwd_flat_kernel<MT_, LM_, LPR_, (MT_ == 2 && LM_ < 2)> \
-                                       : (moe_flat_kernel_t)moe_bwd_flat_kernel<MT_, LM_, LPR_, false>))
+         : (hot && MT_ == 2 && LM_ < 2                                                                                 \
+                ? (pk ? (moe_flat_kernel_t)moe_bwd_flat_kernel<MT_, LM_, LPR_, (MT_ == 2 && LM_ < 2), (MT_ == 2 && LM_ < 2)> \
+                      : (moe_flat_kernel_t)moe_bwd_flat_kernel<MT_, LM_, LPR_, (MT_ == 2 && LM_ < 2), false>)         \
+                : (moe_flat_kernel_t)moe_bwd_flat_kernel<MT_, LM_, LPR_, false, false>))
     return lm == 0 ? MOE_F(0) : (lm == 1 ? MOE_F(1) : MOE_F(2));
 #undef MOE_F
 }
 template <bool FWD, int MT_>
-static moe_flat_kernel_t pick_flat_lpr(int lpr, int lm, bool hot) {
+static moe_flat_kernel_t pick_flat_lpr(int lpr, int lm, bool hot, bool pk) {
     switch (lpr) {
-        case 4: return pick_flat_lm<FWD, MT_, 4>(lm, hot);
-        case 8: return pick_flat_lm<FWD, MT_, 8>(lm, hot);
-        case 16: return pick_flat_lm<FWD, MT_, 16>(lm, hot);
-        case 32: return pick_flat_lm<FWD, MT_, 32>(lm, hot);
+        case 4: return pick_flat_lm<FWD, MT_, 4>(lm, hot, pk);
+        case 8: return pick_flat_lm<FWD, MT_, 8>(lm, hot, pk);
+        case 16: return pick_flat_lm<FWD, MT_, 16>(lm, hot, pk);
+        case 32: return pick_flat_lm<FWD, MT_, 32>(lm, hot, pk);
     }
     return nullptr;
 }
@@ -1042,9 +1064,33 @@ static moe_flat_kernel_t pick_flat_kernel(const MoeParams& p, FlatPlan* plan) {
     const int64_t ntiles = (p.B + rpw - 1) / rpw;
     int ksplit = 1;
     while (ksplit < kFlatWarps && ntiles * ksplit < (int64_t)kNumSMs * 16 && ksplit * 2 <= p.K) ksplit <<= 1;
+    const int64_t cap = (int64_t)kNumSMs * (FWD ? (p.M <= 2 ? 3 : 2) : (p.M <= 2 ? 2 : 1));
+    // Wave quantisation: the CTAs are persistent over equal-cost row groups, so the last round of a grid-stride loop
+    // runs with (ngroups mod cap) of the cap resident CTAs busy.  r2 sweep, C4 latent-only at B = 16k: 1024 groups
+    // over 444 (forward) / 296 (backward) CTAs = 2.3 / 3.5 rounds -> 77 % / 86 % of the rate at B = 64k.  Splitting K
+    // over more warps makes the groups finer: take the smallest split whose last round is >= 94 % full (each warp
+    // keeps >= 6 k steps so that the staging ring still fills), else the fullest one.
+    auto fill_of = [&](int ks) {
+        const int npw_ = kFlatWarps / ks;
+        const int64_t ng = (ntiles + npw_ - 1) / npw_;
+        if (ng <= cap) return 1.0;
+        const int64_t rounds = (ng + cap - 1) / cap;
+        return (double)ng / (double)(rounds * cap);
+    };
+    {
+        int best = ksplit;
+        double best_fill = fill_of(ksplit);
+        for (int ks = ksplit * 2; ks <= kFlatWarps && ks * 6 <= p.K && best_fill < 0.94; ks <<= 1) {
+            const double f = fill_of(ks);
+            if (f > best_fill + 0.02) {
+                best = ks;
+                best_fill = f;
+            }
+        }
+        ksplit = best;
+    }
     const int npw = kFlatWarps / ksplit;
     const int64_t ngroups = (ntiles + npw - 1) / npw;
-    const int64_t cap = (int64_t)kNumSMs * (FWD ? (p.M <= 2 ? 3 : 2) : (p.M <= 2 ? 2 : 1));
     plan->lpr = lpr;
     plan->ksplit = ksplit;
     plan->grid = (unsigned)(ngroups < cap ? ngroups : cap);
@@ -1053,10 +1099,11 @@ static moe_flat_kernel_t pick_flat_kernel(const MoeParams& p, FlatPlan* plan) {
     const int lm = nlap == 0 ? 0 : (nlap == p.M ? 1 : 2);
     // the training-step argument pattern (IWAE / DReG) gets the variant without per-iteration pointer tests
     const bool hot = !FWD && p.dz_ext && p.dlq && p.through_z && ((p.rk_w != nullptr) != (p.dlpz != nullptr));
+    const bool pk = hot && p.dlq_packed != 0;  // (entry point: only with M == 2, one family, rk mode)
     switch (p.M) {
-        case 1: return pick_flat_lpr<FWD, 1>(lpr, lm, hot);
-        case 2: return pick_flat_lpr<FWD, 2>(lpr, lm, hot);
-        case 3: return pick_flat_lpr<FWD, 3>(lpr, lm, hot);
+        case 1: return pick_flat_lpr<FWD, 1>(lpr, lm, hot, pk);
+        case 2: return pick_flat_lpr<FWD, 2>(lpr, lm, hot, pk);
+        case 3: return pick_flat_lpr<FWD, 3>(lpr, lm, hot, pk);
     }
     return nullptr;
 }
@@ -1126,13 +1173,13 @@ extern "C" int mmvae_moe_logdens_bwd(const float* mu, const float* s, int M, int
                                      const float* dz_ext, const float* dlq, const float* dlpz, int through_z,
                                      float* dmu, float* ds, float* dprior_ws, float* dmu0, float* ds0, void* stream) {
     return mmvae_moe_logdens_bwd_rk(mu, s, M, B, D, K, dists_host, mu0, s0, eps, dz_ext, dlq, dlpz, through_z, nullptr,
-                                    nullptr, 1.0f, dmu, ds, dprior_ws, dmu0, ds0, stream);
+                                    nullptr, 1.0f, 0, dmu, ds, dprior_ws, dmu0, ds0, stream);
 }
 
 extern "C" int mmvae_moe_logdens_bwd_rk(const float* mu, const float* s, int M, int64_t B, int D, int K,
                                         const int32_t* dists_host, const float* mu0, const float* s0, const float* eps,
                                         const float* dz_ext, const float* dlq, const float* dlpz, int through_z,
-                                        const float* rk_w, const float* rk_scale_dev, float rk_mul,
+                                        const float* rk_w, const float* rk_scale_dev, float rk_mul, int dlq_packed,
                                         float* dmu, float* ds, float* dprior_ws, float* dmu0, float* ds0, void* stream) {
     MoeParams p{};
     int rc = moe_fill(p, mu, s, M, B, D, K, dists_host, mu0, s0, eps);
@@ -1140,7 +1187,12 @@ extern "C" int mmvae_moe_logdens_bwd_rk(const float* mu, const float* s, int M, 
     if (!dmu || !ds || !dprior_ws) return MMVAE_E_ARG;
     if (rk_w && (dlpz || !dlq)) return MMVAE_E_ARG;  // rk mode: dlq holds softmax_j(lq), dlpz is implied (-rk)
     p.dz_ext = dz_ext; p.dlq = dlq; p.dlpz = dlpz; p.through_z = through_z; p.dmu = dmu; p.ds = ds; p.ws = dprior_ws;
-    p.rk_w = rk_w; p.rk_scale = rk_scale_dev; p.rk_mul = rk_mul;
+    p.rk_w = rk_w; p.rk_scale = rk_scale_dev; p.rk_mul = rk_mul; p.dlq_packed = dlq_packed;
+    // the packed layout exists in the training-step variant of the flat kernels only
+    if (dlq_packed) {
+        if (!rk_w || M != 2 || !dz_ext || !through_z || !aligned16(dlq)) return MMVAE_E_ARG;
+        if (p.dist[0] != p.dist[1]) return MMVAE_E_ARG;  // mixed families run the generic variant
+    }
     FlatPlan plan;
     if (moe_flat_kernel_t kf = pick_flat_kernel<false>(p, &plan)) {
         const size_t ring = (size_t)kFlatWarps * kFlatStages * 32 * (2 * M * sizeof(float4) + (M * M + M) * sizeof(float));

@@ -241,25 +241,23 @@ class POE(TorchMMVAE):
         mu0, s0 = self._prior()
         res = ops.latent_draws(mu, s, mu0, s0, eps,
                                [Draw(mods=sub, prior=True, kl_mode=1, width=D, K=1) for sub in subsets])
-        total, kl_rows = 0.0, []
+        terms = []
         rec_log = [None] * M
         for a, sub in enumerate(subsets):
             z = res[a]["z"]
-            kl_rows.append(res[a]["kl"])
             for i, name in enumerate(names):
                 vae = self.vaes[name]
                 self.obj_fn.set_ltype(vae.ltype)
                 masks = mods[name]["masks"] if i in sub else None
                 loc = _first(vae.dec({"latents": z, "masks": masks}))
                 S, rows = self.obj_fn.lpx_weighted_sum(loc, mods[name], vae.llik_scaling, w_const=-1.0,
-                                                       ltype=_ltype(vae), family=_family(vae))
-                total = total + S
+                                                       ltype=_ltype(vae), family=_family(vae), defer=True)
+                terms.append(S)
                 if i == a:  # logging quirk: "mod == 'mod_{m+1}'" with m the subset index (:179-180)
-                    rec_log[i] = -ops.reduce_sum(rows) / vae.llik_scaling
-        kl = torch.stack(kl_rows)  # (S,B)
-        loss = total + beta * kl.sum()
-        return {"loss": loss, "reconstruction_loss": [r for r in rec_log if r is not None],
-                "kld": kl.mean(0).sum()}
+                    rec_log[i] = ops.reduce_sum(rows, -1.0 / vae.llik_scaling)
+        # loss = sum_A -(sum_b sum_m lam_m lpx - beta sum_b KL_A), "kld" = sum_b mean_A KL_A[b]: one launch
+        loss, kld = ops.elbo_combine(terms, res.kl_packed, [beta] * len(subsets), [1.0 / len(subsets)] * len(subsets))
+        return {"loss": loss, "reconstruction_loss": [r for r in rec_log if r is not None], "kld": kld}
 
     def modality_mixing(self, x, K=None):
         """mmvae_models.py:210-232: (mu, var-as-scale, {mod: Normal(mu_m, s_m)}) of the present modalities + prior."""
@@ -351,18 +349,19 @@ class MoPOE(TorchMMVAE):
         draws = [Draw(rowmask=True, kl_mode=1 if i == 0 else 0, width=D, K=K) for i in range(M)]
         draws += [Draw(mods=(i,), direct=True, kl_mode=1, width=D) for i in range(M)]
         res = ops.latent_draws(mu, s, mu0, s0, eps, draws, row_masks)
-        total, ind = 0.0, []
+        terms, ind = [], []
         for i, name in enumerate(names):
             vae = self.vaes[name]
             self.obj_fn.set_ltype(vae.ltype)
             loc = _first(vae.dec({"latents": res[i]["z"], "masks": mods[name]["masks"]}))
             S, rows = self.obj_fn.lpx_weighted_sum(loc, mods[name], vae.llik_scaling, w_const=-1.0 / Bt,
-                                                   ltype=_ltype(vae), family=_family(vae))
-            total = total + S
+                                                   ltype=_ltype(vae), family=_family(vae),
+                                                   defer=vae.ltype != "optimal_sigma")
+            terms.append(S)
             ind.append(-rows / vae.llik_scaling)
-        kl_all = torch.stack([res[0]["kl"]] + [res[M + i]["kl"] for i in range(M)])  # joint + unimodal, (M+1,B)
-        gkl = kl_all.sum() / ((M + 1) * Bt)
-        loss = total + beta * gkl
+        # packed KL rows: joint (draw 0) + the M unimodal posteriors; group KL = sum / ((M+1) * B) (objectives.py:184-201)
+        c = 1.0 / ((M + 1) * Bt)
+        loss, gkl = ops.elbo_combine(terms, res.kl_packed, [beta * c] * (M + 1), [c] * (M + 1))
         return {"loss": loss, "reconstruction_loss": ind, "kld": gkl}
 
     def modality_mixing(self, input_batch):
@@ -471,31 +470,29 @@ class DMVAE(TorchMMVAE):
         beta = self.obj_fn.beta
         names, enc, mu, s, res, index = self._run(mods, 1)
         M = len(names)
-        z_joint, kl_joint = res[0]["z"], res[0]["kl"]
-        total, ind, kl_sh_all = 0.0, [], []
+        z_joint = res[0]["z"]
+        terms, ind = [], []
+        # packed KL rows: joint, then (shared_i, private_i) per modality -- their coefficients in the loss / in "kld"
+        kc, kg = [M * beta], [0.0]
         for i, name in enumerate(names):
             vae = self.vaes[name]
             self.obj_fn.set_ltype(vae.ltype)
-            z_sh, kl_sh = res[index["shared"][i]]["z"], res[index["shared"][i]]["kl"]
-            z_pr, kl_pr = res[index["private"][i]]["z"], res[index["private"][i]]["kl"]
+            z_sh, z_pr = res[index["shared"][i]]["z"], res[index["private"][i]]["z"]
             fam, lam, masks = _family(vae), vae.llik_scaling, mods[name]["masks"]
 
             def term(z_a):
                 loc = _first(vae.dec({"latents": torch.cat([z_a, z_pr], -1), "masks": masks}))
-                return self.obj_fn.lpx_weighted_sum(loc, mods[name], lam, w_const=-1.0, ltype=_ltype(vae), family=fam)
+                return self.obj_fn.lpx_weighted_sum(loc, mods[name], lam, w_const=-1.0, ltype=_ltype(vae), family=fam,
+                                                    defer=True)
 
             S1, rows1 = term(z_sh)
-            S2, _ = term(z_joint)
-            total = total + S1 + beta * kl_sh.sum() + S2 + beta * kl_joint.sum()
-            n_cross = 0
-            for j, di in index["cross"][i].items():
-                S3, _ = term(res[di]["z"])
-                total = total + S3
-                n_cross += 1
-            total = total + beta * n_cross * kl_pr.sum()
-            ind.append(-ops.reduce_sum(rows1) / lam)
-            kl_sh_all.append(kl_sh)
-        return {"loss": total, "reconstruction_loss": ind, "kld": torch.stack(kl_sh_all).mean(0).sum()}
+            terms += [S1, term(z_joint)[0]] + [term(res[di]["z"])[0] for di in index["cross"][i].values()]
+            # -(lpx - beta KL_shared) - (lpx_joint - beta KL_joint) - sum_cross (lpx_cross - beta KL_private)  (:455-463)
+            kc += [beta, beta * len(index["cross"][i])]
+            kg += [1.0 / M, 0.0]  # "kld" = sum_b mean_i KL_shared_i[b]
+            ind.append(ops.reduce_sum(rows1, -1.0 / lam))
+        loss, kld = ops.elbo_combine(terms, res.kl_packed, kc, kg)
+        return {"loss": loss, "reconstruction_loss": ind, "kld": kld}
 
     def modality_mixing(self, mods):
         return mods

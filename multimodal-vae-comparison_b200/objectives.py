@@ -131,15 +131,18 @@ class BaseObjective:
         loc, data = self._prep(loc, target)
         return ReconLoss._rows(ltype, loc, data, float(lam), family, self.group, out)
 
-    def lpx_weighted_sum(self, px_z, target, lam=1.0, w_rows=None, w_const=1.0, ltype=None, family=None):
-        """S = sum_r w_r * rows[r] (+ rows for logging) with the gradient produced in the same pass."""
+    def lpx_weighted_sum(self, px_z, target, lam=1.0, w_rows=None, w_const=1.0, ltype=None, family=None, defer=False):
+        """S = sum_r w_r * rows[r] (+ rows for logging) with the gradient produced in the same pass.  defer=True
+        (constant weights): S is a placeholder whose batch sum is taken by ops.elbo_combine together with every
+        other term of the loss (one launch)."""
         loc, family = _loc_family(px_z, family)
         ltype = self._masked_ltype(ltype or self.ltype, target, loc)
         loc, data = self._prep(loc, target)
         if ltype in ELEMENTWISE:
-            return ops.loglik_weighted_sum(loc, data, ltype, family, float(lam), w_rows=w_rows, w_const=w_const)
+            return ops.loglik_weighted_sum(loc, data, ltype, family, float(lam), w_rows=w_rows, w_const=w_const,
+                                           defer=defer)
         if ltype == "category_ce":
-            return ops.catce_weighted_sum(loc, data, float(lam), w_rows=w_rows, w_const=w_const)
+            return ops.catce_weighted_sum(loc, data, float(lam), w_rows=w_rows, w_const=w_const, defer=defer)
         # optimal_sigma needs a global statistic first: two passes regardless
         rows = ReconLoss._rows(ltype, loc, data, float(lam), family, self.group)
         S = torch.dot(rows, w_rows.float()) if w_rows is not None else w_const * rows.sum()

@@ -161,7 +161,7 @@ class _LoglikWeightedSum(torch.autograd.Function):
     gradient in place by grad_output through a kernel that exits immediately when grad_output == 1."""
 
     @staticmethod
-    def forward(ctx, recon, target, w_rows, w_const, lt, scale, lam):
+    def forward(ctx, recon, target, w_rows, w_const, lt, scale, lam, defer=False):
         ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(recon, target, w_rows)
         rows, B = recon.shape[0], target.shape[0]
@@ -177,7 +177,10 @@ class _LoglikWeightedSum(torch.autograd.Function):
         call("mmvae_loglik_rowreduce_fused", _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, P, lt, scale, lam,
              _ptr(w), float(w_const), _ptr(out), _ptr(g), P, _ptr(ws), _stream())
         S = torch.empty((), dtype=torch.float32, device=recon.device)
-        if w is None:
+        if defer:  # the batch sum is left to ops.elbo_combine (one launch for all terms): S is a placeholder
+            if w is not None:
+                raise RuntimeError("mmvae_b200: deferred term sums need a-priori constant weights (w_const)")
+        elif w is None:
             call("mmvae_reduce_sum", _ptr(out), rows, float(w_const), _ptr(S), _stream())
         else:
             S = torch.dot(out, w)
@@ -191,7 +194,7 @@ class _LoglikWeightedSum(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gS, _g_rows):
         if gS is None:
-            return None, None, None, None, None, None, None
+            return None, None, None, None, None, None, None, None
         if ctx.g is None:
             raise RuntimeError("mmvae_b200: the fused ELBO gradient buffer is single-use (retain_graph unsupported)")
         g, ctx.g = ctx.g, None
@@ -199,7 +202,7 @@ class _LoglikWeightedSum(torch.autograd.Function):
         if not _is_unit(gS):  # (the kernel itself exits at once when *gs == 1; a registered unit gradient skips the launch)
             call("mmvae_scale_inplace", _ptr(g), _dt(g), g.numel(), _ptr(gs), _stream())
         gw = (gs * ctx.rows_out) if ctx.w_needs else None
-        return g.view(ctx.shape), None, gw, None, None, None, None
+        return g.view(ctx.shape), None, gw, None, None, None, None, None
 
 
 def _row_out(out, rows, device):
@@ -216,9 +219,20 @@ def loglik_rows(recon, target, ltype, likelihood="normal", lam=1.0, scale=0.75, 
     return _LoglikRows.apply(recon, target, ltype_code(ltype, likelihood), float(scale), float(lam), out)
 
 
-def loglik_weighted_sum(recon, target, ltype, likelihood="normal", lam=1.0, scale=0.75, w_rows=None, w_const=1.0):
-    return _LoglikWeightedSum.apply(recon, target, w_rows, float(w_const), ltype_code(ltype, likelihood),
-                                    float(scale), float(lam))
+def _deferred(S, rows, w_const, defer):
+    """Tag a placeholder S with what ops.elbo_combine needs to do the sum itself: (row vector, coefficient)."""
+    if defer:
+        S._mmvae_deferred = (rows, float(w_const))
+    return S, rows
+
+
+def loglik_weighted_sum(recon, target, ltype, likelihood="normal", lam=1.0, scale=0.75, w_rows=None, w_const=1.0,
+                        defer=False):
+    """defer=True (constant weights only): skip the batch-sum launch; the returned S is only valid as a term of
+    ops.elbo_combine, which sums the row vectors of every term in its single launch."""
+    S, rows = _LoglikWeightedSum.apply(recon, target, w_rows, float(w_const), ltype_code(ltype, likelihood),
+                                       float(scale), float(lam), bool(defer))
+    return _deferred(S, rows, w_const, defer)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -269,7 +283,7 @@ class _CatceRows(torch.autograd.Function):
 
 class _CatceWeightedSum(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, recon, target, w_rows, w_const, lam):
+    def forward(ctx, recon, target, w_rows, w_const, lam, defer=False):
         ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(recon, target, w_rows)
         x, t, rows, B, C, d, ldx, ldt = _catce_geom(recon.detach(), target.detach())
@@ -279,7 +293,10 @@ class _CatceWeightedSum(torch.autograd.Function):
         call("mmvae_catce_rows", 2, _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, C, d, lam, _ptr(w),
              float(w_const), _ptr(out), _ptr(g), C * d, _P(0), _stream())
         S = torch.empty((), dtype=torch.float32, device=recon.device)
-        if w is None:
+        if defer:  # the batch sum is left to ops.elbo_combine (one launch for all terms): S is a placeholder
+            if w is not None:
+                raise RuntimeError("mmvae_b200: deferred term sums need a-priori constant weights (w_const)")
+        elif w is None:
             call("mmvae_reduce_sum", _ptr(out), rows, float(w_const), _ptr(S), _stream())
         else:
             S = torch.dot(out, w)
@@ -293,7 +310,7 @@ class _CatceWeightedSum(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gS, _g_rows):
         if gS is None:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         if ctx.g is None:
             raise RuntimeError("mmvae_b200: the fused ELBO gradient buffer is single-use (retain_graph unsupported)")
         g, ctx.g = ctx.g, None
@@ -301,15 +318,16 @@ class _CatceWeightedSum(torch.autograd.Function):
         if not _is_unit(gS):
             call("mmvae_scale_inplace", _ptr(g), _dt(g), g.numel(), _ptr(gs), _stream())
         gw = (gs * ctx.rows_out) if ctx.w_needs else None
-        return g.view(ctx.shape), None, gw, None, None
+        return g.view(ctx.shape), None, gw, None, None, None
 
 
 def catce_rows(recon, target, lam=1.0, out=None):
     return _CatceRows.apply(recon, target, float(lam), out)
 
 
-def catce_weighted_sum(recon, target, lam=1.0, w_rows=None, w_const=1.0):
-    return _CatceWeightedSum.apply(recon, target, w_rows, float(w_const), float(lam))
+def catce_weighted_sum(recon, target, lam=1.0, w_rows=None, w_const=1.0, defer=False):
+    S, rows = _CatceWeightedSum.apply(recon, target, w_rows, float(w_const), float(lam), bool(defer))
+    return _deferred(S, rows, w_const, defer)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -473,11 +491,17 @@ class _LatentDraws(torch.autograd.Function):
         return dmu, ds, gm0, gs0, None, None, None
 
 
+class DrawResults(list):
+    """Per-draw result dicts of latent_draws; ``kl_packed`` is the kernel's packed KL output (what elbo_combine reads)."""
+    kl_packed = None
+
+
 def latent_draws(mu, s, mu0, s0, eps, draws: List[Draw], row_masks=None):
     """Run a list of draws.  Returns per-draw dicts with views: z (K,B,w) | None, loc/scale (B,w) | None, kl (B) | None."""
     M, B, Dtot = mu.shape
     z, ploc, pscale, kl = _LatentDraws.apply(mu, s, mu0, s0, eps, draws, row_masks)
-    out = []
+    out = DrawResults()
+    out.kl_packed = kl if any(d.kl_mode for d in draws) else None  # (n_kl * B): rows of the draws with a KL, in order
     eo = po = ko = 0
     for d in draws:
         e = {"z": None, "loc": None, "scale": None, "kl": None}
@@ -535,22 +559,27 @@ class _MoeLogdens(torch.autograd.Function):
         rk, ctx.rk = getattr(ctx, "rk", None), None
         rk_w = rk_g = None
         rk_mul = 1.0
+        packed = 0
         if rk is not None:
-            wt, g, mul, soft = rk
+            wt, g, mul, soft, soft_packed = rk
             if dlq is None and dlpz is None and moe_rk_supported(M, D):
-                rk_w, rk_g, rk_mul, dlq = wt, g, mul, soft
+                rk_w, rk_g, rk_mul, dlq, packed = wt, g, mul, soft, int(soft_packed)
+                if packed and dz is None:  # the packed layout exists in the training-step kernel variant only
+                    dz = torch.zeros((M, K, B, D), dtype=torch.float32, device=dev)
             else:  # lq / lpz also feed something else (or an unsupported shape): materialise and add
+                if soft_packed:  # (K, B, M*M) [r*M + j] -> (M, M, K, B)
+                    soft = soft.view(K, B, M, M).permute(2, 3, 0, 1)
                 c = wt * mul if g is None else wt * (g * mul)
                 d1, d2 = c.view(M, 1, K, 1) * soft, (-c).view(M, K, 1).expand(M, K, B)
-                dlq = d1 if dlq is None else dlq + d1
+                dlq = d1.contiguous() if dlq is None else dlq + d1
                 dlpz = d2.contiguous() if dlpz is None else dlpz + d2
         dmu, ds = torch.empty_like(mu_c), torch.empty_like(s_c)
         nws = _lib.load().mmvae_moe_logdens_bwd_ws_floats(B, D, K)
         ws = torch.empty(nws, dtype=torch.float32, device=dev)
         dprior = torch.empty(2, D, dtype=torch.float32, device=dev)
         call("mmvae_moe_logdens_bwd_rk", _ptr(mu_c), _ptr(s_c), M, B, D, K, darr, _ptr(mu0_c), _ptr(s0_c), _ptr(eps_c),
-             _ptr(dz), _ptr(dlq), _ptr(dlpz), through_z, _ptr(rk_w), _ptr(rk_g), float(rk_mul), _ptr(dmu), _ptr(ds),
-             _ptr(ws), _ptr(dprior[0]), _ptr(dprior[1]), _stream())
+             _ptr(dz), _ptr(dlq), _ptr(dlpz), through_z, _ptr(rk_w), _ptr(rk_g), float(rk_mul), packed, _ptr(dmu),
+             _ptr(ds), _ptr(ws), _ptr(dprior[0]), _ptr(dprior[1]), _stream())
         return dmu, ds, dprior[0].reshape(sh0), dprior[1].reshape(sh1), None, None, None
 
 
@@ -769,9 +798,16 @@ class _DregRows(torch.autograd.Function):
         ptrs = (ctypes.c_void_p * (M * L))(*[r.data_ptr() for r in rows_c])
         dev = lpz.device
         part = torch.empty(((_lib.DREG_MAX_SPLIT + 1), M * K), dtype=torch.float64, device=dev)
-        lq_soft = torch.empty((M, M, K, B), dtype=torch.float32, device=dev)
+        # softmax_j(lq) for the backward.  When the MoE backward kernel will fold the log q gradients in (node given,
+        # M == 2, one posterior family, gradient through z), it is written as (K, B, 4) vectors: that kernel then needs
+        # one 16-byte copy per (k, b) instead of four scattered 4-byte ones
+        soft_packed = False
+        if node is not None and M == 2:
+            nM, nB, nD, nK, ndarr, nthru = node.meta[:6]
+            soft_packed = bool(nthru) and moe_rk_supported(nM, nD) and ndarr[0] == ndarr[1]
+        lq_soft = torch.empty((K, B, M * M) if soft_packed else (M, M, K, B), dtype=torch.float32, device=dev)
         call("mmvae_objective_dreg_stage1_ptrs", _ptr(lpz_c), _ptr(lq_c), _P(0), ptrs, M, L, K, B, _ptr(part),
-             _ptr(lq_soft), _stream())
+             _ptr(lq_soft), int(soft_packed), _stream())
         lw = part[0]
         peer, pgroup = _peer(group)
         wt = torch.empty((M, K), dtype=torch.float32, device=dev)
@@ -788,6 +824,7 @@ class _DregRows(torch.autograd.Function):
         ctx.save_for_backward(wt, lq_soft)
         ctx.meta = (M, L, K, B, [r.shape for r in rows])
         ctx.node = node
+        ctx.soft_packed = soft_packed
         lw_out = lw.clone().view(M, K)
         ctx.mark_non_differentiable(lw_out)
         return loss, lw_out
@@ -803,7 +840,7 @@ class _DregRows(torch.autograd.Function):
         call("mmvae_objective_dreg_rowgrads", _ptr(gs), _ptr(wt), M, L, K, B, _ptr(d_rows), _stream())
         row_grads = tuple(d_rows[i // L, i % L].reshape(shapes[i]) for i in range(M * L))
         if ctx.node is not None:
-            ctx.node.rk = (wt, gs, 1.0 / M, lq_soft)
+            ctx.node.rk = (wt, gs, 1.0 / M, lq_soft, ctx.soft_packed)
             return (None, None, None, None, None) + row_grads
         c = wt / M if gs is None else wt * (gs / M)
         return (((-c).view(M, K, 1).expand(M, K, B)), c.view(M, 1, K, 1) * lq_soft, None, None, None) + row_grads
@@ -816,6 +853,74 @@ def dreg_combine_rows(lpz, lq, rows, L, group=None):
     if node is None or node is not lpz.grad_fn or not isinstance(node, _MoeLogdens._backward_cls):
         node = None
     return _DregRows.apply(lpz, lq, int(L), group, node, *rows)
+
+
+class _ElboCombine(torch.autograd.Function):
+    """include/mmvae_b200.h mmvae_objective_elbo: loss = sum_i coef_i * sum(term_i) + sum_j kl_coef_j * sum_b kl[j,b]
+    in one launch.  Differentiable inputs: the packed KL rows and the term scalars S_i (placeholders when their sum was
+    deferred to this launch); `vecs` are the vectors actually read (row vectors or the S_i themselves)."""
+
+    @staticmethod
+    def forward(ctx, kl, kl_coef, kl_log_coef, coefs, vecs, *S):
+        ctx.set_materialize_grads(False)
+        _need_cuda(kl, *vecs)
+        n_t, n_kl = len(vecs), len(kl_coef)
+        if n_t > _lib.ELBO_MAX_TERMS or n_kl > _lib.ELBO_MAX_TERMS:
+            raise RuntimeError("mmvae_b200: elbo_combine takes at most %d terms / KL segments" % _lib.ELBO_MAX_TERMS)
+        dev = (kl if kl is not None else vecs[0]).device
+        B = 0
+        klc = None
+        if n_kl:
+            klc = kl.detach().float().contiguous().reshape(-1)
+            if klc.numel() % n_kl:
+                raise RuntimeError("mmvae_b200: packed KL rows (%d) do not split into %d segments" % (klc.numel(), n_kl))
+            B = klc.numel() // n_kl
+        vs = [v.detach().float().contiguous().reshape(-1) for v in vecs]
+        ptrs = (ctypes.c_void_p * max(n_t, 1))(*[v.data_ptr() for v in vs])
+        ns = (ctypes.c_int64 * max(n_t, 1))(*[v.numel() for v in vs])
+        cf = (ctypes.c_float * max(n_t, 1))(*[float(c) for c in coefs])
+        kc = (ctypes.c_float * max(n_kl, 1))(*[float(c) for c in kl_coef])
+        kg = (ctypes.c_float * max(n_kl, 1))(*[float(c) for c in (kl_log_coef or [0.0] * n_kl)])
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        kld = torch.empty((), dtype=torch.float32, device=dev)  # the logged "kld"
+        dkl = torch.empty(max(n_kl * B, 1), dtype=torch.float32, device=dev) if n_kl else None
+        call("mmvae_objective_elbo", ptrs, ns, cf, n_t, _ptr(klc), B, kc, kg, n_kl, _ptr(loss), _ptr(kld), _ptr(dkl),
+             _stream())
+        ctx.dkl = dkl
+        ctx.n_S = len(S)
+        ctx.kl_shape = None if kl is None else kl.shape
+        ctx.mark_non_differentiable(kld)
+        return loss, kld
+
+    @staticmethod
+    def backward(ctx, g, _gk):
+        if g is None:
+            return (None,) * (5 + ctx.n_S)
+        dkl = None
+        if ctx.dkl is not None:
+            # unit upstream gradient (registered static ones tensor): the forward already wrote the KL-row gradients
+            dkl = ctx.dkl if _is_unit(g) else ctx.dkl * g
+            dkl = dkl.view(ctx.kl_shape)
+        return (dkl, None, None, None, None) + (g,) * ctx.n_S  # every S_i enters with coefficient 1
+
+
+def elbo_combine(terms, kl=None, kl_coef=(), kl_log_coef=None):
+    """loss, kld = sum of the likelihood terms + sum_j kl_coef[j] * sum_b kl[j, b]  (kld: same with kl_log_coef).
+    terms: 0-d tensors S_i from loglik_weighted_sum / catce_weighted_sum (defer=True: their batch sum happens here) or
+    any other differentiable 0-d tensor (coefficient 1).  kl: packed (n_kl * B) KL rows (latent_draws(...).kl_packed)."""
+    vecs, coefs = [], []
+    for S in terms:
+        d = getattr(S, "_mmvae_deferred", None)
+        if d is not None:
+            vecs.append(d[0])
+            coefs.append(d[1])
+        else:
+            vecs.append(S)
+            coefs.append(1.0)
+    return _ElboCombine.apply(kl, tuple(kl_coef), None if kl_log_coef is None else tuple(kl_log_coef), tuple(coefs),
+                              tuple(vecs), *terms)
+
+
 class _KlElementwise(torch.autograd.Function):
     """include/mmvae_b200.h mmvae_kl_elementwise_{fwd,bwd}: (n, D) KL(q || N(loc0, scale0)), prior broadcast over n."""
 

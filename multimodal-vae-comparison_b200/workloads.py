@@ -202,6 +202,9 @@ class LeafStep:
             for t in tensors:
                 if torch.is_tensor(t):
                     t.record_stream(cur)
+                    d = getattr(t, "_mmvae_deferred", None)
+                    if d is not None:  # the row vector ops.elbo_combine reads in place of the placeholder sum
+                        d[0].record_stream(cur)
         self._forked = []
 
     def leaves(self):
@@ -228,17 +231,22 @@ class LeafStep:
             return ops.osigma_rows(self.recon[i], self.targets[tm], m["lam"], self.group, i)
         return ops.loglik_rows(self.recon[i], self.targets[tm], m["ltype"], fam, m["lam"])
 
-    def _wsum(self, i, w_const=1.0, w_rows=None):
+    def _wsum(self, i, w_const=1.0, w_rows=None, defer=False):
+        """defer: leave the batch sum of the term to ops.elbo_combine (one launch for the whole loss)."""
         tm, tag = self.plan[i]
         m = self.cfg["mods"][tm]
         fam = self._family(tm, tag)
         if m["ltype"] == "category_ce":
-            return ops.catce_weighted_sum(self.recon[i], self.targets[tm], m["lam"], w_rows=w_rows, w_const=w_const)
+            return ops.catce_weighted_sum(self.recon[i], self.targets[tm], m["lam"], w_rows=w_rows, w_const=w_const,
+                                          defer=defer)
         if m["ltype"] == "optimal_sigma":
             rows = ops.osigma_rows(self.recon[i], self.targets[tm], m["lam"], self.group, i)
             return (torch.dot(rows, w_rows) if w_rows is not None else w_const * rows.sum()), rows.detach()
         return ops.loglik_weighted_sum(self.recon[i], self.targets[tm], m["ltype"], fam, m["lam"], w_rows=w_rows,
-                                       w_const=w_const)
+                                       w_const=w_const, defer=defer)
+
+    def _osigma(self, i):
+        return self.cfg["mods"][self.plan[i][0]]["ltype"] == "optimal_sigma"
 
     def _prior(self):
         return self._mu0, ops.prior_scale(self.pz_logits, self.peer)
@@ -307,17 +315,14 @@ class LeafStep:
 
         def latent():
             mu0, s0 = self._prior()
-            res = ops.latent_draws(self.mu, self.s, mu0, s0, self.eps_packed,
-                                   [Draw(mods=sub, prior=True, kl_mode=1, width=D, K=1) for sub in subsets])
-            return self.beta * torch.stack([r["kl"] for r in res]).sum()
+            return ops.latent_draws(self.mu, self.s, mu0, s0, self.eps_packed,
+                                    [Draw(mods=sub, prior=True, kl_mode=1, width=D, K=1) for sub in subsets]).kl_packed
 
         kl = self._latent(latent)
-        sums = self._terms(lambda i: self._wsum(i, w_const=-1.0)[0])
+        sums = self._terms(lambda i: self._wsum(i, w_const=-1.0, defer=True)[0])
         self._join(kl, *sums)
-        total = kl
-        for S in sums:
-            total = total + S
-        return total
+        # loss = -sum_A sum_m sum_b lpx + beta sum_A sum_b KL_A: one launch (mmvae_objective_elbo)
+        return ops.elbo_combine(sums, kl, [self.beta] * len(subsets))[0]
 
     def _mopoe(self):
         M, D = self.M, self.D
@@ -326,17 +331,12 @@ class LeafStep:
 
         def latent():
             mu0, s0 = self._prior()
-            res = ops.latent_draws(self.mu, self.s, mu0, s0, self.eps_packed, draws, self.row_masks)
-            kl_all = torch.stack([res[0]["kl"]] + [res[M + i]["kl"] for i in range(M)])
-            return self.beta * kl_all.sum() / ((M + 1) * self.Bt)
+            return ops.latent_draws(self.mu, self.s, mu0, s0, self.eps_packed, draws, self.row_masks).kl_packed
 
-        kl = self._latent(latent)
-        sums = self._terms(lambda i: self._wsum(i, w_const=-1.0 / self.Bt)[0])
+        kl = self._latent(latent)  # packed rows: joint (draw 0), then the M unimodal posteriors
+        sums = self._terms(lambda i: self._wsum(i, w_const=-1.0 / self.Bt, defer=not self._osigma(i))[0])
         self._join(kl, *sums)
-        total = kl
-        for S in sums:
-            total = total + S
-        return total
+        return ops.elbo_combine(sums, kl, [self.beta / ((M + 1) * self.Bt)] * (M + 1))[0]
 
     def _dmvae(self):
         M, D, pv = self.M, self.D, self.pv
@@ -350,20 +350,14 @@ class LeafStep:
 
         def latent():
             mu0, s0 = self._prior()
-            res = ops.latent_draws(self.mu, self.s, mu0, s0, self.eps_packed, draws)
-            kl = 0.0
-            for i in range(M):
-                kl = kl + self.beta * (res[idx[i]]["kl"].sum() + res[0]["kl"].sum()
-                                       + (M - 1) * res[idx[i] + 1]["kl"].sum())
-            return kl
+            return ops.latent_draws(self.mu, self.s, mu0, s0, self.eps_packed, draws).kl_packed
 
         kl = self._latent(latent)
-        sums = self._terms(lambda i: self._wsum(i, w_const=-1.0)[0])
+        sums = self._terms(lambda i: self._wsum(i, w_const=-1.0, defer=True)[0])
         self._join(kl, *sums)
-        total = kl
-        for S in sums:
-            total = total + S
-        return total
+        # packed KL rows: joint, then (shared_i, private_i) per modality; the joint KL enters once per modality, the
+        # private KL once per cross term (reference mmvae_models.py:455-463)
+        return ops.elbo_combine(sums, kl, [M * self.beta] + [self.beta, (M - 1) * self.beta] * M)[0]
 
 
 class GraphedStep:

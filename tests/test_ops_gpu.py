@@ -589,3 +589,50 @@ def test_kl_elementwise_and_objective_api(ops, laplace):
     r, o = run("cpu"), run("cuda")
     for x, y in zip(o, r):
         assert rel(x, y) < FP32_TOL
+
+
+@pytest.mark.parametrize("B,unit", [(5, False), (1000, True), (4099, False)])
+def test_elbo_combine(ops, B, unit):
+    """mmvae_objective_elbo against the eager spelling of reference objectives.py:54-67 / mmvae_models.py:181-187:
+    sum of (deferred and already reduced) likelihood terms + weighted KL row sums, the logged kld, every gradient."""
+    g = torch.Generator().manual_seed(5)
+    dev = "cuda"
+    x = [torch.sigmoid(torch.randn(B, 3, 8, 8, generator=g)).clamp(1e-6, 1 - 1e-6) for _ in range(2)]
+    c = torch.randn(B, 7, 27, generator=g)
+    t_img, t_txt = torch.rand(B, 3, 8, 8, generator=g), torch.softmax(torch.randn(B, 7, 27, generator=g), 1)
+    kl = (torch.rand(3 * B, generator=g) * 4).to(dev).requires_grad_(True)
+    extra = torch.randn((), generator=g).to(dev).requires_grad_(True)  # an already reduced term (coefficient 1)
+    kc, kg = [0.7, 1.3, 2.0], [1 / 3.0, 0.0, 0.5]
+    xs = [a.to(dev).requires_grad_(True) for a in x]
+    cs = c.to(dev).requires_grad_(True)
+    terms = [ops.loglik_weighted_sum(xs[0], t_img.to(dev), "bce", "normal", 0.4, w_const=-1.0, defer=True)[0],
+             ops.loglik_weighted_sum(xs[1], t_img.to(dev), "bce", "normal", 1.0, w_const=-0.25, defer=True)[0],
+             ops.catce_weighted_sum(cs, t_txt.to(dev), 2.0, w_const=-1.0, defer=True)[0], extra]
+    loss, kld = ops.elbo_combine(terms, kl, kc, kg)
+    up = ops.mark_unit_grad(torch.ones((), device=dev)) if unit else torch.tensor(0.37, device=dev)
+    loss.backward(up)
+    # eager reference with the oracle's row functions
+    xo = [a.clone().requires_grad_(True) for a in x]
+    co = c.clone().requires_grad_(True)
+    klo = kl.detach().cpu().clone().requires_grad_(True)
+    eo = extra.detach().cpu().clone().requires_grad_(True)
+    ref = (-refmath.lpx_rows("bce", xo[0], t_img, 0.4, 1, "normal").sum()
+           - 0.25 * refmath.lpx_rows("bce", xo[1], t_img, 1.0, 1, "normal").sum()
+           - refmath.lpx_rows("category_ce", co, t_txt, 2.0, 1, "normal").sum() + eo
+           + sum(kc[j] * klo[j * B:(j + 1) * B].sum() for j in range(3)))
+    ref_kld = sum(kg[j] * klo[j * B:(j + 1) * B].sum() for j in range(3))
+    (ref * float(up)).backward()
+    assert rel(loss, ref) < FP32_TOL and rel(kld, ref_kld) < FP32_TOL
+    assert rel(kl.grad, klo.grad) < FP32_TOL and rel(extra.grad, eo.grad) < FP32_TOL
+    for a, b in zip(xs + [cs], xo + [co]):
+        assert rel(a.grad, b.grad) < FP32_TOL
+    if unit:
+        ops.unmark_unit_grad(up)
+
+
+def test_elbo_combine_limits(ops):
+    z = torch.zeros((), device="cuda", requires_grad=True)
+    with pytest.raises(RuntimeError):
+        ops.elbo_combine([z] * 49)
+    loss, _ = ops.elbo_combine([z + 1.5, z + 2.0])  # no KL segments at all
+    assert abs(float(loss) - 3.5) < 1e-6
