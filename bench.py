@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="N>1: skip the sharded-vs-unsharded numerical check")
+    ap.add_argument("--no-roofline-timer", action="store_true",
+                    help="skip the per-kernel CUDA-event leg (profiling runs under ncu: fewer launches to wade through)")
     ap.add_argument("--nccl-only", action="store_true",
                     help="N>1: every collective through NCCL (default: the small ones fused into our kernels over peer memory)")
     ap.add_argument("--cpu-batch", type=int, default=None,
@@ -269,7 +271,7 @@ class PluginStep:
     """The call a user of the reference makes: model.objective(batch) + backward through the drop-in plugin, batch from
     pinned host memory, replicated-parameter gradients all-reduced (SUM) at N>1, loss read back."""
 
-    def __init__(self, cfg, B, dev, group, world, rank, fused_tail, graphed):
+    def __init__(self, cfg, B, dev, group, world, rank, fused_tail, graphed, fused_enc=False):
         import torch
         import mmvae_b200
         import mmvae_b200.parallel as par
@@ -282,7 +284,7 @@ class PluginStep:
         for i, m in enumerate(cfg["mods"]):
             name = "mod_%d" % (i + 1)
             dz = cfg["D"] + (pv or 0)
-            enc = syn.LinearEncoder(m["data_dim"], dz)
+            enc = syn.LinearEncoder(m["data_dim"], dz, returns_raw_logvar=fused_enc)
             dec = syn.LinearDecoder(dz, m["data_dim"], squash=(m["ltype"] == "bce"), returns_logits=fused_tail)
             vaes[name] = syn.StubVAE(enc, dec, cfg["D"], m["ltype"], private_latents=pv, llik_scaling=m["lam"],
                                      prior_dist=m["dist"], id_name=name)
@@ -302,7 +304,8 @@ class PluginStep:
         self.h2d = sum(v.numel() * v.element_size() for v in self.host.values())
         self.api = "mmvae_b200.%s(vaes, ...).objective(batch) + backward, linear stand-in encoders/decoders (torch), %s%s%s" % (
             cfg["model"], "mmvae_b200.GraphedObjective (one CUDA-graph replay per step)" if graphed else "eager launches",
-            "; decoder tail sigmoid+clamp fused into the likelihood kernel (bce_logits)" if fused_tail else "",
+            ("; decoder tail sigmoid+clamp fused into the likelihood kernel (bce_logits)" if fused_tail else "") +
+            ("; encoder tail softmax+1e-6 fused into the latent kernels" if fused_enc else ""),
             "; flat-bucket NCCL all-reduce(SUM) of the parameter gradients" if world > 1 else "")
 
     def step(self):
@@ -492,7 +495,7 @@ def main():
     kt = KernelTimer(names)
     L.timer = kt
     step.streams = 1  # per-kernel durations: one kernel at a time (the step itself runs two streaming kernels at once)
-    for _ in range(min(K_, 10)):
+    for _ in range(0 if args.no_roofline_timer else min(K_, 10)):
         step.run()
     torch.cuda.synchronize()
     step.streams = args.streams
@@ -558,7 +561,8 @@ def main():
         if not cfg.get("latent_only"):
             e2e_variants = {}
             fused = any(m["ltype"] == "bce" for m in cfg["mods"])
-            for key, kw in (("graphed", dict(fused_tail=fused, graphed=True)), ("eager", dict(fused_tail=False, graphed=False))):
+            for key, kw in (("graphed", dict(fused_tail=fused, graphed=True, fused_enc=True)),
+                            ("eager", dict(fused_tail=False, graphed=False))):
                 if key == "eager" and world > 1:
                     continue
                 try:

@@ -53,6 +53,7 @@ enum { MMVAE_LT_BCE = 0, MMVAE_LT_LPROB_NORMAL = 1, MMVAE_LT_LPROB_LAPLACE = 2, 
 
 /* peer-memory all-reduce (mmvae_*_peer entry points): layout constants of the per-rank symmetric buffer */
 #define MMVAE_ELBO_MAX_TERMS 48     /* likelihood terms / KL segments of one mmvae_objective_elbo call */
+#define MMVAE_ELBO_MAX_CTAS 64      /* grid limit of mmvae_objective_elbo (size of its partials scratch / 2) */
 #define MMVAE_PEER_CHANNELS 8        /* independent call sites / streams                       */
 #define MMVAE_PEER_MAX_WORLD 32      /* ranks of one NVLink domain                             */
 #define MMVAE_PEER_BUFFER_BYTES (72 * 1024) /* bytes to allocate (zeroed) per rank             */
@@ -196,6 +197,19 @@ MMVAE_API int mmvae_latent_draws_bwd(const float* mu, const float* s, int M, int
                            const float* eps, const float* dz, const float* dkl,
                            const float* dpar_loc, const float* dpar_scale,
                            float* dmu, float* ds, float* dprior_ws, float* dmu0, float* ds0, void* stream);
+/* Latent draws with the encoder tail fused in (reference encoders.py:49-54): `s` holds the RAW output
+ * of the encoder's second Linear head (M,B,Dtot); the kernels evaluate s = softmax(raw, -1) + 1e-6 per row themselves.
+ * enc_tail == 0: identical to mmvae_latent_draws_{fwd,bwd}.  s_out (may be NULL): (M,B,Dtot) copy of the scales.  The
+ * backward writes into `ds` the gradient with respect to the raw logits: d/draw = p (d/ds - <d/ds, p>), p = s - 1e-6. */
+MMVAE_API int mmvae_latent_draws_fwd_tail(const float* mu, const float* s, int M, int64_t B, int Dtot,
+                                const mmvae_draw_desc* descs_host, int n_draws, const uint32_t* row_masks,
+                                const float* mu0, const float* s0, const float* eps, float* z, float* par_loc,
+                                float* par_scale, float* kl, int enc_tail, float* s_out, void* stream);
+MMVAE_API int mmvae_latent_draws_bwd_tail(const float* mu, const float* s, int M, int64_t B, int Dtot,
+                                const mmvae_draw_desc* descs_host, int n_draws, const uint32_t* row_masks,
+                                const float* mu0, const float* s0, const float* eps, const float* dz,
+                                const float* dkl, const float* dpar_loc, const float* dpar_scale, int enc_tail,
+                                float* dmu, float* ds, float* dprior_ws, float* dmu0, float* ds0, void* stream);
 
 /* Element-wise KL(q || N(loc0, scale0)): the (n, D) tensor reference calc_kld returns (objectives.py:148-161,
  * utils.py:399-405) and the per-dimension KL tables of the analysis hooks use (utils.py:130-162).  q is Normal or
@@ -230,6 +244,13 @@ MMVAE_API int mmvae_kl_table(const float* loc, const float* scale, int M, const 
 MMVAE_API int mmvae_moe_logdens_fwd(const float* mu, const float* s, int M, int64_t B, int D, int K, const int32_t* dists_host,
                           const float* mu0, const float* s0, const float* eps,
                           float* z, float* lq, float* lpz, void* stream);
+/* same with the encoder tail fused in (reference encoders.py:49-54): s_raw (M,B,D) holds the RAW output
+ * of the encoder's second Linear head, the kernel evaluates s = softmax(s_raw, -1) + 1e-6 itself; s_out (M,B,D, may be
+ * NULL) receives the scales (for the torch.distributions objects the plugin API hands out).  Needs the flat kernels:
+ * D % 4 == 0, D <= 128, M <= 3, 16-byte aligned buffers (MMVAE_E_LIMIT otherwise). */
+MMVAE_API int mmvae_moe_logdens_fwd_tail(const float* mu, const float* s_raw, int M, int64_t B, int D, int K,
+                               const int32_t* dists_host, const float* mu0, const float* s0, const float* eps,
+                               float* z, float* lq, float* lpz, float* s_out, void* stream);
 MMVAE_API int64_t mmvae_moe_logdens_bwd_ws_floats(int64_t B, int D, int K);
 MMVAE_API int mmvae_moe_logdens_bwd(const float* mu, const float* s, int M, int64_t B, int D, int K, const int32_t* dists_host,
                           const float* mu0, const float* s0, const float* eps,
@@ -249,6 +270,13 @@ MMVAE_API int mmvae_moe_logdens_bwd_rk(const float* mu, const float* s, int M, i
                              const float* dz_ext, const float* dlq, const float* dlpz, int through_z,
                              const float* rk_w, const float* rk_scale_dev, float rk_mul, int dlq_packed,
                              float* dmu, float* ds, float* dprior_ws, float* dmu0, float* ds0, void* stream);
+/* same; enc_tail != 0: `s` holds the raw logits of mmvae_moe_logdens_fwd_tail and `ds` receives the gradient with
+ * respect to THEM: d/draw = p (d/ds - <d/ds, p>), p = softmax(raw) (backward through the fused encoder tail). */
+MMVAE_API int mmvae_moe_logdens_bwd_tail(const float* mu, const float* s, int M, int64_t B, int D, int K, const int32_t* dists_host,
+                               const float* mu0, const float* s0, const float* eps,
+                               const float* dz_ext, const float* dlq, const float* dlpz, int through_z,
+                               const float* rk_w, const float* rk_scale_dev, float rk_mul, int dlq_packed, int enc_tail,
+                               float* dmu, float* ds, float* dprior_ws, float* dmu0, float* ds0, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Objective combination (forward value + the per-row weights its backward needs, in one launch):
@@ -312,12 +340,14 @@ MMVAE_API int mmvae_objective_dreg_rowgrads(const float* g_dev, const float* wt,
  *   dkl_unit[j*B + b] = kl_coef[j]   (gradient of the packed KL rows for a unit upstream gradient; may be NULL)
  * term_ptrs_host / term_n_host / term_coef_host / kl_coef_host / kl_log_coef_host are HOST arrays (copied into the
  * kernel parameters; at most MMVAE_ELBO_MAX_TERMS entries each); term_i: device fp32 vectors (likelihood row vectors,
- * or already reduced scalars with n = 1); kl: the packed (n_kl, B) KL rows of mmvae_latent_draws_fwd.  One single-CTA
- * launch, fixed summation order (deterministic). */
+ * or already reduced scalars with n = 1); kl: the packed (n_kl, B) KL rows of mmvae_latent_draws_fwd.  One launch of
+ * up to MMVAE_ELBO_MAX_CTAS CTAs; ws (2 * MMVAE_ELBO_MAX_CTAS floats) and ticket (one zero-initialised unsigned int,
+ * zero again when the kernel ends) let the last CTA add the per-CTA partials in CTA order (deterministic); with
+ * ws == NULL or ticket == NULL a single CTA does everything. */
 MMVAE_API int mmvae_objective_elbo(const float* const* term_ptrs_host, const int64_t* term_n_host,
                          const float* term_coef_host, int n_terms, const float* kl, int64_t B,
                          const float* kl_coef_host, const float* kl_log_coef_host, int n_kl, float* loss, float* kld,
-                         float* dkl_unit, void* stream);
+                         float* dkl_unit, float* ws, unsigned int* ticket, void* stream);
 MMVAE_API int mmvae_reduce_sum(const float* x, int64_t n, float scale, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -18,7 +18,7 @@ LT_LPROB_NORMAL_SELF, LT_LPROB_LAPLACE_SELF = 6, 7
 DRAW_PRIOR, DRAW_DIRECT, DRAW_LAPLACE, DRAW_ROWMASK = 1, 2, 4, 8
 MAX_MODS, MAX_COLS, MAX_DRAWS, DREG_MAX_SPLIT = 8, 256, 64, 64
 PEER_CHANNELS, PEER_MAX_WORLD, PEER_BUFFER_BYTES = 8, 32, 72 * 1024
-ELBO_MAX_TERMS = 48
+ELBO_MAX_TERMS, ELBO_MAX_CTAS = 48, 64
 
 
 class DrawDesc(ctypes.Structure):
@@ -45,6 +45,14 @@ SIGNATURES = {
     "mmvae_latent_draws_bwd_ws_floats": (c_i64, [c_i64, c_i]),
     "mmvae_latent_draws_bwd": (c_i, [c_p, c_p, c_i, c_i64, c_i, ctypes.POINTER(DrawDesc), c_i, c_p, c_p, c_p, c_p,
                                      c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "mmvae_latent_draws_fwd_tail": (c_i, [c_p, c_p, c_i, c_i64, c_i, ctypes.POINTER(DrawDesc), c_i, c_p, c_p, c_p, c_p,
+                                          c_p, c_p, c_p, c_p, c_i, c_p, c_p]),
+    "mmvae_latent_draws_bwd_tail": (c_i, [c_p, c_p, c_i, c_i64, c_i, ctypes.POINTER(DrawDesc), c_i, c_p, c_p, c_p, c_p,
+                                          c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "mmvae_moe_logdens_fwd_tail": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_i, ctypes.POINTER(ctypes.c_int32), c_p, c_p, c_p,
+                                         c_p, c_p, c_p, c_p, c_p]),
+    "mmvae_moe_logdens_bwd_tail": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_i, ctypes.POINTER(ctypes.c_int32), c_p, c_p, c_p,
+                                         c_p, c_p, c_p, c_i, c_p, c_p, c_f, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     "mmvae_kl_elementwise_fwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i64, c_i, c_p, c_p]),
     "mmvae_kl_elementwise_ws_floats": (c_i64, [c_i64, c_i]),
     "mmvae_kl_elementwise_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i64, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
@@ -71,7 +79,7 @@ SIGNATURES = {
     "mmvae_objective_dreg_rowgrads": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i64, c_p, c_p]),
     "mmvae_reduce_sum": (c_i, [c_p, c_i64, c_f, c_p, c_p]),
     "mmvae_objective_elbo": (c_i, [ctypes.POINTER(c_p), ctypes.POINTER(c_i64), ctypes.POINTER(c_f), c_i, c_p, c_i64,
-                                   ctypes.POINTER(c_f), ctypes.POINTER(c_f), c_i, c_p, c_p, c_p, c_p]),
+                                   ctypes.POINTER(c_f), ctypes.POINTER(c_f), c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     "mmvae_peer_error_offset": (c_i64, []),
     "mmvae_prior_scale_bwd_peer": (c_i, [c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_p]),
     "mmvae_objective_dreg_stage2_peer": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_p]),
@@ -85,6 +93,8 @@ launch_count = 0
 _LAUNCHES = {"mmvae_loglik_rowreduce_fwd": 1, "mmvae_loglik_rowreduce_bwd": 1, "mmvae_loglik_rowreduce_fused": 1,
              "mmvae_catce_rows": 1, "mmvae_osigma_sumsq": 1, "mmvae_osigma_fwd": 1, "mmvae_osigma_bwd": 2,
              "mmvae_latent_draws_fwd": 1, "mmvae_latent_draws_bwd": 2, "mmvae_moe_logdens_fwd": 1,
+             "mmvae_latent_draws_fwd_tail": 1, "mmvae_latent_draws_bwd_tail": 2, "mmvae_moe_logdens_fwd_tail": 1,
+             "mmvae_moe_logdens_bwd_tail": 2,
              "mmvae_moe_logdens_bwd": 2, "mmvae_moe_logdens_bwd_rk": 2, "mmvae_objective_iwae": 1, "mmvae_objective_iwae_fused": 1, "mmvae_objective_dreg_stage1": 2, "mmvae_objective_dreg_stage1_ptrs": 2,
              "mmvae_objective_dreg_stage2": 1, "mmvae_reduce_sum": 1, "mmvae_scale_inplace": 1}
 

@@ -11,6 +11,8 @@
 //     slowed the streaming backward from 21.7 to 35.6 us and left the forward unchanged -- both slabs stay staged)
 //   * two passes over the class axis (max, then exp-sum / target sums: one MUFU.EX2 per element), warp-shuffle row
 //     sum; the gradient is written in place over the staged x and leaves through one TMA bulk store.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mmvae {
@@ -26,6 +28,7 @@ struct CatceParams {
     int C, d, R, W, tma;
     int G;               // rows a warp works on at once (32 / d for d < 32, else 1): lane -> (row in group, column)
     int S, TS;           // ring kernel: x stages, target slots
+    int npw, lg_ns, same_rows;  // resident kernel: periods per warp, log2 of the merge segment, rows == B
     float inv_n, inv_d;  // v2 flat backward: 1/(C*d), 1/d for the exact float-reciprocal index split
     float lam, w_const;
 };
@@ -366,7 +369,28 @@ __global__ void __launch_bounds__(512) catce_kernel(const CatceParams p) {
 #ifndef MMVAE_CATCE_PAIRS_STAGE_T
 #define MMVAE_CATCE_PAIRS_STAGE_T 0
 #endif
-constexpr int kPairCh = 8;  // periods per register chunk: 8 words per tensor in flight per lane
+// STAGE_X = 0 (r2, measured and rejected; kept as a build option): x not staged either -- the words of a lane's streams
+// come straight from global memory in register chunks (pass 1 allocates in L1, pass 2 re-reads the slice from L1 / L2),
+// the gradient goes straight back, ~15 KB of shared memory per CTA.  C5 captions (4096 x 246 x 27 bf16), fused:
+// 63.9 us (R4 W4) / 60.2 us (R4 W2) against 59.8 us for the TMA-staged form -- neither the TMA round trip nor the
+// occupancy is the limit.  The SASS is: 16 (pass 1) / 22 (pass 2) instructions per element, 57 % of them 64-bit
+// address arithmetic and bounds predicates of the strided word accesses (run-time period length).  Hence DT below.
+#ifndef MMVAE_CATCE_PAIRS_STAGE_X
+#define MMVAE_CATCE_PAIRS_STAGE_X 1
+#endif
+#ifndef MMVAE_CATCE_RESIDENT
+#define MMVAE_CATCE_RESIDENT 1
+#endif
+#ifndef MMVAE_CATCE_RESIDENT_OCC
+#define MMVAE_CATCE_RESIDENT_OCC 3  // CTAs of 256 threads per SM the register allocation aims for
+#endif
+#ifndef MMVAE_CATCE_RESIDENT_MINW
+#define MMVAE_CATCE_RESIDENT_MINW 1
+#endif
+#ifndef MMVAE_CATCE_PAIRS_CH
+#define MMVAE_CATCE_PAIRS_CH 8
+#endif
+constexpr int kPairCh = MMVAE_CATCE_PAIRS_CH;  // periods per register chunk: words per tensor in flight per lane
 
 __device__ __forceinline__ f32x2 bf2_to_f2(uint32_t w) { return f2_pack(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
 __device__ __forceinline__ uint32_t f2_to_bf2(f32x2 v) {
@@ -377,16 +401,20 @@ __device__ __forceinline__ uint32_t f2_to_bf2(f32x2 v) {
     return r;
 }
 
-template <int MODE, bool STAGE_T>  // MODE 0: forward (+ statistics), 2: fused value + gradient
+// DT: compile-time d (27 = the character vocabulary of every text modality of the reference, datasets.py / config_cub;
+// 0 = run-time d).  With it the period length is an immediate: the word accesses of a register chunk become
+// [pointer + constant] operands of one running pointer per tensor instead of a 64-bit multiply-add each.
+template <int MODE, bool STAGE_T, bool STAGE_X, int DT>  // MODE 0: forward (+ statistics), 2: fused value + gradient
 __global__ void __launch_bounds__(512) catce_pairs_kernel(const CatceParams p) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    const int n = p.C * p.d, R = p.R, W = p.W, d = p.d;
+    const int d = DT ? DT : p.d;
+    const int n = p.C * d, R = p.R, W = p.W;
     const bool odd = (d & 1) != 0;
     const int Pw = odd ? d : d / 2;        // words per period
     const int NP = odd ? p.C / 2 : p.C;    // periods per row
     const int NPAR = odd ? 2 : 1;
     uint32_t* sx = reinterpret_cast<uint32_t*>(smraw);
-    size_t off = up16((size_t)R * n * 2);
+    size_t off = STAGE_X ? up16((size_t)R * n * 2) : 0;
     uint32_t* stg = reinterpret_cast<uint32_t*>(smraw + off);
     if (STAGE_T) off += up16((size_t)R * n * 2);
     float* s_lse = reinterpret_cast<float*>(smraw + off);  // R*d merged logsumexp
@@ -399,13 +427,15 @@ __global__ void __launch_bounds__(512) catce_pairs_kernel(const CatceParams p) {
     const int64_t row0 = (int64_t)blockIdx.x * R;
     const __nv_bfloat16* xg = reinterpret_cast<const __nv_bfloat16*>(p.x);
     const __nv_bfloat16* tg = reinterpret_cast<const __nv_bfloat16*>(p.t);
-    if (threadIdx.x == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t bx = (uint32_t)((size_t)R * n * 2);
-        mbar_expect_tx(bar, STAGE_T ? 2 * bx : bx);
-        bulk_g2s(sx, xg + row0 * p.ldx, bx, bar);
-        if (STAGE_T) bulk_g2s(stg, tg + (row0 % p.B) * p.ldt, bx, bar);
+    if (STAGE_X || STAGE_T) {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bx = (uint32_t)((size_t)R * n * 2);
+            mbar_expect_tx(bar, (STAGE_T ? bx : 0) + (STAGE_X ? bx : 0));
+            if (STAGE_X) bulk_g2s(sx, xg + row0 * p.ldx, bx, bar);
+            if (STAGE_T) bulk_g2s(stg, tg + (row0 % p.B) * p.ldt, bx, bar);
+        }
     }
     // this lane's two streams: (parity, column) of the low and the high half of its word
     const bool lane_ok = lane < Pw;
@@ -416,23 +446,32 @@ __global__ void __launch_bounds__(512) catce_pairs_kernel(const CatceParams p) {
         else if (lane > h) { parL = parH = 1; colL = 2 * lane - d; colH = colL + 1; }
     }
     const int NPw = (NP + W - 1) / W, q_lo = w * NPw, q_hi = min(NP, q_lo + NPw);
-    const uint32_t* rx = sx + (size_t)rl * (n / 2) + lane;
+    const uint32_t* rx = STAGE_X ? sx + (size_t)rl * (n / 2) + lane
+                                 : reinterpret_cast<const uint32_t*>(xg + (row0 + rl) * p.ldx) + lane;
     const uint32_t* rt = STAGE_T ? stg + (size_t)rl * (n / 2) + lane
                                  : reinterpret_cast<const uint32_t*>(tg + ((row0 + rl) % p.B) * p.ldt) + lane;
-    if (warp == 0) mbar_wait(bar, 0);
-    __syncthreads();
+    if (STAGE_X || STAGE_T) {
+        if (warp == 0) mbar_wait(bar, 0);
+        __syncthreads();
+    }
 
     // ---- pass 1: online softmax statistics of the two streams over this warp's periods ------------------------------
     float mL = -INFINITY, mH = -INFINITY;
     f32x2 SE = 0ull, TS = 0ull, TX = 0ull;
     const f32x2 L2E = f2_bcast(kLog2e);
     if (lane_ok) {
-        for (int q0 = q_lo; q0 < q_hi; q0 += kPairCh) {
+        // (a chunk that lies entirely inside the slice -- all but the last -- runs without per-word bounds tests: the
+        // body is instantiated twice, `full` is a compile-time constant in each copy)
+        auto chunk1 = [&](const int q0, auto full_tag) {
+            constexpr bool full = decltype(full_tag)::value;
             uint32_t xw[kPairCh], tw[kPairCh];
+            const uint32_t* cx = rx + q0 * Pw;  // one pointer per tensor and chunk; u * Pw is an immediate when DT != 0
+            const uint32_t* ct = rt + q0 * Pw;
 #pragma unroll
-            for (int u = 0; u < kPairCh; ++u) xw[u] = q0 + u < q_hi ? rx[(q0 + u) * Pw] : 0xff80ff80u;  // -inf pairs
+            for (int u = 0; u < kPairCh; ++u)  // (-inf pairs past the slice; un-staged: L1-allocating read-only loads)
+                xw[u] = (full || q0 + u < q_hi) ? (STAGE_X ? cx[u * Pw] : __ldg(cx + u * Pw)) : 0xff80ff80u;
 #pragma unroll
-            for (int u = 0; u < kPairCh; ++u) tw[u] = q0 + u < q_hi ? (STAGE_T ? rt[(q0 + u) * Pw] : __ldg(rt + (q0 + u) * Pw)) : 0u;
+            for (int u = 0; u < kPairCh; ++u) tw[u] = (full || q0 + u < q_hi) ? (STAGE_T ? ct[u * Pw] : __ldg(ct + u * Pw)) : 0u;
             float cL = -INFINITY, cH = -INFINITY;
 #pragma unroll
             for (int u = 0; u < kPairCh; ++u) {
@@ -450,11 +489,14 @@ __global__ void __launch_bounds__(512) catce_pairs_kernel(const CatceParams p) {
                 f2_unpack(f2_fma(X, L2E, NM), a0, a1);
                 SE = f2_add(SE, f2_pack(ex2_ftz(a0), ex2_ftz(a1)));
                 TS = f2_add(TS, T);
-                if (q0 + u < q_hi) TX = f2_fma(T, X, TX);  // (-inf padding: t = 0 but 0 * -inf is NaN)
+                if (full || q0 + u < q_hi) TX = f2_fma(T, X, TX);  // (-inf padding: t = 0 but 0 * -inf is NaN)
             }
             mL = nL;
             mH = nH;
-        }
+        };
+        int q0 = q_lo;
+        for (; q0 + kPairCh <= q_hi; q0 += kPairCh) chunk1(q0, std::true_type{});
+        if (q0 < q_hi) chunk1(q0, std::false_type{});
         part[((size_t)(rl * W + w) * NPAR + parL) * d + colL] = make_float4(mL, f2_lo(SE), f2_lo(TS), f2_lo(TX));
         if (colH < d) part[((size_t)(rl * W + w) * NPAR + parH) * d + colH] = make_float4(mH, f2_hi(SE), f2_hi(TS), f2_hi(TX));
     }
@@ -499,34 +541,233 @@ __global__ void __launch_bounds__(512) catce_pairs_kernel(const CatceParams p) {
         if (lane_ok) {
             const float wl = (p.w_rows ? __ldg(p.w_rows + row0 + rl) : p.w_const) * p.lam;
             const f32x2 NL = f2_pack(-lseL * kLog2e, -lseH * kLog2e), WTS = f2_pack(-wl * tsL, -wl * tsH), WL = f2_bcast(wl);
-            uint32_t* gx = sx + (size_t)rl * (n / 2) + lane;  // in place over the staged x
-            for (int q0 = q_lo; q0 < q_hi; q0 += kPairCh) {
+            // gradient: in place over the staged x (one bulk store per CTA), or straight to global memory
+            uint32_t* gx = STAGE_X ? sx + (size_t)rl * (n / 2) + lane
+                                   : reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.g) + (row0 + rl) * p.ldg) + lane;
+            auto chunk2 = [&](const int q0, auto full_tag) {
+                constexpr bool full = decltype(full_tag)::value;
                 uint32_t xw[kPairCh], tw[kPairCh];
+                const uint32_t* cx = rx + q0 * Pw;
+                const uint32_t* ct = rt + q0 * Pw;
+                uint32_t* cg = gx + q0 * Pw;
 #pragma unroll
-                for (int u = 0; u < kPairCh; ++u) xw[u] = q0 + u < q_hi ? rx[(q0 + u) * Pw] : 0u;
+                for (int u = 0; u < kPairCh; ++u)
+                    xw[u] = (full || q0 + u < q_hi) ? (STAGE_X ? cx[u * Pw] : __ldg(cx + u * Pw)) : 0u;
 #pragma unroll
-                for (int u = 0; u < kPairCh; ++u) tw[u] = q0 + u < q_hi ? (STAGE_T ? rt[(q0 + u) * Pw] : __ldg(rt + (q0 + u) * Pw)) : 0u;
+                for (int u = 0; u < kPairCh; ++u) tw[u] = (full || q0 + u < q_hi) ? (STAGE_T ? ct[u * Pw] : __ldg(ct + u * Pw)) : 0u;
 #pragma unroll
                 for (int u = 0; u < kPairCh; ++u) {
                     float a0, a1;
                     f2_unpack(f2_fma(bf2_to_f2(xw[u]), L2E, NL), a0, a1);
                     const f32x2 G = f2_fma(f2_pack(ex2_ftz(a0), ex2_ftz(a1)), WTS, f2_mul(WL, bf2_to_f2(tw[u])));
-                    if (q0 + u < q_hi) gx[(q0 + u) * Pw] = f2_to_bf2(G);
+                    if (full || q0 + u < q_hi) cg[u * Pw] = f2_to_bf2(G);
                 }
-            }
+            };
+            int q0 = q_lo;
+            for (; q0 + kPairCh <= q_hi; q0 += kPairCh) chunk2(q0, std::true_type{});
+            if (q0 < q_hi) chunk2(q0, std::false_type{});
         }
-        fence_async_smem();  // generic-proxy smem writes -> visible to the async (TMA) proxy
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            bulk_s2g(reinterpret_cast<__nv_bfloat16*>(p.g) + row0 * p.ldg, sx, (uint32_t)((size_t)R * n * 2));
-            bulk_wait_read();  // smem must stay alive until the bulk store has read it
+        if (STAGE_X) {
+            fence_async_smem();  // generic-proxy smem writes -> visible to the async (TMA) proxy
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                bulk_s2g(reinterpret_cast<__nv_bfloat16*>(p.g) + row0 * p.ldg, sx, (uint32_t)((size_t)R * n * 2));
+                bulk_wait_read();  // smem must stay alive until the bulk store has read it
+            }
         }
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Register-resident rows (r2): ONE row per CTA, W = ceil(periods / 16) warps; a lane loads ITS words of the warp's
+// <= 16 periods of x and of t up front -- 32 independent 4-byte loads in flight per lane, one global round trip -- and
+// keeps them in registers through the statistics pass, the single barrier of the column merge and the gradient pass;
+// the gradient goes straight back to global memory.  No staging, no TMA round trip, no second read of anything.
+// ncu on the TMA-staged form above at the C5 captions (4096 x 246 x 27 bf16, fused, 49.7 us): issue-active 49 % at 8
+// warps per scheduler, stalls split between the barrier (3.2 per issue: 16 warps of a CTA wait for its slowest slice),
+// the scoreboard of the chunked target loads (3.3) and fixed-latency waits; DRAM 32 % of peak.  Halving its
+// instruction count (compile-time d) moved it by 2 %: latency bound, not issue bound.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kResCh = 16;
+
+template <int MODE, int DT, int TB>  // TB: threads per CTA bound (256: three CTAs per SM, W <= 8; else 512)
+__global__ void __launch_bounds__(TB, TB == 256 ? MMVAE_CATCE_RESIDENT_OCC : 1) catce_resident_kernel(const CatceParams p) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int d = DT ? DT : p.d;
+    const int W = p.W;
+    const bool odd = (d & 1) != 0;
+    const int Pw = odd ? d : d / 2;      // words per period
+    const int NP = odd ? p.C / 2 : p.C;  // periods per row
+    const int NPAR = odd ? 2 : 1;
+    float4* part = reinterpret_cast<float4*>(smraw);                      // W*NPAR*d partial statistics
+    float* s_lse = reinterpret_cast<float*>(part + (size_t)W * NPAR * d);  // d merged logsumexp
+    float* s_ts = s_lse + d;                                                // d merged sum t
+    float* s_acc = s_ts + d;                                                // W per-warp parts of the row value
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t row = blockIdx.x;
+    const bool lane_ok = lane < Pw;
+    int parL = 0, colL = 2 * lane, parH = 0, colH = 2 * lane + 1;
+    if (odd) {
+        const int h = (d - 1) / 2;
+        if (lane == h) { colL = d - 1; parH = 1; colH = 0; }
+        else if (lane > h) { parL = parH = 1; colL = 2 * lane - d; colH = colL + 1; }
+    }
+    const int NPw = p.npw, q_lo = w * NPw;        // (host: ceil(NP / W); no integer division in the kernel)
+    const int cnt = min(NP, q_lo + NPw) - q_lo;  // <= kResCh (host); <= 0 for warps past the end
+    const int64_t trow = p.same_rows ? row : row % p.B;
+    const uint32_t* rx = reinterpret_cast<const uint32_t*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + row * p.ldx) + lane + q_lo * Pw;
+    const uint32_t* rt = reinterpret_cast<const uint32_t*>(reinterpret_cast<const __nv_bfloat16*>(p.t) + trow * p.ldt) + lane + q_lo * Pw;
+    uint32_t xw[kResCh], tw[kResCh];
+    if (cnt == kResCh && lane_ok) {  // full slice: no per-word bounds tests
+#pragma unroll
+        for (int u = 0; u < kResCh; ++u) xw[u] = ldg_stream_u32(rx + u * Pw);
+#pragma unroll
+        for (int u = 0; u < kResCh; ++u) tw[u] = __ldg(rt + u * Pw);
+    } else {
+#pragma unroll
+        for (int u = 0; u < kResCh; ++u) xw[u] = (lane_ok && u < cnt) ? ldg_stream_u32(rx + u * Pw) : 0xff80ff80u;  // -inf pairs
+#pragma unroll
+        for (int u = 0; u < kResCh; ++u) tw[u] = (lane_ok && u < cnt) ? __ldg(rt + u * Pw) : 0u;
+    }
+    // ---- statistics of the lane's two streams over the slice ---------------------------------------------------
+    float mL = -INFINITY, mH = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < kResCh; ++u) {
+        mL = fmaxf(mL, __uint_as_float(xw[u] << 16));
+        mH = fmaxf(mH, __uint_as_float(xw[u] & 0xffff0000u));
+    }
+    const f32x2 L2E = f2_bcast(kLog2e);
+    f32x2 SE = 0ull, TS = 0ull, TX = 0ull;
+    {
+        const f32x2 NM = f2_pack(mL == -INFINITY ? 0.f : -mL * kLog2e, mH == -INFINITY ? 0.f : -mH * kLog2e);
+#pragma unroll
+        for (int u = 0; u < kResCh; ++u) {
+            const f32x2 X = bf2_to_f2(xw[u]), T = bf2_to_f2(tw[u]);
+            float a0, a1;
+            f2_unpack(f2_fma(X, L2E, NM), a0, a1);
+            SE = f2_add(SE, f2_pack(ex2_ftz(a0), ex2_ftz(a1)));
+            TS = f2_add(TS, T);
+            if (u < cnt) TX = f2_fma(T, X, TX);  // (-inf padding: t = 0 but 0 * -inf is NaN)
+        }
+    }
+    if (lane_ok) {
+        part[((size_t)w * NPAR + parL) * d + colL] = make_float4(mL, f2_lo(SE), f2_lo(TS), f2_lo(TX));
+        if (colH < d) part[((size_t)w * NPAR + parH) * d + colH] = make_float4(mH, f2_hi(SE), f2_hi(TS), f2_hi(TX));
+    }
+    __syncthreads();
+    // ---- merge, spread over the CTA: warp w takes the column groups w, w + W, ...; a group is GC = 32 / NS columns, the
+    // NS = pow2 >= W*NPAR lanes of a column hold ONE partial each and combine them with log2(NS) shuffle steps.  (The
+    // first version had every warp merge all d columns over all W*NPAR partials in two serial loops: ~250 dependent
+    // instructions per warp, as many as the two passes over its data.)
+    const int np = W * NPAR;
+    const int NS = 1 << p.lg_ns;  // (host: pow2 >= np)
+    const int GC = 32 >> p.lg_ns, sub = lane & (NS - 1), cg_i = lane >> p.lg_ns;
+    float accw = 0.f;
+    for (int j0 = w * GC; j0 < d; j0 += W * GC) {
+        const int j = j0 + cg_i;
+        const bool have = j < d && sub < np;
+        const float4 v = have ? part[(size_t)sub * d + j] : make_float4(-INFINITY, 0.f, 0.f, 0.f);
+        // segmented butterflies over the NS lanes of a column: the five steps are unrolled, a step that would cross a
+        // segment is masked by a uniform predicate (a run-time trip count cost a branch + a register shuffle per step)
+        float mm = v.x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_xor_sync(0xffffffffu, mm, o);
+            mm = o < NS ? fmaxf(mm, t) : mm;
+        }
+        const float nm = mm == -INFINITY ? 0.f : -mm * kLog2e;
+        float se = have ? v.y * ex2_ftz(fmaf(v.x, kLog2e, nm)) : 0.f, ts = v.z, txs = v.w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float a = __shfl_xor_sync(0xffffffffu, se, o), b = __shfl_xor_sync(0xffffffffu, ts, o),
+                        c = __shfl_xor_sync(0xffffffffu, txs, o);
+            if (o < NS) {
+                se += a;
+                ts += b;
+                txs += c;
+            }
+        }
+        if (j < d && sub == 0) {
+            const float lse = mm + logf(se);
+            s_lse[j] = lse;
+            s_ts[j] = ts;
+            accw += txs - lse * ts;
+            if (p.stats) {
+                p.stats[row * 2 * d + j] = lse;
+                p.stats[row * 2 * d + d + j] = ts;
+            }
+        }
+    }
+    accw = warp_sum(accw);
+    if (lane == 0) s_acc[w] = accw;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f;
+        for (int q = 0; q < W; ++q) a += s_acc[q];  // fixed order
+        p.out_rows[row] = p.lam * a;
+    }
+    if (MODE == 2) {
+        const float lseL = s_lse[min(colL, d - 1)], tsL = s_ts[min(colL, d - 1)];
+        const float lseH = s_lse[min(colH, d - 1)], tsH = s_ts[min(colH, d - 1)];
+        if (lane_ok && cnt > 0) {
+            const float wl = (p.w_rows ? __ldg(p.w_rows + row) : p.w_const) * p.lam;
+            const f32x2 NL = f2_pack(-lseL * kLog2e, -lseH * kLog2e), WTS = f2_pack(-wl * tsL, -wl * tsH), WL = f2_bcast(wl);
+            uint32_t* cg = reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.g) + row * p.ldg) + lane + q_lo * Pw;
+#pragma unroll
+            for (int u = 0; u < kResCh; ++u) {
+                float a0, a1;
+                f2_unpack(f2_fma(bf2_to_f2(xw[u]), L2E, NL), a0, a1);
+                const f32x2 G = f2_fma(f2_pack(ex2_ftz(a0), ex2_ftz(a1)), WTS, f2_mul(WL, bf2_to_f2(tw[u])));
+                if (u < cnt) stg_stream_u32(cg + u * Pw, f2_to_bf2(G));
+            }
+        }
+    }
+}
+
+// bf16 / bf16 rows whose periods fit 16 per warp with <= 16 warps: register-resident kernel; false otherwise
+static bool launch_catce_resident(int mode, CatceParams p, cudaStream_t st, int* rc) {
+#if MMVAE_CATCE_RESIDENT
+    const int d = p.d;
+    if (mode == 1 || p.C < 64) return false;
+    if ((d & 1) ? (d > 31 || (p.C & 1)) : d > 64) return false;
+    const int NP = (d & 1) ? p.C / 2 : p.C, npar = (d & 1) ? 2 : 1;
+    int W = (NP + kResCh - 1) / kResCh;
+    if (W > 16) return false;
+    const int Pw = (d & 1) ? d : d / 2;
+    if (Pw < 24) return false;  // a lane per word of a period: shorter periods leave most of the warp idle
+    if (W < MMVAE_CATCE_RESIDENT_MINW) W = MMVAE_CATCE_RESIDENT_MINW;
+    // 4-byte words: even row strides and 4-byte aligned bases
+    const bool ok = (p.ldx % 2 == 0) && (p.ldt % 2 == 0) && (mode == 0 || p.ldg % 2 == 0) && ((p.C * d) % 2 == 0) &&
+                    (reinterpret_cast<uintptr_t>(p.x) % 4 == 0) && (reinterpret_cast<uintptr_t>(p.t) % 4 == 0) &&
+                    (mode == 0 || reinterpret_cast<uintptr_t>(p.g) % 4 == 0);
+    if (!ok) return false;
+    p.R = 1;
+    p.W = W;
+    p.npw = (NP + W - 1) / W;
+    p.lg_ns = 0;
+    while ((1 << p.lg_ns) < W * npar) ++p.lg_ns;
+    p.same_rows = p.rows == p.B;
+    const size_t smem = (size_t)W * npar * d * 16 + 2 * d * 4 + 16 * 4;
+    void (*k)(const CatceParams);
+    if (W <= 8)
+        k = d == 27 ? (mode == 0 ? catce_resident_kernel<0, 27, 256> : catce_resident_kernel<2, 27, 256>)
+                    : (mode == 0 ? catce_resident_kernel<0, 0, 256> : catce_resident_kernel<2, 0, 256>);
+    else
+        k = d == 27 ? (mode == 0 ? catce_resident_kernel<0, 27, 512> : catce_resident_kernel<2, 27, 512>)
+                    : (mode == 0 ? catce_resident_kernel<0, 0, 512> : catce_resident_kernel<2, 0, 512>);
+    k<<<(unsigned)p.rows, W * 32, smem, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    *rc = e == cudaSuccess ? 0 : (int)e;
+    return true;
+#else
+    (void)mode; (void)p; (void)st; (void)rc;
+    return false;
+#endif
+}
+
 static size_t pairs_smem(int R, int W, int n, int d, bool stage_t) {
     const int npar = (d & 1) ? 2 : 1;
-    size_t off = up16((size_t)R * n * 2) * (stage_t ? 2 : 1);
+    size_t off = up16((size_t)R * n * 2) * ((stage_t ? 1 : 0) + (MMVAE_CATCE_PAIRS_STAGE_X ? 1 : 0));
     off = up16(off + (size_t)2 * R * d * 4);
     return off + (size_t)R * W * npar * d * 16 + 16;
 }
@@ -546,7 +787,9 @@ static bool launch_catce_pairs(int mode, CatceParams p, cudaStream_t st, int* rc
     p.R = R;
     p.W = W;
     const size_t smem = pairs_smem(R, W, n, d, MMVAE_CATCE_PAIRS_STAGE_T);
-    auto k = mode == 0 ? catce_pairs_kernel<0, MMVAE_CATCE_PAIRS_STAGE_T != 0> : catce_pairs_kernel<2, MMVAE_CATCE_PAIRS_STAGE_T != 0>;
+    constexpr bool kST = MMVAE_CATCE_PAIRS_STAGE_T != 0, kSX = MMVAE_CATCE_PAIRS_STAGE_X != 0;
+    auto k = d == 27 ? (mode == 0 ? catce_pairs_kernel<0, kST, kSX, 27> : catce_pairs_kernel<2, kST, kSX, 27>)
+                     : (mode == 0 ? catce_pairs_kernel<0, kST, kSX, 0> : catce_pairs_kernel<2, kST, kSX, 0>);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { *rc = (int)e; return true; }
@@ -1071,6 +1314,7 @@ extern "C" int mmvae_catce_rows(int mode, const void* recon, int64_t ld_recon, i
     if (dtype_recon == MMVAE_BF16 && dtype_target == MMVAE_F32) return launch_catce<__nv_bfloat16, float>(mode, p, st);
     if (dtype_recon == MMVAE_BF16 && dtype_target == MMVAE_BF16) {
         int rc = 0;
+        if (launch_catce_resident(mode, p, st, &rc)) return rc;
         if (launch_catce_pairs(mode, p, st, &rc)) return rc;
         return launch_catce<__nv_bfloat16, __nv_bfloat16>(mode, p, st);
     }

@@ -25,9 +25,14 @@ struct DrawsParams {
     float *dmu, *ds, *ws;                     // backward outputs
     int64_t B;
     int M, Dtot, n;
+    // encoder tail fused in (reference encoders.py:49-54): `s` holds the raw logits of the encoder's second head, a warp
+    // evaluates s = softmax(raw, -1) + 1e-6 for its row into shared memory before it runs the draws; s_out: optional
+    // (M,B,Dtot) copy of the scales; the backward returns d/draw = p (d/ds - <d/ds, p>), p = s - 1e-6
+    int enc_tail;
+    float* s_out;
     mmvae_draw_desc d[MMVAE_MAX_DRAWS];
 };
-static_assert(sizeof(DrawsParams) <= 4000, "kernel parameter block too large");
+static_assert(sizeof(DrawsParams) <= 4050, "kernel parameter block too large");
 
 __device__ __forceinline__ float noise_eff(float e, bool laplace) {
     // Normal: z = loc + scale*eps.  Laplace (torch laplace.py:73-84): z = loc - scale*sign(u)*log1p(-|u|)
@@ -48,14 +53,43 @@ __device__ __forceinline__ void desc_mask(const DrawsParams& p, const mmvae_draw
     }
 }
 
-// loc / scale of one column; Tsum returned for the backward
+constexpr float kEncEta = 1e-6f;  // reference utils.Constants.eta
+
+// Fused encoder tail: s_row[m*Dtot + c] = softmax(raw[m, b, :])[c] + eta for the warp's row b (lanes stride over the
+// columns, two warp reductions per modality).
+__device__ __forceinline__ void stage_scales(const DrawsParams& p, int64_t b, float* s_row, int lane) {
+    for (int m = 0; m < p.M; ++m) {
+        const float* raw = p.s + ((int64_t)m * p.B + b) * p.Dtot;
+        float mx = -INFINITY;
+        for (int c = lane; c < p.Dtot; c += 32) mx = fmaxf(mx, __ldg(raw + c));
+        mx = warp_max(mx);
+        float se = 0.f;
+        for (int c = lane; c < p.Dtot; c += 32) {
+            const float e = expf(__ldg(raw + c) - mx);
+            s_row[m * p.Dtot + c] = e;
+            se += e;
+        }
+        se = warp_sum(se);
+        const float inv = 1.0f / se;
+        for (int c = lane; c < p.Dtot; c += 32) {
+            const float v = s_row[m * p.Dtot + c] * inv + kEncEta;
+            s_row[m * p.Dtot + c] = v;
+            if (p.s_out) p.s_out[((int64_t)m * p.B + b) * p.Dtot + c] = v;
+        }
+    }
+    __syncwarp();
+}
+
+// loc / scale of one column; Tsum returned for the backward.  s_row: the row's scales in shared memory (fused
+// encoder tail) or NULL (scales read from p.s)
 __device__ __forceinline__ void fuse_column(const DrawsParams& p, const mmvae_draw_desc& d, uint32_t mask, bool prior,
-                                            int64_t b, int c, float& loc, float& scale, float& Tsum) {
+                                            int64_t b, int c, float& loc, float& scale, float& Tsum,
+                                            const float* s_row = nullptr) {
     if (d.flags & MMVAE_DRAW_DIRECT) {
         const int m = __ffs(mask) - 1;
         const int64_t o = ((int64_t)m * p.B + b) * p.Dtot + c;
         loc = __ldg(p.mu + o);
-        scale = __ldg(p.s + o);
+        scale = s_row ? s_row[m * p.Dtot + c] : __ldg(p.s + o);
         Tsum = 0.f;
         return;
     }
@@ -65,7 +99,7 @@ __device__ __forceinline__ void fuse_column(const DrawsParams& p, const mmvae_dr
     for (int m = 0; m < p.M; ++m) {
         if (!((mask >> m) & 1u)) continue;
         const int64_t o = ((int64_t)m * p.B + b) * p.Dtot + c;
-        const float T = 1.0f / (expf(__ldg(p.s + o)) + 1e-8f);
+        const float T = 1.0f / (expf(s_row ? s_row[m * p.Dtot + c] : __ldg(p.s + o)) + 1e-8f);
         ts += T;
         num += __ldg(p.mu + o) * T;
     }
@@ -104,10 +138,16 @@ __device__ __forceinline__ void kl_grads(bool laplace, float l, float sg, float 
 }
 
 __global__ void __launch_bounds__(kWarps * 32) draws_fwd_kernel(const DrawsParams p) {
+    extern __shared__ float sm[];  // fused encoder tail only: (M, Dtot) scales per warp
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+    float* s_row = p.enc_tail ? sm + (size_t)(threadIdx.x >> 5) * p.M * p.Dtot : nullptr;
     for (int64_t b = warp0; b < p.B; b += nwarps) {
+        if (s_row) {
+            __syncwarp();  // the previous row's readers are done
+            stage_scales(p, b, s_row, lane);
+        }
         for (int j = 0; j < p.n; ++j) {
             const mmvae_draw_desc& d = p.d[j];
             uint32_t mask;
@@ -117,7 +157,7 @@ __global__ void __launch_bounds__(kWarps * 32) draws_fwd_kernel(const DrawsParam
             float klacc = 0.f;
             for (int cc = lane; cc < d.width; cc += 32) {
                 float loc, scale, ts;
-                fuse_column(p, d, mask, prior, b, d.col0 + cc, loc, scale, ts);
+                fuse_column(p, d, mask, prior, b, d.col0 + cc, loc, scale, ts, s_row);
                 if (d.par_off >= 0) {
                     p.ploc[d.par_off + b * d.width + cc] = loc;
                     p.pscale[d.par_off + b * d.width + cc] = scale;
@@ -143,16 +183,19 @@ __global__ void __launch_bounds__(kWarps * 32) draws_bwd_kernel(const DrawsParam
     extern __shared__ float sm[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int MD = p.M * p.Dtot;
-    float* acc_mu = sm + (size_t)wid * (2 * MD + 2 * p.Dtot);  // (M, Dtot)
-    float* acc_s = acc_mu + MD;                                  // (M, Dtot)
-    float* pr_mu = acc_s + MD;                                   // (Dtot) learnable prior grads, summed over rows
+    const int per_warp = 2 * MD + 2 * p.Dtot + (p.enc_tail ? MD : 0);
+    float* acc_mu = sm + (size_t)wid * per_warp;  // (M, Dtot)
+    float* acc_s = acc_mu + MD;                   // (M, Dtot)
+    float* pr_mu = acc_s + MD;                    // (Dtot) learnable prior grads, summed over rows
     float* pr_s = pr_mu + p.Dtot;
+    float* s_row = p.enc_tail ? pr_s + p.Dtot : nullptr;  // (M, Dtot) scales of the row (fused encoder tail)
     for (int i = lane; i < 2 * p.Dtot; i += 32) pr_mu[i] = 0.f;
     const int64_t warp0 = (int64_t)blockIdx.x * kWarps + wid;
     const int64_t nwarps = (int64_t)gridDim.x * kWarps;
     for (int64_t b = warp0; b < p.B; b += nwarps) {
         for (int i = lane; i < 2 * MD; i += 32) acc_mu[i] = 0.f;
         __syncwarp();
+        if (s_row) stage_scales(p, b, s_row, lane);
         for (int j = 0; j < p.n; ++j) {
             const mmvae_draw_desc& d = p.d[j];
             uint32_t mask;
@@ -163,7 +206,7 @@ __global__ void __launch_bounds__(kWarps * 32) draws_bwd_kernel(const DrawsParam
             for (int cc = lane; cc < d.width; cc += 32) {
                 const int c = d.col0 + cc;
                 float loc, scale, ts;
-                fuse_column(p, d, mask, prior, b, c, loc, scale, ts);
+                fuse_column(p, d, mask, prior, b, c, loc, scale, ts, s_row);
                 float g_loc = 0.f, g_scale = 0.f;
                 if (p.dz) {
                     for (int k = 0; k < d.K; ++k) {
@@ -198,7 +241,7 @@ __global__ void __launch_bounds__(kWarps * 32) draws_bwd_kernel(const DrawsParam
                     for (int m = 0; m < p.M; ++m) {
                         if (!((mask >> m) & 1u)) continue;
                         const int64_t o = ((int64_t)m * p.B + b) * p.Dtot + c;
-                        const float ex = expf(__ldg(p.s + o));
+                        const float ex = expf(s_row ? s_row[m * p.Dtot + c] : __ldg(p.s + o));
                         const float T = 1.0f / (ex + 1e-8f);
                         const float dT = g_loc * (__ldg(p.mu + o) - loc) * inv_ts - g_scale * inv_ts * inv_ts;
                         acc_mu[m * p.Dtot + c] += g_loc * T * inv_ts;
@@ -207,6 +250,16 @@ __global__ void __launch_bounds__(kWarps * 32) draws_bwd_kernel(const DrawsParam
                 }
             }
             __syncwarp();  // column ownership may move between lanes when col0 changes
+        }
+        if (s_row) {  // back through s = softmax(raw) + eta: d/draw = p (d/ds - <d/ds, p>), p = s - eta
+            for (int m = 0; m < p.M; ++m) {
+                float dot = 0.f;
+                for (int c = lane; c < p.Dtot; c += 32) dot += acc_s[m * p.Dtot + c] * (s_row[m * p.Dtot + c] - kEncEta);
+                dot = warp_sum(dot);
+                for (int c = lane; c < p.Dtot; c += 32)
+                    acc_s[m * p.Dtot + c] = (s_row[m * p.Dtot + c] - kEncEta) * (acc_s[m * p.Dtot + c] - dot);
+            }
+            __syncwarp();
         }
         for (int i = lane; i < MD; i += 32) {
             const int m = i / p.Dtot, c = i - m * p.Dtot;
@@ -220,7 +273,7 @@ __global__ void __launch_bounds__(kWarps * 32) draws_bwd_kernel(const DrawsParam
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * p.Dtot; i += blockDim.x) {
         float tot = 0.f;
-        for (int w = 0; w < kWarps; ++w) tot += sm[(size_t)w * (2 * MD + 2 * p.Dtot) + 2 * MD + i];
+        for (int w = 0; w < kWarps; ++w) tot += sm[(size_t)w * per_warp + 2 * MD + i];
         p.ws[(size_t)blockIdx.x * 2 * p.Dtot + i] = tot;
     }
 }
@@ -341,6 +394,14 @@ extern "C" int mmvae_latent_draws_fwd(const float* mu, const float* s, int M, in
                                       const mmvae_draw_desc* descs_host, int n_draws, const uint32_t* row_masks,
                                       const float* mu0, const float* s0, const float* eps, float* z, float* par_loc,
                                       float* par_scale, float* kl, void* stream) {
+    return mmvae_latent_draws_fwd_tail(mu, s, M, B, Dtot, descs_host, n_draws, row_masks, mu0, s0, eps, z, par_loc,
+                                       par_scale, kl, 0, nullptr, stream);
+}
+
+extern "C" int mmvae_latent_draws_fwd_tail(const float* mu, const float* s, int M, int64_t B, int Dtot,
+                                           const mmvae_draw_desc* descs_host, int n_draws, const uint32_t* row_masks,
+                                           const float* mu0, const float* s0, const float* eps, float* z, float* par_loc,
+                                           float* par_scale, float* kl, int enc_tail, float* s_out, void* stream) {
     DrawsParams p{};
     int rc = fill(p, mu, s, M, B, Dtot, descs_host, n_draws, row_masks, mu0, s0, eps);
     if (rc) return rc;
@@ -350,7 +411,13 @@ extern "C" int mmvae_latent_draws_fwd(const float* mu, const float* s, int M, in
         if (p.d[j].kl_mode != 0 && p.d[j].kl_off >= 0 && !kl) return MMVAE_E_ARG;
     }
     p.z = z; p.ploc = par_loc; p.pscale = par_scale; p.kl = kl;
-    draws_fwd_kernel<<<draws_grid(B), kWarps * 32, 0, (cudaStream_t)stream>>>(p);
+    p.enc_tail = enc_tail; p.s_out = s_out;
+    const size_t smem_f = enc_tail ? (size_t)kWarps * M * Dtot * sizeof(float) : 0;  // <= 8 * 8 * 256 * 4 = 64 KB
+    if (smem_f > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(draws_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+        if (e != cudaSuccess) return (int)e;
+    }
+    draws_fwd_kernel<<<draws_grid(B), kWarps * 32, smem_f, (cudaStream_t)stream>>>(p);
     MMVAE_LAUNCH_CHECK();
     return 0;
 }
@@ -364,14 +431,25 @@ extern "C" int mmvae_latent_draws_bwd(const float* mu, const float* s, int M, in
                                       const float* mu0, const float* s0, const float* eps, const float* dz,
                                       const float* dkl, const float* dpar_loc, const float* dpar_scale, float* dmu,
                                       float* ds, float* dprior_ws, float* dmu0, float* ds0, void* stream) {
+    return mmvae_latent_draws_bwd_tail(mu, s, M, B, Dtot, descs_host, n_draws, row_masks, mu0, s0, eps, dz, dkl,
+                                       dpar_loc, dpar_scale, 0, dmu, ds, dprior_ws, dmu0, ds0, stream);
+}
+
+extern "C" int mmvae_latent_draws_bwd_tail(const float* mu, const float* s, int M, int64_t B, int Dtot,
+                                           const mmvae_draw_desc* descs_host, int n_draws, const uint32_t* row_masks,
+                                           const float* mu0, const float* s0, const float* eps, const float* dz,
+                                           const float* dkl, const float* dpar_loc, const float* dpar_scale,
+                                           int enc_tail, float* dmu, float* ds, float* dprior_ws, float* dmu0, float* ds0,
+                                           void* stream) {
     DrawsParams p{};
     int rc = fill(p, mu, s, M, B, Dtot, descs_host, n_draws, row_masks, mu0, s0, eps);
     if (rc) return rc;
     if (!dmu || !ds || !dprior_ws) return MMVAE_E_ARG;
     if ((dpar_loc == nullptr) != (dpar_scale == nullptr)) return MMVAE_E_ARG;
     p.dz = dz; p.dkl = dkl; p.dploc = dpar_loc; p.dpscale = dpar_scale; p.dmu = dmu; p.ds = ds; p.ws = dprior_ws;
+    p.enc_tail = enc_tail;
     const unsigned grid = draws_grid(B);
-    const size_t smem = (size_t)kWarps * (2 * M * Dtot + 2 * Dtot) * sizeof(float);
+    const size_t smem = (size_t)kWarps * (2 * M * Dtot + 2 * Dtot + (enc_tail ? M * Dtot : 0)) * sizeof(float);
     if (smem > 200 * 1024) return MMVAE_E_LIMIT;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(draws_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -31,6 +31,16 @@ struct MoeParams {
     const float *rk_w, *rk_scale;  // (M,K) device weights; optional device scalar
     float rk_mul;
     int dlq_packed;                // rk mode, M == 2: dlq is (K, B, 4) [r*2 + j] (one 16-byte vector per (k, b))
+    // 64-bit element strides of the flat kernels, computed once on the host: as kernel parameters they are operands
+    // straight from the constant bank.  r2 SASS: computed in the kernel, ptxas re-derived K*B*D and K*B (12-instruction
+    // 64-bit multiply chains) inside the k loop of every kernel rather than hold them in registers -- ~45 of the 266
+    // instructions of a forward k step.
+    int64_t sBD, sKBD, sKB, sKstepD, sKstep;
+    // Encoder tail fused in (reference encoders.py:49-54: s = softmax(raw, -1) + 1e-6): `s` then holds the RAW logits of
+    // the encoder's second head; the flat kernels evaluate the row softmax themselves (a row is the lpr lanes of a
+    // row group: two butterflies), the backward returns d/draw = p (d/ds - <d/ds, p>), p = s - 1e-6.
+    int enc_tail;
+    float* s_out;  // forward: optional (M,B,D) copy of the scales for the distributions the plugin API hands out
 };
 
 // -log1p(-a) for a in [0, 1): torch's Laplace.rsample evaluates log1p(-|u|) (laplace.py:84).  The libdevice log1pf
@@ -512,7 +522,7 @@ __device__ __forceinline__ float lg2_ftz(float x) {
 // (r1 used an 8-term Taylor series below 1/8 and a rounding-residual correction d/w through MUFU.RCP above: 1.3e-6
 // relative and 7 more instructions per element).  The branch value is selected per element; its sign never matters
 // because the result takes the sign of u (copysign).
-__device__ __forceinline__ f32x2 laplace_noise2(f32x2 E) {
+__device__ __forceinline__ f32x2 laplace_noise2(f32x2 E, f32x2* mag = nullptr) {
     const f32x2 A = f2_abs(E);
     const f32x2 W = f2_sub(f2_bcast(1.0f), A);
     float w0, w1, a0, a1, e0, e1, s0, s1, t0, t1;
@@ -529,7 +539,9 @@ __device__ __forceinline__ f32x2 laplace_noise2(f32x2 E) {
     f2_unpack(E, e0, e1);
     f2_unpack(SM, s0, s1);
     f2_unpack(T, t0, t1);
-    return f2_pack(copysignf(a0 < 0.25f ? s0 : t0, e0), copysignf(a1 < 0.25f ? s1 : t1, e1));
+    const float m0 = a0 < 0.25f ? s0 : -t0, m1 = a1 < 0.25f ? s1 : -t1;  // -log1p(-|u|) >= 0 (t = log1p(-|u|) <= 0)
+    if (mag) *mag = f2_pack(m0, m1);
+    return f2_pack(copysignf(m0, e0), copysignf(m1, e1));
 }
 
 __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
@@ -547,6 +559,31 @@ __device__ __forceinline__ float row_sum(float v) {
     for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+template <int LPR>
+__device__ __forceinline__ float row_max(float v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+constexpr float kEncEta = 1e-6f;  // reference utils.Constants.eta
+// s = softmax(raw, -1) + eta over the row owned by a group of LPR lanes (4 columns per lane; lanes that are not `ok`
+// contribute nothing).  Executed by whole warps (shuffles).
+template <int LPR>
+__device__ __forceinline__ void enc_tail_row(float (&v)[4], bool ok) {
+    float mx = ok ? fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])) : -INFINITY;
+    mx = row_max<LPR>(mx);
+    float e[4], se = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        e[i] = ok ? expf(v[i] - mx) : 0.f;
+        se += e[i];
+    }
+    se = row_sum<LPR>(se);
+    const float inv = 1.0f / se;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = ok ? e[i] * inv + kEncEta : 1.f;
+}
+
 // sum over the lanes of a warp that own the same columns (same lane % LPR)
 template <int LPR>
 __device__ __forceinline__ float col_sum(float v) {
@@ -584,7 +621,7 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 3 : 2) moe_fwd_flat
     }
     pc = row_sum<lpr>(pc);
     const int64_t ntiles = (p.B + rpw - 1) / rpw;
-    const int64_t BD = p.B * p.D;
+    const int64_t BD = p.sBD;
     for (int64_t t = (int64_t)blockIdx.x * npw + pw; t < ntiles; t += (int64_t)gridDim.x * npw) {
         const int64_t b = t * rpw + lane / lpr;
         const bool ok = colok && b < p.B;
@@ -596,7 +633,12 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 3 : 2) moe_fwd_flat
             const int64_t o = ((int64_t)j * p.B + b) * p.D + c;
             const float4 m4 = ok ? __ldg(reinterpret_cast<const float4*>(p.mu + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 s4 = ok ? __ldg(reinterpret_cast<const float4*>(p.s + o)) : make_float4(1.f, 1.f, 1.f, 1.f);
-            const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+            const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+            float ss[4] = {s4.x, s4.y, s4.z, s4.w};
+            if (p.enc_tail) {  // uniform: s holds raw logits
+                enc_tail_row<lpr>(ss, ok);
+                if (p.s_out && ok && ks == 0) *reinterpret_cast<float4*>(p.s_out + o) = make_float4(ss[0], ss[1], ss[2], ss[3]);
+            }
             float cst = 0.f, sgv[4], iv[4], nm[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -612,8 +654,8 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 3 : 2) moe_fwd_flat
             rc[j] = row_sum<lpr>(cst);
         }
         // running pointers: one 64-bit add per tensor and k step instead of a fresh (r, k, b, c) product per access
-        const int64_t KBD = (int64_t)p.K * BD, KB = (int64_t)p.K * p.B;
-        const int64_t kstepD = (int64_t)ksplit * BD, kstep = (int64_t)ksplit * p.B;
+        const int64_t KBD = p.sKBD, KB = p.sKB;
+        const int64_t kstepD = p.sKstepD, kstep = p.sKstep;
         const float* ek = p.eps + b * p.D + c + (int64_t)ks * BD;  // issue-side running pointer
         float* zk = p.z + b * p.D + c + (int64_t)ks * BD;
         float* lqk = p.lq + b + (int64_t)ks * p.B;
@@ -649,19 +691,34 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 3 : 2) moe_fwd_flat
             for (int r = 0; r < MT; ++r) {
                 const f32x2 E[2] = {f2_pack(e[r].x, e[r].y), f2_pack(e[r].z, e[r].w)};
                 f32x2 ZZ[2], ACC[MT], AP = 0ull;
+                float accl[MT];  // Laplace |u| sums of the OTHER posteriors: scalar adds take |x| as an operand modifier
 #pragma unroll
-                for (int j = 0; j < MT; ++j) ACC[j] = 0ull;
+                for (int j = 0; j < MT; ++j) {
+                    ACC[j] = 0ull;
+                    accl[j] = 0.f;
+                }
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const f32x2 EF = lap[r] ? laplace_noise2(E[h]) : E[h];
+                    f32x2 MAG = 0ull;
+                    const f32x2 EF = lap[r] ? laplace_noise2(E[h], &MAG) : E[h];
                     ZZ[h] = f2_fma(EF, SG[r][h], MU[r][h]);
 #pragma unroll
                     for (int j = 0; j < MT; ++j) {
                         // own posterior: (z - mu_r)/s_r IS the transformed noise (what an exact evaluation gives; the
                         // reference recovers it from the rounded z, |difference| <= ulp(z)/s_r).  Others: z/s_j - mu_j/s_j
                         // as one FMA (error <= ulp(mu_j/s_j), negligible against |u| ~ 1/s_j).
-                        const f32x2 U = j == r ? EF : f2_fma(ZZ[h], INV[j][h], NM[j][h]);
-                        ACC[j] = lap[j] ? f2_add(ACC[j], f2_abs(U)) : f2_fma(U, U, ACC[j]);
+                        if (j == r) {
+                            // Laplace: |noise| is the magnitude the transform produced before it took the sign of u
+                            ACC[j] = lap[j] ? f2_add(ACC[j], MAG) : f2_fma(EF, EF, ACC[j]);
+                        } else {
+                            const f32x2 U = f2_fma(ZZ[h], INV[j][h], NM[j][h]);
+                            if (lap[j]) {  // two FADD with |.| modifiers instead of two LOP3 + one FADD2
+                                accl[j] += fabsf(f2_lo(U));
+                                accl[j] += fabsf(f2_hi(U));
+                            } else {
+                                ACC[j] = f2_fma(U, U, ACC[j]);
+                            }
+                        }
                     }
                     const f32x2 U0 = f2_fma(ZZ[h], PINV[h], PNM[h]);
                     AP = f2_fma(U0, U0, AP);
@@ -672,7 +729,7 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 3 : 2) moe_fwd_flat
                 }
                 part[r][MT] = f2_lo(AP) + f2_hi(AP);
 #pragma unroll
-                for (int j = 0; j < MT; ++j) part[r][j] = f2_lo(ACC[j]) + f2_hi(ACC[j]);
+                for (int j = 0; j < MT; ++j) part[r][j] = f2_lo(ACC[j]) + f2_hi(ACC[j]) + accl[j];
             }
             // row sums of the MT*(MT+1) partials.  MT == 2 and >= 2 lanes per row: the first butterfly step TRANSPOSES
             // (lanes of the lower half of a row group keep the r = 0 partials and send their r = 1 ones, the upper half
@@ -765,7 +822,7 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 2 : 1) moe_bwd_flat
     }
     const float rk_mul = p.rk_w ? p.rk_mul * (p.rk_scale ? __ldg(p.rk_scale) : 1.0f) : 0.f;
     const int64_t ntiles = (p.B + rpw - 1) / rpw, ngroups = (ntiles + npw - 1) / npw;
-    const int64_t BD = p.B * p.D;
+    const int64_t BD = p.sBD;
     for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
         const int64_t b = (g * npw + pw) * rpw + lane / lpr;
         const bool ok = colok && b < p.B;
@@ -778,7 +835,8 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 2 : 1) moe_bwd_flat
             const int64_t o = ((int64_t)j * p.B + b) * p.D + c;
             const float4 m4 = ok ? __ldg(reinterpret_cast<const float4*>(p.mu + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 s4 = ok ? __ldg(reinterpret_cast<const float4*>(p.s + o)) : make_float4(1.f, 1.f, 1.f, 1.f);
-            const float ss[4] = {s4.x, s4.y, s4.z, s4.w};
+            float ss[4] = {s4.x, s4.y, s4.z, s4.w};
+            if (p.enc_tail) enc_tail_row<lpr>(ss, ok);  // uniform: s holds raw logits
             float sgv[4], ivp[4];
             Cs[j] = 0.f;
 #pragma unroll
@@ -799,8 +857,8 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 2 : 1) moe_bwd_flat
         // copied itself, completion is tracked by cp.async groups).  r2 ncu before this: the un-prefetched scalar
         // coefficient loads stalled every iteration (long scoreboard 5.2 per issue, issue-active 39 % at 16 warps/SM),
         // and a register double buffer of the same depth spilled at the 128-register budget of two CTAs per SM.
-        const int64_t KBD = (int64_t)p.K * BD, KB = (int64_t)p.K * p.B;
-        const int64_t kstepD = (int64_t)ksplit * BD, kstep = (int64_t)ksplit * p.B;
+        const int64_t KBD = p.sKBD, KB = p.sKB;
+        const int64_t kstepD = p.sKstepD, kstep = p.sKstep;
         const int64_t off = b * p.D + c + (int64_t)ks * BD, offr = b + (int64_t)ks * p.B;
         const float* ek = p.eps + off;  // issue-side running pointers
         const float* dk = has_dz ? p.dz_ext + off : nullptr;
@@ -956,6 +1014,21 @@ __global__ void __launch_bounds__(kFlatWarps * 32, MT <= 2 ? 2 : 1) moe_bwd_flat
                     }
             }
         }
+        if (p.enc_tail && ks == 0) {  // warp-uniform: back through s = softmax(raw) + eta
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+                const float sg4[4] = {f2_lo(SG[j][0]), f2_hi(SG[j][0]), f2_lo(SG[j][1]), f2_hi(SG[j][1])};
+                float pr[4], dot = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    pr[i] = ok ? sg4[i] - kEncEta : 0.f;
+                    dot += ok ? fs[j][i] * pr[i] : 0.f;
+                }
+                dot = row_sum<lpr>(dot);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) fs[j][i] = pr[i] * (fs[j][i] - dot);
+            }
+        }
         if (ok && ks == 0) {
 #pragma unroll
             for (int j = 0; j < MT; ++j) {
@@ -1065,30 +1138,11 @@ static moe_flat_kernel_t pick_flat_kernel(const MoeParams& p, FlatPlan* plan) {
     int ksplit = 1;
     while (ksplit < kFlatWarps && ntiles * ksplit < (int64_t)kNumSMs * 16 && ksplit * 2 <= p.K) ksplit <<= 1;
     const int64_t cap = (int64_t)kNumSMs * (FWD ? (p.M <= 2 ? 3 : 2) : (p.M <= 2 ? 2 : 1));
-    // Wave quantisation: the CTAs are persistent over equal-cost row groups, so the last round of a grid-stride loop
-    // runs with (ngroups mod cap) of the cap resident CTAs busy.  r2 sweep, C4 latent-only at B = 16k: 1024 groups
-    // over 444 (forward) / 296 (backward) CTAs = 2.3 / 3.5 rounds -> 77 % / 86 % of the rate at B = 64k.  Splitting K
-    // over more warps makes the groups finer: take the smallest split whose last round is >= 94 % full (each warp
-    // keeps >= 6 k steps so that the staging ring still fills), else the fullest one.
-    auto fill_of = [&](int ks) {
-        const int npw_ = kFlatWarps / ks;
-        const int64_t ng = (ntiles + npw_ - 1) / npw_;
-        if (ng <= cap) return 1.0;
-        const int64_t rounds = (ng + cap - 1) / cap;
-        return (double)ng / (double)(rounds * cap);
-    };
-    {
-        int best = ksplit;
-        double best_fill = fill_of(ksplit);
-        for (int ks = ksplit * 2; ks <= kFlatWarps && ks * 6 <= p.K && best_fill < 0.94; ks <<= 1) {
-            const double f = fill_of(ks);
-            if (f > best_fill + 0.02) {
-                best = ks;
-                best_fill = f;
-            }
-        }
-        ksplit = best;
-    }
+    // (r2, measured and rejected: a wave-aware K split -- finer row groups so that the last round of the persistent
+    // grid-stride loop is >= 94 % full.  C4 latent-only at B = 16k: forward 4.9 -> 4.1 TB/s with K split 8 ways (a warp
+    // then runs 6 k steps behind a 4-stage ring fill and a full set of row constants), backward unchanged with 2 ways:
+    // the partly filled last round is not the loss the fill factor suggests, its warps have the issue slots of their
+    // SM to themselves.)
     const int npw = kFlatWarps / ksplit;
     const int64_t ngroups = (ntiles + npw - 1) / npw;
     plan->lpr = lpr;
@@ -1106,6 +1160,14 @@ static moe_flat_kernel_t pick_flat_kernel(const MoeParams& p, FlatPlan* plan) {
         case 3: return pick_flat_lpr<FWD, 3>(lpr, lm, hot, pk);
     }
     return nullptr;
+}
+
+static void flat_strides(MoeParams& p, int ksplit) {
+    p.sBD = p.B * p.D;
+    p.sKBD = (int64_t)p.K * p.sBD;
+    p.sKB = (int64_t)p.K * p.B;
+    p.sKstepD = (int64_t)ksplit * p.sBD;
+    p.sKstep = (int64_t)ksplit * p.B;
 }
 
 static unsigned moe_grid(int64_t B) {
@@ -1130,21 +1192,43 @@ static int moe_fill(MoeParams& p, const float* mu, const float* s, int M, int64_
 
 using namespace mmvae;
 
+static int moe_fwd_impl(const float* mu, const float* s, int M, int64_t B, int D, int K, const int32_t* dists_host,
+                        const float* mu0, const float* s0, const float* eps, float* z, float* lq, float* lpz,
+                        int enc_tail, float* s_out, void* stream);
+
 extern "C" int mmvae_moe_logdens_fwd(const float* mu, const float* s, int M, int64_t B, int D, int K,
                                      const int32_t* dists_host, const float* mu0, const float* s0, const float* eps,
                                      float* z, float* lq, float* lpz, void* stream) {
+    return moe_fwd_impl(mu, s, M, B, D, K, dists_host, mu0, s0, eps, z, lq, lpz, 0, nullptr, stream);
+}
+
+extern "C" int mmvae_moe_logdens_fwd_tail(const float* mu, const float* s_raw, int M, int64_t B, int D, int K,
+                                          const int32_t* dists_host, const float* mu0, const float* s0,
+                                          const float* eps, float* z, float* lq, float* lpz, float* s_out,
+                                          void* stream) {
+    return moe_fwd_impl(mu, s_raw, M, B, D, K, dists_host, mu0, s0, eps, z, lq, lpz, 1, s_out, stream);
+}
+
+static int moe_fwd_impl(const float* mu, const float* s, int M, int64_t B, int D, int K, const int32_t* dists_host,
+                        const float* mu0, const float* s0, const float* eps, float* z, float* lq, float* lpz,
+                        int enc_tail, float* s_out, void* stream) {
     MoeParams p{};
     int rc = moe_fill(p, mu, s, M, B, D, K, dists_host, mu0, s0, eps);
     if (rc) return rc;
     if (!z || !lq || !lpz) return MMVAE_E_ARG;
     p.z = z; p.lq = lq; p.lpz = lpz;
+    p.enc_tail = enc_tail; p.s_out = s_out;
+    if (s_out && !aligned16(s_out)) return MMVAE_E_ARG;
     FlatPlan plan;
-    if (moe_flat_kernel_t kf = pick_flat_kernel<true>(p, &plan)) {
+    moe_flat_kernel_t kflat = pick_flat_kernel<true>(p, &plan);
+    if (enc_tail && !kflat) return MMVAE_E_LIMIT;  // the fused tail exists in the flat kernels only
+    if (moe_flat_kernel_t kf = kflat) {
         const size_t ring = (size_t)kFlatWarps * kFwdStages * M * 32 * sizeof(float4);
         if (ring > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute((const void*)kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
             if (e != cudaSuccess) return (int)e;
         }
+        flat_strides(p, plan.ksplit);
         kf<<<plan.grid, kFlatWarps * 32, ring, (cudaStream_t)stream>>>(p, plan.ksplit);
         MMVAE_LAUNCH_CHECK();
         return 0;
@@ -1181,10 +1265,21 @@ extern "C" int mmvae_moe_logdens_bwd_rk(const float* mu, const float* s, int M, 
                                         const float* dz_ext, const float* dlq, const float* dlpz, int through_z,
                                         const float* rk_w, const float* rk_scale_dev, float rk_mul, int dlq_packed,
                                         float* dmu, float* ds, float* dprior_ws, float* dmu0, float* ds0, void* stream) {
+    return mmvae_moe_logdens_bwd_tail(mu, s, M, B, D, K, dists_host, mu0, s0, eps, dz_ext, dlq, dlpz, through_z, rk_w,
+                                      rk_scale_dev, rk_mul, dlq_packed, 0, dmu, ds, dprior_ws, dmu0, ds0, stream);
+}
+
+extern "C" int mmvae_moe_logdens_bwd_tail(const float* mu, const float* s, int M, int64_t B, int D, int K,
+                                          const int32_t* dists_host, const float* mu0, const float* s0, const float* eps,
+                                          const float* dz_ext, const float* dlq, const float* dlpz, int through_z,
+                                          const float* rk_w, const float* rk_scale_dev, float rk_mul, int dlq_packed,
+                                          int enc_tail, float* dmu, float* ds, float* dprior_ws, float* dmu0, float* ds0,
+                                          void* stream) {
     MoeParams p{};
     int rc = moe_fill(p, mu, s, M, B, D, K, dists_host, mu0, s0, eps);
     if (rc) return rc;
     if (!dmu || !ds || !dprior_ws) return MMVAE_E_ARG;
+    p.enc_tail = enc_tail;
     if (rk_w && (dlpz || !dlq)) return MMVAE_E_ARG;  // rk mode: dlq holds softmax_j(lq), dlpz is implied (-rk)
     p.dz_ext = dz_ext; p.dlq = dlq; p.dlpz = dlpz; p.through_z = through_z; p.dmu = dmu; p.ds = ds; p.ws = dprior_ws;
     p.rk_w = rk_w; p.rk_scale = rk_scale_dev; p.rk_mul = rk_mul; p.dlq_packed = dlq_packed;
@@ -1200,6 +1295,7 @@ extern "C" int mmvae_moe_logdens_bwd_rk(const float* mu, const float* s, int M, 
             cudaError_t e = cudaFuncSetAttribute((const void*)kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
             if (e != cudaSuccess) return (int)e;
         }
+        flat_strides(p, plan.ksplit);
         kf<<<plan.grid, kFlatWarps * 32, ring, (cudaStream_t)stream>>>(p, plan.ksplit);
         MMVAE_LAUNCH_CHECK();
         if (dmu0 && ds0) {
@@ -1208,7 +1304,7 @@ extern "C" int mmvae_moe_logdens_bwd_rk(const float* mu, const float* s, int M, 
         }
         return 0;
     }
-    if (rk_w) return MMVAE_E_LIMIT;  // rk mode exists in the flat kernels only (D % 4 == 0, D <= 128, M <= 3)
+    if (rk_w || enc_tail) return MMVAE_E_LIMIT;  // rk mode / the fused encoder tail exist in the flat kernels only (D % 4 == 0, D <= 128, M <= 3)
     const int nw = moe_warps(K);
     const size_t smem = (size_t)(4 * M * D + 2 * D + nw * (2 * M * D + 2 * D)) * sizeof(float);
     if (smem > 200 * 1024) return MMVAE_E_LIMIT;

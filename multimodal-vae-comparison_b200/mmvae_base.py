@@ -90,21 +90,36 @@ class TorchMMVAE(nn.Module):
             out.set_with_dict(vals[f], f)
         return out
 
-    def encode(self, inputs):
-        """mmvae_base.py:139-159: {mod: {"shared": (mu, s), "private": (mu, s) | None}}."""
+    def encode(self, inputs, raw_ok=False):
+        """mmvae_base.py:139-159: {mod: {"shared": (mu, s), "private": (mu, s) | None}}.
+
+        An encoder that declares ``returns_raw_logvar = True`` returns the RAW output of its second Linear head instead
+        of applying the reference tail ``softmax(raw, -1) + 1e-6`` (encoders.py:49-54).  With raw_ok (the objectives)
+        the raw tensor is passed on under "full" with "raw": True and the latent kernels evaluate the tail themselves
+        (SURVEY 8f rank 1); otherwise the tail is applied here, so every other caller sees reference semantics."""
         qz_xs = {}
         for modality, vae in self.vaes.items():
             if modality in inputs and inputs[modality]["data"] is not None:
                 mu, s = vae.enc(inputs[modality])
-                if not self.latent_factorization:
-                    qz_xs[modality] = {"shared": (mu, s), "private": None, "full": (mu, s)}
+                raw = bool(getattr(vae.enc, "returns_raw_logvar", False))
+                if raw and not raw_ok:
+                    s, raw = self._enc_tail(s), False
+                if raw:  # slices of raw logits mean nothing: only the full row goes to the kernels
+                    qz_xs[modality] = {"shared": None, "private": None, "full": (mu, s), "raw": True}
+                elif not self.latent_factorization:
+                    qz_xs[modality] = {"shared": (mu, s), "private": None, "full": (mu, s), "raw": False}
                 else:
                     n = vae.n_latents
                     qz_xs[modality] = {"shared": [mu[:, :n], s[:, :n]], "private": [mu[:, n:], s[:, n:]],
-                                       "full": (mu, s)}
+                                       "full": (mu, s), "raw": False}
             elif modality in inputs:
-                qz_xs[modality] = {"shared": None, "private": None, "full": None}
+                qz_xs[modality] = {"shared": None, "private": None, "full": None, "raw": False}
         return qz_xs
+
+    @staticmethod
+    def _enc_tail(raw):
+        """Reference encoders.py:52: F.softmax(logvar_layer(data), dim=-1) + Constants.eta."""
+        return F.softmax(raw, dim=-1) + 1e-6
 
     def decode(self, samples):
         out = {}
@@ -163,6 +178,28 @@ class TorchMMVAE(nn.Module):
             mus = [F.pad(m, (0, width - m.shape[-1])) for m in mus]
             ss = [F.pad(s, (0, width - s.shape[-1]), value=1.0) for s in ss]
         return torch.stack(mus), torch.stack(ss)
+
+    def _stack_raw(self, enc, names, part="full"):
+        """(mu, s, s_raw): like _stack, for encoder outputs obtained with encode(raw_ok=True).  s_raw is True when `s`
+        holds raw second-head logits for the kernels' fused encoder tail -- every encoder of `names` returned raw
+        logits, all of the same width, and `part` is the whole encoder row.  Otherwise the tail is applied here."""
+        whole = part == "full" or not self.latent_factorization
+        raws = [bool(enc[n].get("raw")) for n in names]
+        widths = {enc[n]["full"][0].shape[-1] for n in names}
+        if all(raws) and whole and len(widths) == 1:
+            return (torch.stack([enc[n]["full"][0].float() for n in names]),
+                    torch.stack([enc[n]["full"][1].float() for n in names]), True)
+        fixed = {}
+        for n in names:
+            e = enc[n]
+            if e.get("raw"):
+                mu, s = e["full"][0], self._enc_tail(e["full"][1])
+                k = self.vaes[n].n_latents
+                e = {"full": (mu, s), "shared": (mu, s) if not self.latent_factorization else [mu[:, :k], s[:, :k]],
+                     "private": None if not self.latent_factorization else [mu[:, k:], s[:, k:]]}
+            fixed[n] = e
+        mu, s = self._stack(fixed, names, part)
+        return mu, s, False
 
     def _batch_total(self, B):
         return self.global_batch if self.global_batch is not None else B

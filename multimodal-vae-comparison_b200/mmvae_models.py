@@ -114,12 +114,18 @@ class MOE(TorchMMVAE):
         return others[-1] if others else None
 
     def _sample(self, names, enc, K, prior, through_z):
-        mu, s = self._stack(enc, names, "shared")
+        """Returns (mu, s, s_raw, codes, z, lq, lpz); s_raw: `s` holds raw encoder logits (tail fused into the kernels)."""
+        mu, s, raw = self._stack_raw(enc, names, "shared")
         M, B, D = mu.shape
+        if raw and not ops.moe_rk_supported(M, D):  # the fused tail lives in the flat MoE kernels only
+            s, raw = self._enc_tail(s), False
         codes = [dist_code(self.vaes[n]) for n in names]
         eps = torch.stack([self._noise("laplace" if c else "normal", (K, B, D), mu.device) for c in codes])
-        z, lq, lpz = ops.moe_logdens(mu, s, prior[0], prior[1], eps, codes, through_z)
-        return mu, s, codes, z, lq, lpz
+        if raw:
+            z, lq, lpz, _ = ops.moe_logdens_tail(mu, s, prior[0], prior[1], eps, codes, through_z)
+        else:
+            z, lq, lpz = ops.moe_logdens(mu, s, prior[0], prior[1], eps, codes, through_z)
+        return mu, s, raw, codes, z, lq, lpz
 
     def objective(self, data):
         self._require_all(data)
@@ -130,17 +136,17 @@ class MOE(TorchMMVAE):
             # source, mmvae_models.py:112-116) and its objective mis-shapes for M = 3: only M <= 2 is defined
             raise ValueError("MOE.objective is only defined for at most two modalities (the reference's cross-modal "
                              "bookkeeping, mmvae_models.py:112-116, breaks for M >= 3); got %d" % M)
-        enc = self.encode(data)
+        enc = self.encode(data, raw_ok=True)
         obj = self.obj_fn.obj_name
         if obj == "elbo":
             if K != 1:
                 raise ValueError("MOE elbo needs K == 1 (the reference breaks for K > 1, mmvae_models.py:62)")
             # the ELBO branch never touches the learnable prior (fixed N(0,1) VAE prior, :45): keep its grad None
             prior = tuple(p.detach() for p in self.pz_params)
-            mu, s, codes, z, lq, _ = self._sample(names, enc, 1, prior, through_z=False)
+            mu, s, raw, codes, z, lq, _ = self._sample(names, enc, 1, prior, through_z=False)
             kls = ops.latent_draws(mu, s, None, None, None,
                                    [Draw(mods=(m,), direct=True, laplace=bool(codes[m]), kl_mode=2, width=mu.shape[-1])
-                                    for m in range(M)])
+                                    for m in range(M)], s_raw=raw)
             total, rows_log, n_keep = 0.0, [], 0.0
             for r, name in enumerate(names):
                 vae = self.vaes[name]
@@ -166,7 +172,7 @@ class MOE(TorchMMVAE):
             kld = torch.stack([k["kl"] for k in kls])  # (M,B)
             loss = total + (beta / M) * n_keep * kld.sum()  # total KL once per kept row (objectives.py:67)
             return {"loss": loss, "reconstruction_loss": torch.stack(rows_log), "kld": kld}
-        mu, s, codes, z, lq, lpz = self._sample(names, enc, K, self._prior(), through_z=True)
+        mu, s, _, codes, z, lq, lpz = self._sample(names, enc, K, self._prior(), through_z=True)
         B = mu.shape[1]
         L = 1 if M == 1 else 2
         # the row kernels write straight into slices of one (M, L, K*B) buffer: the list of row vectors IS the stacked
@@ -196,7 +202,7 @@ class MOE(TorchMMVAE):
         assert len(filled) > 0, "at least one modality must be present for forward call"
         enc = self.encode(x)
         prior = tuple(p.detach() for p in self.pz_params)
-        mu, s, codes, z, _, _ = self._sample(filled, enc, K, prior, through_z=False)
+        mu, s, _, codes, z, _, _ = self._sample(filled, enc, K, prior, through_z=False)
         zs, qzs, px_zs, cross = {}, {}, {}, {}
         for i, name in enumerate(filled):
             qzs[name] = self.vaes[name].qz_x(mu[i], s[i])
@@ -233,14 +239,14 @@ class POE(TorchMMVAE):
         self._require_all(mods)
         names = list(self.vaes.keys())
         M, beta, D = len(names), self.obj_fn.beta, self.n_latents
-        enc = self.encode(mods)  # each encoder runs once; the reference re-runs it per subset with equal outputs
-        mu, s = self._stack(enc, names, "shared")
+        enc = self.encode(mods, raw_ok=True)  # each encoder runs once; the reference re-runs it per subset, same outputs
+        mu, s, raw = self._stack_raw(enc, names, "shared")
         B = mu.shape[1]
         subsets = poe_subsets(range(M))
         eps = torch.cat([self._noise("normal", (1, B, D), mu.device).reshape(-1) for _ in subsets])
         mu0, s0 = self._prior()
         res = ops.latent_draws(mu, s, mu0, s0, eps,
-                               [Draw(mods=sub, prior=True, kl_mode=1, width=D, K=1) for sub in subsets])
+                               [Draw(mods=sub, prior=True, kl_mode=1, width=D, K=1) for sub in subsets], s_raw=raw)
         terms = []
         rec_log = [None] * M
         for a, sub in enumerate(subsets):
@@ -337,8 +343,8 @@ class MoPOE(TorchMMVAE):
         self._require_all(mods)
         names = list(self.vaes.keys())
         M, beta, D = len(names), self.obj_fn.beta, self.n_latents
-        enc = self.encode(mods)
-        mu, s = self._stack(enc, names, "shared")
+        enc = self.encode(mods, raw_ok=True)
+        mu, s, raw = self._stack_raw(enc, names, "shared")
         B = mu.shape[1]
         Bt = self._batch_total(B)  # batch means are global under batch sharding
         K = 1  # objective() calls forward(mods) with the default K (:305)
@@ -348,7 +354,7 @@ class MoPOE(TorchMMVAE):
         mu0, s0 = self._prior()
         draws = [Draw(rowmask=True, kl_mode=1 if i == 0 else 0, width=D, K=K) for i in range(M)]
         draws += [Draw(mods=(i,), direct=True, kl_mode=1, width=D) for i in range(M)]
-        res = ops.latent_draws(mu, s, mu0, s0, eps, draws, row_masks)
+        res = ops.latent_draws(mu, s, mu0, s0, eps, draws, row_masks, s_raw=raw)
         terms, ind = [], []
         for i, name in enumerate(names):
             vae = self.vaes[name]
@@ -453,22 +459,22 @@ class DMVAE(TorchMMVAE):
             index["cross"].append(cr)
         return draws, index
 
-    def _run(self, mods, K):
+    def _run(self, mods, K, raw_ok=False):
         names = list(self.vaes.keys())
-        enc = self.encode(mods)
-        mu, s = self._stack(enc, names, "full")
+        enc = self.encode(mods, raw_ok=raw_ok)
+        mu, s, raw = self._stack_raw(enc, names, "full")
         B = mu.shape[1]
         draws, index = self._draws(names, K)
         eps = torch.cat([self._noise("normal", (d.K, B, d.width), mu.device).reshape(-1) for d in draws])
         mu0, s0 = self._prior()
-        res = ops.latent_draws(mu, s, mu0, s0, eps, draws)
+        res = ops.latent_draws(mu, s, mu0, s0, eps, draws, s_raw=raw)
         return names, enc, mu, s, res, index
 
     def objective(self, mods):
         """mmvae_models.py:436-465: per modality three ELBO terms (own shared, joint, cross)."""
         self._require_all(mods)
         beta = self.obj_fn.beta
-        names, enc, mu, s, res, index = self._run(mods, 1)
+        names, enc, mu, s, res, index = self._run(mods, 1, raw_ok=True)
         M = len(names)
         z_joint = res[0]["z"]
         terms, ind = [], []

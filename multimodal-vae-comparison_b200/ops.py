@@ -434,7 +434,7 @@ class _LatentDraws(torch.autograd.Function):
     noise.  Outputs: packed z, packed loc, packed scale, packed kl rows."""
 
     @staticmethod
-    def forward(ctx, mu, s, mu0, s0, eps, draws, row_masks):
+    def forward(ctx, mu, s, mu0, s0, eps, draws, row_masks, s_raw=False):
         ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(mu, s, mu0, s0, eps, row_masks)
         M, B, Dtot = mu.shape
@@ -451,15 +451,21 @@ class _LatentDraws(torch.autograd.Function):
         ploc = torch.empty(max(npar, 1), dtype=torch.float32, device=dev)
         pscale = torch.empty(max(npar, 1), dtype=torch.float32, device=dev)
         kl = torch.empty(max(nkl, 1), dtype=torch.float32, device=dev)
-        call("mmvae_latent_draws_fwd", _ptr(mu_c), _ptr(s_c), M, B, Dtot, arr, len(draws), _ptr(row_masks),
-             _ptr(mu0_c), _ptr(s0_c), _ptr(eps_c), _ptr(z), _ptr(ploc), _ptr(pscale), _ptr(kl), _stream())
+        # s_raw: `s` is the raw output of the encoders' second head; the kernel applies softmax(.,-1) + 1e-6 itself
+        scales = torch.empty_like(s_c) if s_raw else None
+        call("mmvae_latent_draws_fwd_tail", _ptr(mu_c), _ptr(s_c), M, B, Dtot, arr, len(draws), _ptr(row_masks),
+             _ptr(mu0_c), _ptr(s0_c), _ptr(eps_c), _ptr(z), _ptr(ploc), _ptr(pscale), _ptr(kl), int(bool(s_raw)),
+             _ptr(scales), _stream())
         ctx.save_for_backward(mu_c, s_c, mu0_c, s0_c, eps_c, row_masks)
         ctx.arr, ctx.n, ctx.dims = arr, len(draws), (M, B, Dtot, ne, npar, nkl)
         ctx.prior_shape = None if mu0 is None else (mu0.shape, s0.shape)
-        return z, ploc, pscale, kl
+        ctx.s_raw = bool(s_raw)
+        if scales is not None:
+            ctx.mark_non_differentiable(scales)
+        return z, ploc, pscale, kl, scales
 
     @staticmethod
-    def backward(ctx, dz, dploc, dpscale, dkl):
+    def backward(ctx, dz, dploc, dpscale, dkl, _dscales=None):
         mu_c, s_c, mu0_c, s0_c, eps_c, row_masks = ctx.saved_tensors
         M, B, Dtot, ne, npar, nkl = ctx.dims
         dev = mu_c.device
@@ -480,27 +486,32 @@ class _LatentDraws(torch.autograd.Function):
         nws = _lib.load().mmvae_latent_draws_bwd_ws_floats(B, Dtot)
         ws = torch.empty(nws, dtype=torch.float32, device=dev)
         dprior = torch.zeros(2, Dtot, dtype=torch.float32, device=dev)
-        call("mmvae_latent_draws_bwd", _ptr(mu_c), _ptr(s_c), M, B, Dtot, ctx.arr, ctx.n, _ptr(row_masks),
-             _ptr(mu0_c), _ptr(s0_c), _ptr(eps_c), _ptr(dz), _ptr(dkl), _ptr(dploc), _ptr(dpscale), _ptr(dmu),
-             _ptr(ds), _ptr(ws), _ptr(dprior[0]), _ptr(dprior[1]), _stream())
+        call("mmvae_latent_draws_bwd_tail", _ptr(mu_c), _ptr(s_c), M, B, Dtot, ctx.arr, ctx.n, _ptr(row_masks),
+             _ptr(mu0_c), _ptr(s0_c), _ptr(eps_c), _ptr(dz), _ptr(dkl), _ptr(dploc), _ptr(dpscale), int(ctx.s_raw),
+             _ptr(dmu), _ptr(ds), _ptr(ws), _ptr(dprior[0]), _ptr(dprior[1]), _stream())
         gm0 = gs0 = None
         if ctx.prior_shape is not None:
             D = mu0_c.numel()
             gm0 = dprior[0, :D].reshape(ctx.prior_shape[0])
             gs0 = dprior[1, :D].reshape(ctx.prior_shape[1])
-        return dmu, ds, gm0, gs0, None, None, None
+        return dmu, ds, gm0, gs0, None, None, None, None
 
 
 class DrawResults(list):
     """Per-draw result dicts of latent_draws; ``kl_packed`` is the kernel's packed KL output (what elbo_combine reads)."""
     kl_packed = None
+    scales = None
 
 
-def latent_draws(mu, s, mu0, s0, eps, draws: List[Draw], row_masks=None):
-    """Run a list of draws.  Returns per-draw dicts with views: z (K,B,w) | None, loc/scale (B,w) | None, kl (B) | None."""
+def latent_draws(mu, s, mu0, s0, eps, draws: List[Draw], row_masks=None, s_raw=False):
+    """Run a list of draws.  Returns per-draw dicts with views: z (K,B,w) | None, loc/scale (B,w) | None, kl (B) | None.
+    s_raw=True: `s` holds the raw logits of the encoders' second head and the kernels apply the encoder tail
+    softmax(., -1) + 1e-6 themselves (reference encoders.py:49-54); the result's ``scales`` is the (M,B,Dtot) tensor of
+    the scales they computed (no gradient), and the gradient returned for `s` is the one of the raw logits."""
     M, B, Dtot = mu.shape
-    z, ploc, pscale, kl = _LatentDraws.apply(mu, s, mu0, s0, eps, draws, row_masks)
+    z, ploc, pscale, kl, scales = _LatentDraws.apply(mu, s, mu0, s0, eps, draws, row_masks, s_raw)
     out = DrawResults()
+    out.scales = scales
     out.kl_packed = kl if any(d.kl_mode for d in draws) else None  # (n_kl * B): rows of the draws with a KL, in order
     eo = po = ko = 0
     for d in draws:
@@ -527,7 +538,7 @@ class _MoeLogdens(torch.autograd.Function):
     """include/mmvae_b200.h mmvae_moe_logdens_{fwd,bwd}."""
 
     @staticmethod
-    def forward(ctx, mu, s, mu0, s0, eps, dists, through_z):
+    def forward(ctx, mu, s, mu0, s0, eps, dists, through_z, s_raw=False):
         ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(mu, s, mu0, s0, eps)
         M, B, D = mu.shape
@@ -540,14 +551,24 @@ class _MoeLogdens(torch.autograd.Function):
         lq = torch.empty((M, M, K, B), dtype=torch.float32, device=dev)
         lpz = torch.empty((M, K, B), dtype=torch.float32, device=dev)
         darr = (ctypes.c_int32 * M)(*[int(x) for x in dists])
-        call("mmvae_moe_logdens_fwd", _ptr(mu_c), _ptr(s_c), M, B, D, K, darr, _ptr(mu0_c), _ptr(s0_c), _ptr(eps_c),
-             _ptr(z), _ptr(lq), _ptr(lpz), _stream())
+        scales = None
+        if s_raw:  # encoder tail softmax(., -1) + 1e-6 evaluated inside the kernel (flat kernels only)
+            if not moe_rk_supported(M, D):
+                raise RuntimeError("mmvae_b200: the fused encoder tail of moe_logdens needs D % 4 == 0, D <= 128, M <= 3")
+            scales = torch.empty_like(s_c)
+            call("mmvae_moe_logdens_fwd_tail", _ptr(mu_c), _ptr(s_c), M, B, D, K, darr, _ptr(mu0_c), _ptr(s0_c),
+                 _ptr(eps_c), _ptr(z), _ptr(lq), _ptr(lpz), _ptr(scales), _stream())
+            ctx.mark_non_differentiable(scales)
+        else:
+            call("mmvae_moe_logdens_fwd", _ptr(mu_c), _ptr(s_c), M, B, D, K, darr, _ptr(mu0_c), _ptr(s0_c), _ptr(eps_c),
+                 _ptr(z), _ptr(lq), _ptr(lpz), _stream())
         ctx.save_for_backward(mu_c, s_c, mu0_c, s0_c, eps_c)
         ctx.meta = (M, B, D, K, darr, int(through_z), mu0.shape, s0.shape)
-        return z, lq, lpz
+        ctx.s_raw = bool(s_raw)
+        return z, lq, lpz, scales
 
     @staticmethod
-    def backward(ctx, dz, dlq, dlpz):
+    def backward(ctx, dz, dlq, dlpz, _dscales=None):
         mu_c, s_c, mu0_c, s0_c, eps_c = ctx.saved_tensors
         M, B, D, K, darr, through_z, sh0, sh1 = ctx.meta
         f = lambda t: None if t is None else t.detach().float().contiguous()
@@ -577,10 +598,15 @@ class _MoeLogdens(torch.autograd.Function):
         nws = _lib.load().mmvae_moe_logdens_bwd_ws_floats(B, D, K)
         ws = torch.empty(nws, dtype=torch.float32, device=dev)
         dprior = torch.empty(2, D, dtype=torch.float32, device=dev)
-        call("mmvae_moe_logdens_bwd_rk", _ptr(mu_c), _ptr(s_c), M, B, D, K, darr, _ptr(mu0_c), _ptr(s0_c), _ptr(eps_c),
-             _ptr(dz), _ptr(dlq), _ptr(dlpz), through_z, _ptr(rk_w), _ptr(rk_g), float(rk_mul), packed, _ptr(dmu),
-             _ptr(ds), _ptr(ws), _ptr(dprior[0]), _ptr(dprior[1]), _stream())
-        return dmu, ds, dprior[0].reshape(sh0), dprior[1].reshape(sh1), None, None, None
+        if ctx.s_raw:
+            call("mmvae_moe_logdens_bwd_tail", _ptr(mu_c), _ptr(s_c), M, B, D, K, darr, _ptr(mu0_c), _ptr(s0_c),
+                 _ptr(eps_c), _ptr(dz), _ptr(dlq), _ptr(dlpz), through_z, _ptr(rk_w), _ptr(rk_g), float(rk_mul), packed, 1,
+                 _ptr(dmu), _ptr(ds), _ptr(ws), _ptr(dprior[0]), _ptr(dprior[1]), _stream())
+        else:
+            call("mmvae_moe_logdens_bwd_rk", _ptr(mu_c), _ptr(s_c), M, B, D, K, darr, _ptr(mu0_c), _ptr(s0_c), _ptr(eps_c),
+                 _ptr(dz), _ptr(dlq), _ptr(dlpz), through_z, _ptr(rk_w), _ptr(rk_g), float(rk_mul), packed, _ptr(dmu),
+                 _ptr(ds), _ptr(ws), _ptr(dprior[0]), _ptr(dprior[1]), _stream())
+        return dmu, ds, dprior[0].reshape(sh0), dprior[1].reshape(sh1), None, None, None, None
 
 
 def moe_rk_supported(M, D):
@@ -590,7 +616,14 @@ def moe_rk_supported(M, D):
 
 
 def moe_logdens(mu, s, mu0, s0, eps, dists, through_z=True):
-    return _MoeLogdens.apply(mu, s, mu0, s0, eps, tuple(dists), through_z)
+    return _MoeLogdens.apply(mu, s, mu0, s0, eps, tuple(dists), through_z, False)[:3]
+
+
+def moe_logdens_tail(mu, s_raw, mu0, s0, eps, dists, through_z=True):
+    """moe_logdens with the encoder tail fused in: `s_raw` holds the raw logits of the encoders' second head, the kernel
+    applies softmax(., -1) + 1e-6 (reference encoders.py:49-54).  Returns (z, lq, lpz, scales); the gradient that comes
+    back for `s_raw` is the one of the raw logits.  Shapes: moe_rk_supported(M, D)."""
+    return _MoeLogdens.apply(mu, s_raw, mu0, s0, eps, tuple(dists), through_z, True)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -884,8 +917,9 @@ class _ElboCombine(torch.autograd.Function):
         loss = torch.empty((), dtype=torch.float32, device=dev)
         kld = torch.empty((), dtype=torch.float32, device=dev)  # the logged "kld"
         dkl = torch.empty(max(n_kl * B, 1), dtype=torch.float32, device=dev) if n_kl else None
+        ws = torch.empty(2 * _lib.ELBO_MAX_CTAS, dtype=torch.float32, device=dev)  # per-CTA partials
         call("mmvae_objective_elbo", ptrs, ns, cf, n_t, _ptr(klc), B, kc, kg, n_kl, _ptr(loss), _ptr(kld), _ptr(dkl),
-             _stream())
+             _ptr(ws), _ptr(_ticket(dev)), _stream())
         ctx.dkl = dkl
         ctx.n_S = len(S)
         ctx.kl_shape = None if kl is None else kl.shape

@@ -33,16 +33,19 @@ class LeafEncoder(nn.Module):
 class LinearEncoder(nn.Module):
     """flatten -> two Linear heads with the reference tail (encoders.py:49-54): mu, softmax(raw,-1)+1e-6."""
 
-    def __init__(self, data_dim, out_dim):
+    def __init__(self, data_dim, out_dim, returns_raw_logvar=False):
         super().__init__()
         self.data_dim = tuple(data_dim)
         p = int(math.prod(self.data_dim))
         self.mu_layer = nn.Linear(p, out_dim)
         self.logvar_layer = nn.Linear(p, out_dim)
+        # True: hand the raw output of the second head to the latent kernels, which apply the tail themselves
+        self.returns_raw_logvar = bool(returns_raw_logvar)
 
     def forward(self, x):
         d = x["data"].float().reshape(x["data"].shape[0], -1)
-        return self.mu_layer(d), F.softmax(self.logvar_layer(d), dim=-1) + ETA
+        raw = self.logvar_layer(d)
+        return self.mu_layer(d), raw if self.returns_raw_logvar else F.softmax(raw, dim=-1) + ETA
 
 
 class LinearDecoder(nn.Module):

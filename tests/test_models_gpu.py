@@ -349,3 +349,55 @@ def test_mopoe_fusion_methods_match_oracle():
     sel, _ = model.moe_fusion(stack.cuda(), stack.cuda(), torch.ones(S).cuda() / S)
     ref_sel, _ = refmath.mixture_component_selection(stack, stack, torch.ones(S) / S)
     assert torch.equal(sel.cpu(), ref_sel)  # index work: bit exact
+
+
+class _RawLeafEncoder(torch.nn.Module):
+    """Leaf encoder that hands over the RAW second-head logits (returns_raw_logvar): the plugins then let the latent
+    kernels evaluate softmax(raw, -1) + 1e-6 themselves (reference encoders.py:49-54)."""
+    returns_raw_logvar = True
+
+    def __init__(self, data_dim, mu, s):
+        super().__init__()
+        self.data_dim = tuple(data_dim)
+        self.mu = torch.nn.Parameter(mu.clone())
+        self.raw = torch.nn.Parameter(torch.log((s.double() - 1e-6).clamp_min(1e-30)).float())  # softmax(raw) == s - 1e-6
+
+    def forward(self, x):
+        return self.mu, self.raw
+
+
+@pytest.mark.parametrize("idx", [0, 5, 6, 7, 9, 12])
+def test_fused_encoder_tail_matches_reference_golden(golden, idx):
+    """Same frozen reference outputs as test_dropin_matches_reference_golden, with encoders that return raw logits:
+    loss and every gradient must still match; d loss / d raw is the reference's d loss / d s taken back through the
+    encoder tail, p (g - <g, p>)."""
+    import mmvae_b200
+    entry = golden["cases"][idx]
+    case, ref = entry["case"], entry["reference"]
+    device = "cuda"
+    vaes = cases.build_vaes(case, device)
+    for i, m in enumerate(case["mods"]):
+        v = vaes["mod_%d" % (i + 1)]
+        v.enc = _RawLeafEncoder(m["data_dim"], m["mu"], m["s"]).to(device)
+    cls = mmvae_b200.MODEL_REGISTRY[case["model"]]
+    model = cls(vaes, case["D"], {"obj": case["obj"], "beta": case["beta"], "K": case["K"]}, None).to(device)
+    with torch.no_grad():
+        model._pz_params[1].copy_(case["pz_logits"])
+    src, q = _noise_queue(case)
+    model.noise_source = src
+    out = model.objective(cases.build_batch(case, device))
+    assert not q
+    out["loss"].backward()
+    assert _rel(out["loss"], ref["loss"]) < TOL
+    for i, m in enumerate(case["mods"]):
+        name = "mod_%d" % (i + 1)
+        enc = vaes[name].enc
+        assert _rel(enc.mu.grad, ref["grad.%s.mu" % name]) < TOL
+        gs = ref["grad.%s.s" % name]
+        p = m["s"].double() - 1e-6
+        want = p * (gs - (gs * p).sum(-1, keepdim=True))
+        assert _rel(enc.raw.grad, want) < 2 * TOL, (case["name"], name)  # (raw = fl(log p): one more rounding than s)
+        assert _rel(vaes[name].dec.lin.weight.grad if hasattr(vaes[name].dec, "lin") else vaes[name].dec.inner.lin.weight.grad,
+                    ref["grad.%s.W" % name]) < TOL
+    if ref.get("grad.pz_logits") is not None:
+        assert _rel(model._pz_params[1].grad, ref["grad.pz_logits"]) < TOL

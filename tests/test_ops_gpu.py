@@ -636,3 +636,97 @@ def test_elbo_combine_limits(ops):
         ops.elbo_combine([z] * 49)
     loss, _ = ops.elbo_combine([z + 1.5, z + 2.0])  # no KL segments at all
     assert abs(float(loss) - 3.5) < 1e-6
+
+
+@pytest.mark.parametrize("M,B,D,K,dists", [(2, 37, 16, 3, ("normal", "normal")), (2, 9, 64, 4, ("laplace", "laplace")),
+                                           (3, 5, 32, 2, ("normal", "laplace", "normal"))])
+def test_moe_logdens_fused_encoder_tail(ops, M, B, D, K, dists):
+    """mmvae_moe_logdens_{fwd,bwd}_tail: raw second-head logits in, s = softmax(raw, -1) + 1e-6 (reference
+    encoders.py:49-54) evaluated inside the kernel, gradient with respect to the raw logits -- against the same kernels
+    fed with the torch tail (which test_moe_logdens pins to the oracle)."""
+    g = torch.Generator().manual_seed(21)
+    dev = "cuda"
+    mu = torch.randn(M, B, D, generator=g)
+    raw = torch.randn(M, B, D, generator=g) * 1.5
+    mu0, s0 = torch.randn(1, D, generator=g) * 0.1, torch.rand(1, D, generator=g) + 0.5
+    eps = torch.stack([torch.randn(K, B, D, generator=g) if d == "normal" else torch.rand(K, B, D, generator=g) * 1.98 - 0.99
+                       for d in dists])
+    codes = [1 if d == "laplace" else 0 for d in dists]
+    wz, wq, wp = torch.randn(M, K, B, D, generator=g), torch.randn(M, M, K, B, generator=g), torch.randn(M, K, B, generator=g)
+
+    def run(fused):
+        m_, r_ = mu.to(dev).requires_grad_(True), raw.to(dev).requires_grad_(True)
+        p0, p1 = mu0.to(dev).requires_grad_(True), s0.to(dev).requires_grad_(True)
+        if fused:
+            z, lq, lpz, sc = ops.moe_logdens_tail(m_, r_, p0, p1, eps.to(dev), codes)
+        else:
+            sc = torch.softmax(r_, -1) + 1e-6
+            z, lq, lpz = ops.moe_logdens(m_, sc, p0, p1, eps.to(dev), codes)
+        ((z * wz.to(dev)).sum() + (lq * wq.to(dev)).sum() + (lpz * wp.to(dev)).sum()).backward()
+        return [z, lq, lpz, sc.detach(), m_.grad, r_.grad, p0.grad, p1.grad]
+
+    for a, b in zip(run(True), run(False)):
+        assert rel(a, b) < FP32_TOL
+
+
+@pytest.mark.parametrize("M,B,D,pv", [(2, 33, 16, 10), (3, 7, 10, 0)])
+def test_latent_draws_fused_encoder_tail(ops, M, B, D, pv):
+    """mmvae_latent_draws_{fwd,bwd}_tail (PoE subsets with the prior expert, direct shared / private draws, KL rows)
+    against the same kernels fed with the torch encoder tail."""
+    g = torch.Generator().manual_seed(22)
+    dev = "cuda"
+    Dt = D + pv
+    mu, raw = torch.randn(M, B, Dt, generator=g), torch.randn(M, B, Dt, generator=g) * 1.5
+    mu0, s0 = torch.zeros(1, D), torch.rand(1, D, generator=g) + 0.5
+    draws = [ops.Draw(mods=tuple(range(M)), prior=True, kl_mode=1, width=D, K=2, want_params=True),
+             ops.Draw(mods=(0,), direct=True, kl_mode=1, width=D, K=1),
+             ops.Draw(mods=(M - 1,), prior=True, kl_mode=1, width=D, K=1)]
+    if pv:
+        draws.append(ops.Draw(mods=(1,), direct=True, kl_mode=2, col0=D, width=pv, K=1))
+    eps = torch.cat([torch.randn(d.K * B * d.width, generator=g) for d in draws])
+    wz = torch.randn(eps.numel(), generator=g)
+
+    def run(fused):
+        m_, r_ = mu.to(dev).requires_grad_(True), raw.to(dev).requires_grad_(True)
+        p1 = s0.to(dev).requires_grad_(True)
+        s_in = r_ if fused else torch.softmax(r_, -1) + 1e-6
+        res = ops.latent_draws(m_, s_in, mu0.to(dev), p1, eps.to(dev), draws, s_raw=fused)
+        zs = torch.cat([r["z"].reshape(-1) for r in res])
+        loss = (zs * wz.to(dev)).sum() + 0.7 * res.kl_packed.sum() + (res[0]["loc"] * 0.3).sum() + (res[0]["scale"] * 1.1).sum()
+        loss.backward()
+        sc = res.scales if fused else s_in.detach()
+        return [zs, res.kl_packed, res[0]["loc"], res[0]["scale"], sc, m_.grad, r_.grad, p1.grad]
+
+    for a, b in zip(run(True), run(False)):
+        assert rel(a, b) < FP32_TOL
+
+
+@pytest.mark.parametrize("K,B,shape", [(1, 8, (246, 27)), (2, 4, (128, 27)), (1, 8, (64, 6)), (3, 4, (100, 40)),
+                                       (1, 4, (250, 31)), (1, 4, (512, 27)), (1, 4, (600, 27))])
+def test_catce_bf16_long_class_axes(ops, K, B, shape):
+    """bf16 reconstructions AND targets on long class axes: the register-resident kernel (<= 16 periods per warp,
+    d = 27 compile-time and generic), the chunked pair kernel behind it (C = 600: 300 periods do not fit 16 warps) --
+    forward rows + cached-statistics backward, and the fused value + gradient pass, against the oracle on the same
+    bf16-rounded inputs."""
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(K * B, *shape, generator=g).bfloat16()
+    idx = torch.randint(shape[-1], (B, *shape[:-1]), generator=g)
+    t = torch.nn.functional.one_hot(idx, shape[-1]).float()
+    t[:, shape[0] // 2:] = 0  # padded positions
+    t[0] = torch.rand(shape, generator=g)
+    t = t.bfloat16()
+    w = torch.randn(K * B, generator=g)
+    lam = 0.6
+    xo = x.float().clone().requires_grad_(True)
+    ref = refmath.lpx_rows("category_ce", xo, t.float(), lam, K)
+    (ref * w).sum().backward()
+    xc = x.cuda().requires_grad_(True)
+    out = ops.catce_rows(xc, t.cuda(), lam)
+    (out * w.cuda()).sum().backward()
+    assert rel(out, ref) < 1e-5  # fp32 accumulation over bf16 inputs: the row values are fp32 quantities
+    assert rel(xc.grad, xo.grad) < BF16_TOL
+    xc2 = x.cuda().requires_grad_(True)
+    S, rows = ops.catce_weighted_sum(xc2, t.cuda(), lam, w_rows=w.cuda())
+    (2.0 * S).backward()
+    assert rel(S, (ref * w).sum()) < 1e-5 and rel(rows, ref) < 1e-5
+    assert rel(xc2.grad, 2.0 * xo.grad) < BF16_TOL

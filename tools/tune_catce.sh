@@ -7,11 +7,12 @@ cd "$(dirname "$0")/.."
 SRC=multimodal-vae-comparison_b200/csrc
 OUT=gpurun_out/tune_catce; mkdir -p $OUT; rm -f $OUT/lib_*.so
 declare -A V
-V[r1_staged]="-DMMVAE_CATCE_PAIRS=0"
-V[pairs_w4_t0]=""
-V[pairs_w2_t0]="-DMMVAE_CATCE_PAIRS_W=2"
-V[pairs_w4_t1]="-DMMVAE_CATCE_PAIRS_STAGE_T=1"
-V[pairs_w2_t1]="-DMMVAE_CATCE_PAIRS_W=2 -DMMVAE_CATCE_PAIRS_STAGE_T=1"
+V[r1_staged]="-DMMVAE_CATCE_PAIRS=0 -DMMVAE_CATCE_RESIDENT=0"
+V[r2_tma_w4]="-DMMVAE_CATCE_RESIDENT=0"
+V[r2_flat_r4w4]="-DMMVAE_CATCE_RESIDENT=0 -DMMVAE_CATCE_PAIRS_STAGE_X=0"
+V[resident_occ3]=""
+V[resident_occ2]="-DMMVAE_CATCE_RESIDENT_OCC=2"
+V[resident_occ4]="-DMMVAE_CATCE_RESIDENT_OCC=4"
 for k in "${!V[@]}"; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -Iinclude ${V[$k]} -shared $SRC/catce.cu -o $OUT/lib_$k.so -lcudart > $OUT/build_$k.log 2>&1 &
 done
