@@ -60,6 +60,9 @@ def parse():
     ap.add_argument("--no-parity", action="store_true", help="N>1: skip the sharded-vs-unsharded numerical check")
     ap.add_argument("--no-roofline-timer", action="store_true",
                     help="skip the per-kernel CUDA-event leg (profiling runs under ncu: fewer launches to wade through)")
+    ap.add_argument("--sweep", default=None,
+                    help="several configurations in one process group, one JSON line each: workload:global_batch[:w],... "
+                         "(w: the number is the batch per GPU, weak scaling)")
     ap.add_argument("--nccl-only", action="store_true",
                     help="N>1: every collective through NCCL (default: the small ones fused into our kernels over peer memory)")
     ap.add_argument("--cpu-batch", type=int, default=None,
@@ -390,6 +393,40 @@ def main():
                              "backward, DReG (M,K) batch sums inside stage 2, optimal_sigma sum+count): no NCCL call in the step")
             except Exception as ex:
                 coll_note = "NCCL (peer memory unavailable: %s)" % repr(ex)[:160]
+    ctx = dict(rank=rank, local_rank=local_rank, world=world, dev=dev, group=group, coll=coll, coll_note=coll_note)
+    if args.sweep:
+        # several configurations inside ONE process group (a torchrun start-up per point costs more GPU time than the
+        # points themselves): "workload:global_batch[:w|s],..." -- w = weak (the number is the batch per GPU)
+        for item in args.sweep.split(","):
+            f = item.split(":")
+            a = argparse.Namespace(**vars(args))
+            a.workload, a.batch, a.global_batch = f[0], None, None
+            if len(f) > 2 and f[2] == "w":
+                a.batch = int(f[1])
+            else:
+                a.global_batch = int(f[1])
+            line = one_config(a, ctx)
+            if rank == 0:
+                emit(line)
+    else:
+        line = one_config(args, ctx)
+        if rank == 0:
+            emit(line)
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+
+
+def one_config(args, ctx):
+    """Measure one configuration (the body of the bench); returns the JSON line (a dict)."""
+    import torch
+    import torch.distributed as dist
+    import mmvae_b200._lib as L
+    import mmvae_b200.parallel as par
+    import mmvae_b200.synthetic as syn
+    import mmvae_b200.workloads as W
+    rank, local_rank, world, dev = ctx["rank"], ctx["local_rank"], ctx["world"], ctx["dev"]
+    group, coll, coll_note = ctx["group"], ctx["coll"], ctx["coll_note"]
     rdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     B, scaling = local_batch(args, syn.WORKLOADS[args.workload]["B"], world)
     cfg, t = W.make_leaves(args.workload, B=B, seed=1234 + rank, recon_dtype=rdt)
@@ -619,13 +656,14 @@ def main():
         line["parity_n"] = parity_n
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, syn.WORKLOADS[args.workload], B)
-    if rank == 0:
-        emit(line)
-    if world > 1:
-        if runner is not step:
-            runner.close()  # the graph holds the captured all-reduce: it must go before the communicator
-        torch.cuda.synchronize()
-        dist.destroy_process_group()
+    if runner is not step:
+        runner.close()  # the graph holds the captured collectives: it must go before the communicator
+    if step.sync is not None:
+        step.sync.disarm()
+    del runner, step
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return line
 
 
 if __name__ == "__main__":
