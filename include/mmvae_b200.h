@@ -117,6 +117,16 @@ MMVAE_API int mmvae_catce_rows(int mode, const void* recon, int64_t ld_recon, in
                      int64_t rows, int64_t B, int64_t C, int64_t d, float lam,
                      const float* w_rows, float w_const,
                      float* out_rows, void* grad_recon, int64_t ld_grad, float* stats, void* stream);
+/* same with the text decoder's tail fused in (reference decoders.py:722, "zero for padded area": output * mask, SURVEY
+ * 8f rank 1): recon is the UNMASKED decoder output, mask (B, C) bytes (row r uses mask row r % B, non-zero = keep,
+ * ld_mask >= C); the loss is evaluated on x_eff = mask ? x : 0 and grad_recon is the gradient with respect to the
+ * unmasked tensor (zero where masked).  mask == NULL: identical to mmvae_catce_rows.  With a mask the backward (mode 1)
+ * recomputes the column statistics (stats is written by mode 0 but not read). */
+MMVAE_API int mmvae_catce_rows_masked(int mode, const void* recon, int64_t ld_recon, int dtype_recon,
+                            const void* target, int64_t ld_target, int dtype_target,
+                            int64_t rows, int64_t B, int64_t C, int64_t d, float lam,
+                            const float* w_rows, float w_const, float* out_rows, void* grad_recon, int64_t ld_grad,
+                            float* stats, const unsigned char* mask, int64_t ld_mask, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * optimal_sigma (sigma-VAE) rows: replaces ReconLoss.optimal_sigma (objectives.py:502-509) + utils.softclip

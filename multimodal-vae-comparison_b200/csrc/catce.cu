@@ -29,6 +29,8 @@ struct CatceParams {
     int G;               // rows a warp works on at once (32 / d for d < 32, else 1): lane -> (row in group, column)
     int S, TS;           // ring kernel: x stages, target slots
     int npw, lg_ns, same_rows;  // resident kernel: periods per warp, log2 of the merge segment, rows == B
+    const unsigned char* mask;  // (B, C) bytes or NULL: padding mask of the text decoder, fused multiply (masked kernel)
+    int64_t ldm;
     float inv_n, inv_d;  // v2 flat backward: 1/(C*d), 1/d for the exact float-reciprocal index split
     float lam, w_const;
 };
@@ -1223,6 +1225,73 @@ static int launch_catce_v2(int mode, CatceParams p, cudaStream_t st) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Text-decoder tail fused in (reference decoders.py:722, "zero for padded area": output * mask[:, :, None]): the
+// reconstruction arrives UNMASKED together with the (B, C) padding mask, the kernel evaluates the loss on
+// x_eff[r, c, j] = mask[r % B, c] ? x[r, c, j] : 0 and returns the gradient with respect to the unmasked tensor
+// (zero at masked positions).  A warp per row, lanes over the columns j (coalesced d-element runs), the class axis is
+// walked with an online softmax; the gradient pass re-reads the row (L1 / L2).  Any row stride / alignment / dtype.
+// (The transformer text decoder drops the K axis -- SURVEY N3 -- so these tensors are B x T x 27: latency, not bandwidth.)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename TX, typename TT, int MODE>  // 0 forward (+ statistics), 1 backward, 2 fused
+__global__ void __launch_bounds__(256) catce_masked_kernel(const CatceParams p) {
+    const int lane = threadIdx.x & 31, d = p.d, C = p.C;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const TX* __restrict__ xg = reinterpret_cast<const TX*>(p.x);
+    const TT* __restrict__ tg = reinterpret_cast<const TT*>(p.t);
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < p.rows; row += nwarps) {
+        const int64_t b = row % p.B;
+        const TX* xr = xg + row * p.ldx;
+        const TT* tr = tg + b * p.ldt;
+        const unsigned char* mk = p.mask + b * p.ldm;
+        float wl = 0.f;
+        if (MODE != 0) wl = (p.w_rows ? __ldg(p.w_rows + row) : p.w_const) * p.lam;
+        float acc = 0.f;
+        for (int j = lane; j < d; j += 32) {
+            float m = -INFINITY, se = 0.f, ts = 0.f, txs = 0.f;
+            for (int c = 0; c < C; ++c) {
+                const float xv = __ldg(mk + c) ? Elem<TX>::load1(xr + (int64_t)c * d + j) : 0.f;
+                const float tv = Elem<TT>::load1(tr + (int64_t)c * d + j);
+                const float nm = fmaxf(m, xv);
+                se = se * expf(m - nm) + expf(xv - nm);
+                m = nm;
+                ts += tv;
+                txs = fmaf(tv, xv, txs);
+            }
+            const float lse = m + logf(se);
+            acc += txs - lse * ts;
+            if (MODE == 0 && p.stats) {
+                p.stats[row * 2 * d + j] = lse;
+                p.stats[row * 2 * d + d + j] = ts;
+            }
+            if (MODE != 0) {
+                TX* gr = reinterpret_cast<TX*>(p.g) + row * p.ldg;
+                for (int c = 0; c < C; ++c) {
+                    const bool keep = __ldg(mk + c) != 0;
+                    const float xv = keep ? Elem<TX>::load1(xr + (int64_t)c * d + j) : 0.f;
+                    const float tv = Elem<TT>::load1(tr + (int64_t)c * d + j);
+                    Elem<TX>::store1(gr + (int64_t)c * d + j, keep ? wl * (tv - expf(xv - lse) * ts) : 0.f);
+                }
+            }
+        }
+        if (MODE != 1) {
+            acc = warp_sum(acc);
+            if (lane == 0) p.out_rows[row] = p.lam * acc;
+        }
+    }
+}
+
+template <typename TX, typename TT>
+static int launch_catce_masked(int mode, const CatceParams& p, cudaStream_t st) {
+    int64_t grid = (p.rows + 7) / 8;
+    if (grid > (int64_t)kNumSMs * 16) grid = (int64_t)kNumSMs * 16;
+    if (mode == 0) catce_masked_kernel<TX, TT, 0><<<(unsigned)grid, 256, 0, st>>>(p);
+    else if (mode == 1) catce_masked_kernel<TX, TT, 1><<<(unsigned)grid, 256, 0, st>>>(p);
+    else catce_masked_kernel<TX, TT, 2><<<(unsigned)grid, 256, 0, st>>>(p);
+    MMVAE_LAUNCH_CHECK();
+    return 0;
+}
+
 template <typename TX, typename TT>
 static int launch_catce(int mode, CatceParams p, cudaStream_t st) {
 #if MMVAE_CATCE_RING
@@ -1298,7 +1367,17 @@ extern "C" int mmvae_catce_rows(int mode, const void* recon, int64_t ld_recon, i
                                 int64_t ld_target, int dtype_target, int64_t rows, int64_t B, int64_t C, int64_t d,
                                 float lam, const float* w_rows, float w_const, float* out_rows, void* grad_recon,
                                 int64_t ld_grad, float* stats, void* stream) {
+    return mmvae_catce_rows_masked(mode, recon, ld_recon, dtype_recon, target, ld_target, dtype_target, rows, B, C, d, lam,
+                                   w_rows, w_const, out_rows, grad_recon, ld_grad, stats, nullptr, 0, stream);
+}
+
+extern "C" int mmvae_catce_rows_masked(int mode, const void* recon, int64_t ld_recon, int dtype_recon, const void* target,
+                                       int64_t ld_target, int dtype_target, int64_t rows, int64_t B, int64_t C, int64_t d,
+                                       float lam, const float* w_rows, float w_const, float* out_rows, void* grad_recon,
+                                       int64_t ld_grad, float* stats, const unsigned char* mask, int64_t ld_mask,
+                                       void* stream) {
     if (!recon || !target || rows <= 0 || B <= 0 || C <= 0 || d <= 0) return MMVAE_E_ARG;
+    if (mask && ld_mask < C) return MMVAE_E_ARG;
     if (mode < 0 || mode > 2) return MMVAE_E_ENUM;
     if (mode != 1 && !out_rows) return MMVAE_E_ARG;
     if (mode != 0 && !grad_recon) return MMVAE_E_ARG;
@@ -1309,7 +1388,15 @@ extern "C" int mmvae_catce_rows(int mode, const void* recon, int64_t ld_recon, i
     p.x = recon; p.t = target; p.g = grad_recon; p.w_rows = w_rows; p.out_rows = out_rows;
     p.ldx = ld_recon; p.ldt = ld_target; p.ldg = ld_grad; p.rows = rows; p.B = B; p.C = (int)C; p.d = (int)d;
     p.lam = lam; p.w_const = w_const; p.stats = stats;
+    p.mask = mask; p.ldm = ld_mask;
     cudaStream_t st = (cudaStream_t)stream;
+    if (mask) {  // text-decoder tail fused in: one kernel for every shape / stride / dtype pair
+        if (dtype_recon == MMVAE_F32 && dtype_target == MMVAE_F32) return launch_catce_masked<float, float>(mode, p, st);
+        if (dtype_recon == MMVAE_BF16 && dtype_target == MMVAE_F32) return launch_catce_masked<__nv_bfloat16, float>(mode, p, st);
+        if (dtype_recon == MMVAE_BF16 && dtype_target == MMVAE_BF16) return launch_catce_masked<__nv_bfloat16, __nv_bfloat16>(mode, p, st);
+        if (dtype_recon == MMVAE_F32 && dtype_target == MMVAE_BF16) return launch_catce_masked<float, __nv_bfloat16>(mode, p, st);
+        return MMVAE_E_ENUM;
+    }
     if (dtype_recon == MMVAE_F32 && dtype_target == MMVAE_F32) return launch_catce<float, float>(mode, p, st);
     if (dtype_recon == MMVAE_BF16 && dtype_target == MMVAE_F32) return launch_catce<__nv_bfloat16, float>(mode, p, st);
     if (dtype_recon == MMVAE_BF16 && dtype_target == MMVAE_BF16) {

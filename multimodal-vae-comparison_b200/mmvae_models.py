@@ -89,6 +89,12 @@ def _first(t):
     return t[0] if isinstance(t, (tuple, list)) else t
 
 
+def _unmasked(vae):
+    """A text decoder that declares ``returns_unmasked = True`` hands over its output BEFORE the reference's
+    "zero for padded area" multiply (decoders.py:722); category_ce then applies the padding mask inside its kernel."""
+    return bool(getattr(vae.dec, "returns_unmasked", False))
+
+
 def _ltype(vae):
     """Likelihood the kernels evaluate for this VAE.  A decoder that declares ``returns_logits = True`` hands over
     pre-sigmoid logits; its ``bce`` is then evaluated by the fused ``bce_logits`` kernel, which folds the reference
@@ -154,7 +160,7 @@ class MOE(TorchMMVAE):
                 loc = _first(vae.dec({"latents": z[r], "masks": data[name]["masks"]}))
                 # self reconstruction: always a Normal likelihood (dist.Normal(*px_z), :105-107)
                 S_self, rows_self = self.obj_fn.lpx_weighted_sum(loc, data[name], vae.llik_scaling, w_const=-1.0 / M,
-                                                                 ltype=_ltype(vae), family="normal")
+                                                                 ltype=_ltype(vae), unmasked=_unmasked(vae), family="normal")
                 total = total + S_self
                 n_keep = n_keep + (S_self != 0).float()
                 rows_log.append(rows_self)
@@ -165,7 +171,7 @@ class MOE(TorchMMVAE):
                 lwt = lq[src, r, 0] - lq[src, src, 0].detach()  # sum_d log q_r(z_s) - log q_s(z_s)   (:56-59)
                 iw = lwt.exp()
                 S_cross, rows_cross = self.obj_fn.lpx_weighted_sum(loc, data[name], vae.llik_scaling,
-                                                                   w_rows=-iw / M, ltype=_ltype(vae), family=_family(vae))
+                                                                   w_rows=-iw / M, ltype=_ltype(vae), unmasked=_unmasked(vae), family=_family(vae))
                 total = total + S_cross
                 n_keep = n_keep + (S_cross != 0).float()  # rows summing to exactly 0 are dropped (:73)
                 rows_log.append(iw.detach() * rows_cross)
@@ -183,11 +189,11 @@ class MOE(TorchMMVAE):
             vae = self.vaes[name]
             self.obj_fn.set_ltype(vae.ltype)
             rows.append(self.obj_fn.lpx_rows(_first(vae.dec({"latents": z[r], "masks": data[name]["masks"]})), data[name],
-                                             vae.llik_scaling, ltype=_ltype(vae), family="normal", out=buf[r, 0]))
+                                             vae.llik_scaling, ltype=_ltype(vae), unmasked=_unmasked(vae), family="normal", out=buf[r, 0]))
             src = self._cross_source(M, r)
             if src is not None:
                 rows.append(self.obj_fn.lpx_rows(_first(vae.dec({"latents": z[src], "masks": data[name]["masks"]})),
-                                                 data[name], vae.llik_scaling, ltype=_ltype(vae), family=_family(vae),
+                                                 data[name], vae.llik_scaling, ltype=_ltype(vae), unmasked=_unmasked(vae), family=_family(vae),
                                                  out=buf[r, 1]))
         # both combines read the row vectors through a pointer table; "lpx_z" is the same memory, for logging
         d = {"lpz": lpz, "lq": lq, "lpx_z": buf.view(M, L, K, B), "lpx_rows": rows}
@@ -257,7 +263,10 @@ class POE(TorchMMVAE):
                 masks = mods[name]["masks"] if i in sub else None
                 loc = _first(vae.dec({"latents": z, "masks": masks}))
                 S, rows = self.obj_fn.lpx_weighted_sum(loc, mods[name], vae.llik_scaling, w_const=-1.0,
-                                                       ltype=_ltype(vae), family=_family(vae), defer=True)
+                                                       ltype=_ltype(vae), family=_family(vae), defer=True,
+                                                       # (the decoder of a modality outside the subset runs without a
+                                                       # mask, :176 -- nothing to fuse there)
+                                                       unmasked=_unmasked(vae) and masks is not None)
                 terms.append(S)
                 if i == a:  # logging quirk: "mod == 'mod_{m+1}'" with m the subset index (:179-180)
                     rec_log[i] = ops.reduce_sum(rows, -1.0 / vae.llik_scaling)
@@ -361,7 +370,7 @@ class MoPOE(TorchMMVAE):
             self.obj_fn.set_ltype(vae.ltype)
             loc = _first(vae.dec({"latents": res[i]["z"], "masks": mods[name]["masks"]}))
             S, rows = self.obj_fn.lpx_weighted_sum(loc, mods[name], vae.llik_scaling, w_const=-1.0 / Bt,
-                                                   ltype=_ltype(vae), family=_family(vae),
+                                                   ltype=_ltype(vae), unmasked=_unmasked(vae), family=_family(vae),
                                                    defer=vae.ltype != "optimal_sigma")
             terms.append(S)
             ind.append(-rows / vae.llik_scaling)
@@ -488,7 +497,7 @@ class DMVAE(TorchMMVAE):
 
             def term(z_a):
                 loc = _first(vae.dec({"latents": torch.cat([z_a, z_pr], -1), "masks": masks}))
-                return self.obj_fn.lpx_weighted_sum(loc, mods[name], lam, w_const=-1.0, ltype=_ltype(vae), family=fam,
+                return self.obj_fn.lpx_weighted_sum(loc, mods[name], lam, w_const=-1.0, ltype=_ltype(vae), unmasked=_unmasked(vae), family=fam,
                                                     defer=True)
 
             S1, rows1 = term(z_sh)

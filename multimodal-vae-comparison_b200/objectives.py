@@ -21,11 +21,11 @@ class ReconLoss:
     feature axis) -- the only form the model plugins consume."""
 
     @staticmethod
-    def _rows(ltype, loc, target, lam, likelihood, group=None, out=None):
+    def _rows(ltype, loc, target, lam, likelihood, group=None, out=None, mask=None):
         if ltype in ELEMENTWISE:
             return ops.loglik_rows(loc, target, ltype, likelihood, lam, out=out)
         if ltype == "category_ce":
-            return ops.catce_rows(loc, target, lam, out=out)
+            return ops.catce_rows(loc, target, lam, out=out, mask=mask)
         if ltype == "optimal_sigma":
             rows = ops.osigma_rows(loc, target, lam, group)
             if out is not None:  # three-stage kernel sequence with its own output; mirror it into the stacked buffer
@@ -123,26 +123,43 @@ class BaseObjective:
             return "lprob_selfscale"
         return ltype
 
-    def lpx_rows(self, px_z, target, lam=1.0, ltype=None, family=None, out=None):
+    @staticmethod
+    def _unmasked(loc, target, ltype, unmasked):
+        """Decoders that declare ``returns_unmasked = True`` skip the reference's "zero for padded area" multiply
+        (decoders.py:722).  category_ce gets the mask fused into its kernel (returned as the second value); every other
+        likelihood applies the multiply here."""
+        mask = target.get("masks") if unmasked else None
+        if mask is None:
+            return loc, None
+        if ltype == "category_ce" and loc.dim() >= 2 and mask.shape[0] == target["data"].shape[0]:
+            return loc, mask
+        m = mask.to(loc.dtype)
+        return loc * m.reshape(*m.shape, *([1] * (loc.dim() - m.dim()))), None
+
+    def lpx_rows(self, px_z, target, lam=1.0, ltype=None, family=None, out=None, unmasked=False):
         """(recon_loss_fn(px_z, target, K) * lam).sum(-1) of the reference -> (K*B,) rows, k-major.
-        out: optional contiguous (K*B,) fp32 slice the kernel writes into (a row of a stacked buffer)."""
+        out: optional contiguous (K*B,) fp32 slice the kernel writes into (a row of a stacked buffer).
+        unmasked: the decoder output has not been multiplied by the padding mask yet (see _unmasked)."""
         loc, family = _loc_family(px_z, family)
         ltype = self._masked_ltype(ltype or self.ltype, target, loc)
         loc, data = self._prep(loc, target)
-        return ReconLoss._rows(ltype, loc, data, float(lam), family, self.group, out)
+        loc, mask = self._unmasked(loc, target, ltype, unmasked)
+        return ReconLoss._rows(ltype, loc, data, float(lam), family, self.group, out, mask)
 
-    def lpx_weighted_sum(self, px_z, target, lam=1.0, w_rows=None, w_const=1.0, ltype=None, family=None, defer=False):
+    def lpx_weighted_sum(self, px_z, target, lam=1.0, w_rows=None, w_const=1.0, ltype=None, family=None, defer=False,
+                         unmasked=False):
         """S = sum_r w_r * rows[r] (+ rows for logging) with the gradient produced in the same pass.  defer=True
         (constant weights): S is a placeholder whose batch sum is taken by ops.elbo_combine together with every
         other term of the loss (one launch)."""
         loc, family = _loc_family(px_z, family)
         ltype = self._masked_ltype(ltype or self.ltype, target, loc)
         loc, data = self._prep(loc, target)
+        loc, mask = self._unmasked(loc, target, ltype, unmasked)
         if ltype in ELEMENTWISE:
             return ops.loglik_weighted_sum(loc, data, ltype, family, float(lam), w_rows=w_rows, w_const=w_const,
                                            defer=defer)
         if ltype == "category_ce":
-            return ops.catce_weighted_sum(loc, data, float(lam), w_rows=w_rows, w_const=w_const, defer=defer)
+            return ops.catce_weighted_sum(loc, data, float(lam), w_rows=w_rows, w_const=w_const, defer=defer, mask=mask)
         # optimal_sigma needs a global statistic first: two passes regardless
         rows = ReconLoss._rows(ltype, loc, data, float(lam), family, self.group)
         S = torch.dot(rows, w_rows.float()) if w_rows is not None else w_const * rows.sum()

@@ -254,44 +254,58 @@ def _catce_geom(recon, target):
     return x, t, rows, B, C, d, ldx, ldt
 
 
+def _mask_bytes(mask, B, C):
+    """(B, C) padding mask -> contiguous uint8 (what mmvae_catce_rows_masked reads); None stays None."""
+    if mask is None:
+        return None
+    _need_cuda(mask)
+    if mask.dim() != 2 or mask.shape[0] != B or mask.shape[1] < C:
+        raise RuntimeError("mmvae_b200: padding mask %s does not cover the (B = %d, C = %d) class rows" % (
+            tuple(mask.shape), B, C))
+    m = mask.detach()
+    return (m if m.dtype == torch.uint8 else m.to(torch.uint8)).contiguous()
+
+
 class _CatceRows(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, recon, target, lam, out=None):
+    def forward(ctx, recon, target, lam, out=None, mask=None):
         ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(recon, target)
         x, t, rows, B, C, d, ldx, ldt = _catce_geom(recon.detach(), target.detach())
         out = _row_out(out, rows, recon.device)
         stats = torch.empty((rows, 2, d), dtype=torch.float32, device=recon.device)  # cached column statistics
-        call("mmvae_catce_rows", 0, _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, C, d, lam, _P(0), 0.0,
-             _ptr(out), _P(0), 0, _ptr(stats), _stream())
-        ctx.save_for_backward(x, t, stats)
+        mk = _mask_bytes(mask, B, C)
+        call("mmvae_catce_rows_masked", 0, _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, C, d, lam, _P(0), 0.0,
+             _ptr(out), _P(0), 0, _ptr(stats), _ptr(mk), 0 if mk is None else mk.stride(0), _stream())
+        ctx.save_for_backward(x, t, stats, mk)
         ctx.meta = (rows, B, C, d, ldx, ldt, lam, recon.shape)
         return out
 
     @staticmethod
     def backward(ctx, g_rows):
         if g_rows is None:
-            return None, None, None, None
-        x, t, stats = ctx.saved_tensors
+            return None, None, None, None, None
+        x, t, stats, mk = ctx.saved_tensors
         rows, B, C, d, ldx, ldt, lam, shape = ctx.meta
         w = g_rows.detach().to(torch.float32).contiguous()
         g = torch.empty((rows, C * d), dtype=x.dtype, device=x.device)
-        call("mmvae_catce_rows", 1, _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, C, d, lam, _ptr(w), 0.0,
-             _P(0), _ptr(g), C * d, _ptr(stats), _stream())
-        return g.view(shape), None, None, None
+        call("mmvae_catce_rows_masked", 1, _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, C, d, lam, _ptr(w), 0.0,
+             _P(0), _ptr(g), C * d, _ptr(stats), _ptr(mk), 0 if mk is None else mk.stride(0), _stream())
+        return g.view(shape), None, None, None, None
 
 
 class _CatceWeightedSum(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, recon, target, w_rows, w_const, lam, defer=False):
+    def forward(ctx, recon, target, w_rows, w_const, lam, defer=False, mask=None):
         ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
         _need_cuda(recon, target, w_rows)
         x, t, rows, B, C, d, ldx, ldt = _catce_geom(recon.detach(), target.detach())
         out = torch.empty(rows, dtype=torch.float32, device=recon.device)
         g = torch.empty((rows, C * d), dtype=x.dtype, device=x.device)
         w = None if w_rows is None else w_rows.detach().to(torch.float32).contiguous()
-        call("mmvae_catce_rows", 2, _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, C, d, lam, _ptr(w),
-             float(w_const), _ptr(out), _ptr(g), C * d, _P(0), _stream())
+        mk = _mask_bytes(mask, B, C)
+        call("mmvae_catce_rows_masked", 2, _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, C, d, lam, _ptr(w),
+             float(w_const), _ptr(out), _ptr(g), C * d, _P(0), _ptr(mk), 0 if mk is None else mk.stride(0), _stream())
         S = torch.empty((), dtype=torch.float32, device=recon.device)
         if defer:  # the batch sum is left to ops.elbo_combine (one launch for all terms): S is a placeholder
             if w is not None:
@@ -310,7 +324,7 @@ class _CatceWeightedSum(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gS, _g_rows):
         if gS is None:
-            return None, None, None, None, None, None
+            return None, None, None, None, None, None, None
         if ctx.g is None:
             raise RuntimeError("mmvae_b200: the fused ELBO gradient buffer is single-use (retain_graph unsupported)")
         g, ctx.g = ctx.g, None
@@ -318,15 +332,17 @@ class _CatceWeightedSum(torch.autograd.Function):
         if not _is_unit(gS):
             call("mmvae_scale_inplace", _ptr(g), _dt(g), g.numel(), _ptr(gs), _stream())
         gw = (gs * ctx.rows_out) if ctx.w_needs else None
-        return g.view(ctx.shape), None, gw, None, None, None
+        return g.view(ctx.shape), None, gw, None, None, None, None
 
 
-def catce_rows(recon, target, lam=1.0, out=None):
-    return _CatceRows.apply(recon, target, float(lam), out)
+def catce_rows(recon, target, lam=1.0, out=None, mask=None):
+    """mask: optional (B, C) padding mask of a text decoder that returns its output UNMASKED -- the kernel applies
+    recon * mask[:, :, None] (reference decoders.py:722) itself and returns the gradient of the unmasked tensor."""
+    return _CatceRows.apply(recon, target, float(lam), out, mask)
 
 
-def catce_weighted_sum(recon, target, lam=1.0, w_rows=None, w_const=1.0, defer=False):
-    S, rows = _CatceWeightedSum.apply(recon, target, w_rows, float(w_const), float(lam), bool(defer))
+def catce_weighted_sum(recon, target, lam=1.0, w_rows=None, w_const=1.0, defer=False, mask=None):
+    S, rows = _CatceWeightedSum.apply(recon, target, w_rows, float(w_const), float(lam), bool(defer), mask)
     return _deferred(S, rows, w_const, defer)
 
 

@@ -401,3 +401,59 @@ def test_fused_encoder_tail_matches_reference_golden(golden, idx):
                     ref["grad.%s.W" % name]) < TOL
     if ref.get("grad.pz_logits") is not None:
         assert _rel(model._pz_params[1].grad, ref["grad.pz_logits"]) < TOL
+
+
+def test_unmasked_text_decoder_matches_masked_one():
+    """A decoder that declares returns_unmasked hands over its output before the reference's padded-area multiply
+    (decoders.py:722); the plugin then fuses the mask into category_ce.  Same loss and gradients as the decoder that
+    multiplies itself (golden case poe_elbo_masks supplies shapes, masks and noise)."""
+    import mmvae_b200
+    import mmvae_b200.synthetic as syn
+    torch.manual_seed(5)
+    B, T, d, D = 6, 9, 27, 8
+    device = "cuda"
+
+    class TxtDec(torch.nn.Module):
+        def __init__(self, unmasked):
+            super().__init__()
+            self.lin = torch.nn.Linear(D, T * d)
+            self.data_dim = (T, d)
+            self.returns_unmasked = unmasked
+
+        def forward(self, z):
+            lat = z["latents"]
+            lat = lat.unsqueeze(0) if lat.dim() == 2 else lat
+            out = self.lin(lat).reshape(-1, T, d)
+            m = z["masks"]
+            if m is not None and not self.returns_unmasked:
+                out = out * m.repeat(out.shape[0] // m.shape[0], 1).unsqueeze(-1).float()
+            return out, torch.tensor(0.75, device=out.device)
+
+    lens = torch.randint(2, T + 1, (B,))
+    masks = (torch.arange(T)[None] < lens[:, None]).to(device)
+    img = torch.rand(B, 3, 8, 8, device=device)
+    txt = torch.nn.functional.one_hot(torch.randint(d, (B, T)), d).float().to(device) * masks[..., None]
+    results = []
+    for model_name, obj, K in (("poe", "elbo", 1), ("moe", "iwae", 3), ("mopoe", "elbo", 1)):
+        per = []
+        for unmasked in (False, True):
+            torch.manual_seed(7)
+            vaes = {"mod_1": syn.StubVAE(syn.LinearEncoder((3, 8, 8), D), syn.LinearDecoder(D, (3, 8, 8), squash=True), D, "bce",
+                                         id_name="mod_1"),
+                    "mod_2": syn.StubVAE(syn.LinearEncoder((T, d), D), TxtDec(unmasked), D, "category_ce", id_name="mod_2")}
+            model = mmvae_b200.MODEL_REGISTRY[model_name](vaes, D, {"obj": obj, "beta": 1.0, "K": K}, None).to(device)
+            gen = torch.Generator(device=device).manual_seed(3)
+            model.noise_source = lambda kind, shape: (torch.randn(shape, device=device, generator=gen) if kind == "normal"
+                                                       else torch.rand(shape, device=device, generator=gen) * 1.9 - 0.95)
+            batch = {"mod_1": {"data": img, "masks": None, "categorical": False},
+                     "mod_2": {"data": txt, "masks": masks, "categorical": False}}
+            out = model.objective(batch)
+            out["loss"].backward()
+            per.append((out["loss"].detach(), [p.grad.detach().clone() for p in model.parameters() if p.grad is not None]))
+        (l0, g0), (l1, g1) = per
+        assert _rel(l1, l0) < TOL, model_name
+        assert len(g0) == len(g1)
+        for a, b in zip(g1, g0):
+            assert _rel(a, b) < 5 * TOL, model_name  # (different summation order inside the fused kernel)
+        results.append(model_name)
+    assert results == ["poe", "moe", "mopoe"]

@@ -730,3 +730,32 @@ def test_catce_bf16_long_class_axes(ops, K, B, shape):
     (2.0 * S).backward()
     assert rel(S, (ref * w).sum()) < 1e-5 and rel(rows, ref) < 1e-5
     assert rel(xc2.grad, 2.0 * xo.grad) < BF16_TOL
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+@pytest.mark.parametrize("K,B,shape", [(1, 6, (45, 27)), (2, 5, (7, 27)), (1, 4, (12, 40))])
+def test_catce_fused_text_decoder_mask(ops, dtype, tol, K, B, shape):
+    """mmvae_catce_rows_masked: the text decoder's "zero for padded area" multiply (reference decoders.py:722) inside the
+    category_ce kernel -- forward rows, backward, fused value + gradient -- against the oracle fed with output * mask."""
+    g = torch.Generator().manual_seed(31)
+    T, d = shape
+    x = torch.randn(K * B, T, d, generator=g).to(dtype)
+    lens = torch.randint(1, T + 1, (B,), generator=g)
+    mask = torch.arange(T)[None, :] < lens[:, None]  # (B, T) bool
+    t = torch.nn.functional.one_hot(torch.randint(d, (B, T), generator=g), d).float() * mask[..., None]
+    w = torch.randn(K * B, generator=g)
+    lam = 0.8
+    xo = x.float().clone().requires_grad_(True)
+    xm = xo * mask.repeat(K, 1)[..., None].float()
+    ref = refmath.lpx_rows("category_ce", xm, t, lam, K)
+    (ref * w).sum().backward()
+    xc = x.cuda().requires_grad_(True)
+    out = ops.catce_rows(xc, t.cuda(), lam, mask=mask.cuda())
+    (out * w.cuda()).sum().backward()
+    assert rel(out, ref) < 1e-5
+    assert rel(xc.grad, xo.grad) < tol
+    assert float(xc.grad[~mask.repeat(K, 1).cuda()].abs().max()) == 0.0  # nothing flows into padded positions
+    xc2 = x.cuda().requires_grad_(True)
+    S, rows = ops.catce_weighted_sum(xc2, t.cuda(), lam, w_rows=w.cuda(), mask=mask.cuda())
+    S.backward()
+    assert rel(S, (ref * w).sum()) < 1e-5 and rel(xc2.grad, xo.grad) < tol
