@@ -217,6 +217,55 @@ __global__ void __launch_bounds__(256) dreg_stage1_kernel(const CombParams p, do
     if (threadIdx.x == 0) part[(size_t)sp * p.M * p.K + q] = tot;
 }
 
+// DReG stage 1, M == 2 with the packed softmax layout: one CTA per (k, batch split) handles BOTH modalities r, so that
+// a thread owns whole (k, b) coefficient vectors [r*2 + j] and writes them as 128-bit stores (the generic kernel, one CTA
+// per (r, k), wrote them as 8-byte halves 16 bytes apart: r2 launch list at C4 / B = 16k, 27 us for 46 MB).
+__global__ void __launch_bounds__(256) dreg_stage1_pk2_kernel(const CombParams p, double* __restrict__ part, int nsplit,
+                                                              float* __restrict__ lq_soft) {
+    __shared__ double red[32];
+    const int k = blockIdx.x, sp = blockIdx.y;
+    int64_t per = (p.B + nsplit - 1) / nsplit;
+    per = (per + 3) / 4 * 4;
+    const int64_t b0 = sp * per, b1 = min(p.B, b0 + per);
+    double acc[2] = {0.0, 0.0};
+    for (int64_t b = b0 + (int64_t)threadIdx.x * 4; b < b1; b += (int64_t)blockDim.x * 4) {
+        float soft[2][2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int64_t rk = (int64_t)r * p.K + k;
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.lpz + rk * p.B + b));
+            float lw[4] = {t.x, t.y, t.z, t.w};
+            for (int l = 0; l < p.L; ++l) {
+                const float4 u = __ldg(reinterpret_cast<const float4*>(p.lpx_ptr[r * p.L + l] + (int64_t)k * p.B + b));
+                lw[0] += u.x; lw[1] += u.y; lw[2] += u.z; lw[3] += u.w;
+            }
+            const float4 q0 = __ldg(reinterpret_cast<const float4*>(p.lq + (((int64_t)r * 2 + 0) * p.K + k) * p.B + b));
+            const float4 q1 = __ldg(reinterpret_cast<const float4*>(p.lq + (((int64_t)r * 2 + 1) * p.K + k) * p.B + b));
+            const float a0[4] = {q0.x, q0.y, q0.z, q0.w}, a1[4] = {q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float mx = fmaxf(a0[i], a1[i]);
+                const float e0 = expf(a0[i] - mx), e1 = expf(a1[i] - mx), se = e0 + e1;
+                acc[r] += (double)(lw[i] - (mx + logf(se) - logf(2.0f)));  // no beta in _m_dreg_looser (objectives.py:371)
+                const float inv = 1.0f / se;
+                soft[r][0][i] = e0 * inv;
+                soft[r][1][i] = e1 * inv;
+            }
+        }
+        if (lq_soft) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(lq_soft + ((int64_t)k * p.B + b + i) * 4) =
+                    make_float4(soft[0][0][i], soft[0][1][i], soft[1][0][i], soft[1][1][i]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const double tot = block_sum(acc[r], red);
+        if (threadIdx.x == 0) part[(size_t)sp * 2 * p.K + (size_t)r * p.K + k] = tot;
+    }
+}
+
 __global__ void dreg_partial_sum_kernel(const double* __restrict__ ws, int parts, int n, double* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -528,7 +577,11 @@ extern "C" int mmvae_objective_dreg_stage1_ptrs(const float* lpz, const float* l
     if (soft_packed && (M != 2 || !lq_soft || !aligned16(lq_soft))) return MMVAE_E_ARG;
     bool vec = (B % 4 == 0) && aligned16(lpz) && aligned16(lq) && (!lq_soft || aligned16(lq_soft));
     for (int i = 0; i < M * L; ++i) vec = vec && aligned16(p.lpx_ptr[i]);
-    if (vec)
+    if (vec && soft_packed && M == 2) {
+        nsplit = (int)((B + 1023) / 1024);  // half as many (r, k) rows as the generic grid: twice the batch splits
+        nsplit = nsplit < 1 ? 1 : (nsplit > DREG_MAX_SPLIT ? DREG_MAX_SPLIT : nsplit);
+        dreg_stage1_pk2_kernel<<<dim3(K, nsplit), 256, 0, st>>>(p, lw_part + (size_t)M * K, nsplit, lq_soft);
+    } else if (vec)
         dreg_stage1_kernel<4><<<grid, 256, 0, st>>>(p, lw_part + (size_t)M * K, nsplit, lq_soft, soft_packed);
     else
         dreg_stage1_kernel<1><<<grid, 256, 0, st>>>(p, lw_part + (size_t)M * K, nsplit, lq_soft, soft_packed);

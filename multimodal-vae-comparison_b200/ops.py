@@ -501,7 +501,7 @@ class _LatentDraws(torch.autograd.Function):
         ds = torch.empty_like(s_c)
         nws = _lib.load().mmvae_latent_draws_bwd_ws_floats(B, Dtot)
         ws = torch.empty(nws, dtype=torch.float32, device=dev)
-        dprior = torch.zeros(2, Dtot, dtype=torch.float32, device=dev)
+        dprior = torch.empty(2, Dtot, dtype=torch.float32, device=dev)  # fully written by the finalisation kernel
         call("mmvae_latent_draws_bwd_tail", _ptr(mu_c), _ptr(s_c), M, B, Dtot, ctx.arr, ctx.n, _ptr(row_masks),
              _ptr(mu0_c), _ptr(s0_c), _ptr(eps_c), _ptr(dz), _ptr(dkl), _ptr(dploc), _ptr(dpscale), int(ctx.s_raw),
              _ptr(dmu), _ptr(ds), _ptr(ws), _ptr(dprior[0]), _ptr(dprior[1]), _stream())
