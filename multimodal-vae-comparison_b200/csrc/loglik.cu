@@ -63,6 +63,22 @@ __device__ __forceinline__ float rcp_ftz(float x) {
     return r;
 }
 
+#ifndef MMVAE_BCE_BF16_NEWTON
+#define MMVAE_BCE_BF16_NEWTON 0
+#endif
+// r2, measured and rejected (build option): 1/v for v in [1e-12, 0.25] WITHOUT the MUFU pipe, for gradients that are
+// rounded to bf16 anyway -- magic-constant initial guess + two Newton steps on the FMA pipe, relative error 7e-6.
+// Hypothesis: the bf16 fused BCE pass moves 6 bytes per element and spends 3 MUFU operations on it (two LG2, one RCP);
+// at the HBM rate that is 3e12 MUFU/s of the 4.5e12 the 148 SMs have, so the math pipe, not memory, would be the
+// ceiling of its 5.0 TB/s (77 %).  Measured on C5 (B = 4096): 5.03 TB/s with the Newton form, 5.09 TB/s with MUFU.RCP:
+// the MUFU pipe is not the limit.
+__device__ __forceinline__ float rcp_newton2(float v) {
+    float r = __uint_as_float(0x7EF311C7u - __float_as_uint(v));
+    r = fmaf(r, fmaf(-v, r, 1.0f), r);
+    r = fmaf(r, fmaf(-v, r, 1.0f), r);
+    return r;
+}
+
 template <int LT>
 struct LogP {
     // the accumulated values are multiplied by this once per row (BCE accumulates in log2 units)
@@ -88,7 +104,8 @@ struct LogP {
         return fmaf(t, l0 - l1, l1);
     }
     // value of log p(t | x) and its derivative w.r.t. x
-    template <bool NEED_V, bool NEED_D>
+    // LOWP: the derivative is rounded to bf16 by the caller (cheaper reciprocal, see rcp_newton2)
+    template <bool NEED_V, bool NEED_D, bool LOWP = false>
     __device__ __forceinline__ void eval(float x, float t, float& v, float& d) const {
         if (LT == MMVAE_LT_BCE) {
             // F.binary_cross_entropy: log terms clamped at -100; backward denominator clamped at 1e-12
@@ -103,7 +120,10 @@ struct LogP {
                 const float l0 = fmaxf(lg2_ftz(x), -144.26950408889634f);
                 v = fmaf(t, l0 - l1, l1);
             }
-            if (NEED_D) d = (t - x) * rcp_ftz(fmaxf((1.0f - x) * x, 1e-12f));  // denominator in [1e-12, 0.25]
+            if (NEED_D) {  // denominator in [1e-12, 0.25]
+                const float den = fmaxf((1.0f - x) * x, 1e-12f);
+                d = (t - x) * (LOWP && MMVAE_BCE_BF16_NEWTON ? rcp_newton2(den) : rcp_ftz(den));
+            }
         } else if (LT == MMVAE_LT_BCE_LOGITS) {
             // x holds the decoder logit y.  s = sigmoid(y), xc = clamp(s, lo, hi) with lo = fp32(1e-6), hi = fp32(1-1e-6)
             // (reference decoders.py:96-97), value = t log xc + (1-t) log(1-xc).  log is monotonic, so the clamp moves
@@ -256,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, Tune<MODE>::kMinBlocks) loglik_kerne
 #pragma unroll
                 for (int e = 0; e < V; ++e) {
                     float v = 0.f, d = 0.f;
-                    f.template eval<false, true>(xv[e], tv[e], v, d);
+                    f.template eval<false, true, sizeof(TX) == 2>(xv[e], tv[e], v, d);
                     gv[e] = wl * d;
                 }
                 stg_stream(g + i, Elem<TX>::pack(gv));
@@ -265,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, Tune<MODE>::kMinBlocks) loglik_kerne
 #pragma unroll
         for (int e = 0; e < V; ++e) {
             float v = 0.f, d = 0.f;
-            f.template eval<NEED_V, NEED_D>(xv[e], tv[e], v, d);
+            f.template eval<NEED_V, NEED_D, sizeof(TX) == 2>(xv[e], tv[e], v, d);
             if (NEED_V) acc += v;
             if (NEED_D) gv[e] = wl * d;
         }
