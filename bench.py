@@ -60,6 +60,9 @@ def parse():
     ap.add_argument("--no-parity", action="store_true", help="N>1: skip the sharded-vs-unsharded numerical check")
     ap.add_argument("--no-roofline-timer", action="store_true",
                     help="skip the per-kernel CUDA-event leg (profiling runs under ncu: fewer launches to wade through)")
+    ap.add_argument("--fold-terms", action="store_true",
+                    help="ELBO workloads: the likelihood terms of a modality as ONE (terms*B, ...) leaf and launch -- what "
+                         "the plugins do for decoders that fold K (same bytes, same values, fewer and larger launches)")
     ap.add_argument("--sweep", default=None,
                     help="several configurations in one process group, one JSON line each: workload:global_batch[:w],... "
                          "(w: the number is the batch per GPU, weak scaling)")
@@ -434,7 +437,8 @@ def one_config(args, ctx):
     # Default: inside the step (parallel.GradSync hook -> side stream, overlapped with the likelihood backward and
     # captured in the step graph); --eager-sync: one eager NCCL call after the step.
     in_step_sync = world > 1 and not args.eager_sync
-    step = W.LeafStep(cfg, t, device=dev, group=coll, global_batch=B * world, sync_grads=in_step_sync)
+    step = W.LeafStep(cfg, t, device=dev, group=coll, global_batch=B * world, sync_grads=in_step_sync,
+                      fold=args.fold_terms)
     step.streams = args.streams
     W_, K_ = max(args.warmup, 3), args.steps
 
@@ -566,7 +570,10 @@ def one_config(args, ctx):
     if not args.no_e2e:
         # (a) leaf protocol: every input of the step lives in pinned host memory; H2D + loss read-back in the timed region
         pairs = [(step.mu, t["mu"]), (step.s, t["s"]), (step.pz_logits, t["pz_logits"])]
-        pairs += list(zip(step.targets, t["targets"])) + list(zip(step.recon, t["recon"]))
+        host_recon = t["recon"]
+        if step.fold:  # the folded leaves are the per-term tensors of a modality back to back
+            host_recon = [torch.cat([t["recon"][i] for i in step.fold_index[tm]], 0) for tm in sorted(step.fold_index)]
+        pairs += list(zip(step.targets, t["targets"])) + list(zip(step.recon, host_recon))
         if cfg["model"] == "moe":
             pairs.append((step.eps_stacked, torch.stack(t["noise"])))
             if step.dz is not None:
@@ -639,6 +646,9 @@ def one_config(args, ctx):
                             "over ranks"}
 
     conf = config_dict(args, cfg, B, world, scaling)
+    if step.fold:
+        conf["leaf_protocol"] = ("folded: one (terms*B, ...) reconstruction leaf and one likelihood launch per modality "
+                                 "(decoders that fold K); algorithmic bytes unchanged (2R+T per term)")
     run = {"grad_sync": sync_mode, "collectives": coll_note, "launch_mode": "cuda-graph" if runner is not step else "eager",
            "streams": "3 (likelihood terms alternate between two streams, latent kernels on a third; "
                       "forks/joins captured in the graph)" if step.streams == 3 else "single stream"}

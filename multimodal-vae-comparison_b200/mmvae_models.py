@@ -95,6 +95,17 @@ def _unmasked(vae):
     return bool(getattr(vae.dec, "returns_unmasked", False))
 
 
+def _fold_ok(vae, masks):
+    """Term folding: a decoder that declares ``folds_K = True`` decodes the rows of (K, B, Dz) latents independently and
+    returns them k-major -- what the reference's CNN / FNN decoders do (decoders.py:96-98, :400; NOT its transformer text
+    decoder, which drops K).  The latents of all likelihood terms of that modality (the 2^M-1 subset draws of
+    MVAE, the shared / joint / cross draws of DMVAE) are then stacked along K: ONE decoder call and ONE likelihood launch
+    over (terms * B) rows instead of one per term -- same values (row r reads target row r % B), larger grids, one
+    ramp-up and tail per modality.  Only without padding masks (they differ between the terms of MVAE), and not for
+    ``optimal_sigma``, whose sigma is the RMS over all elements of ONE reconstruction (objectives.py:502-509)."""
+    return bool(getattr(vae.dec, "folds_K", False)) and masks is None and vae.ltype != "optimal_sigma"
+
+
 def _ltype(vae):
     """Likelihood the kernels evaluate for this VAE.  A decoder that declares ``returns_logits = True`` hands over
     pre-sigmoid logits; its ``bce`` is then evaluated by the fused ``bce_logits`` kernel, which folds the reference
@@ -255,9 +266,25 @@ class POE(TorchMMVAE):
                                [Draw(mods=sub, prior=True, kl_mode=1, width=D, K=1) for sub in subsets], s_raw=raw)
         terms = []
         rec_log = [None] * M
+        folded = [_fold_ok(self.vaes[n], mods[n]["masks"]) for n in names]
+        for i, name in enumerate(names):
+            if not folded[i]:
+                continue
+            vae = self.vaes[name]
+            self.obj_fn.set_ltype(vae.ltype)
+            # the packed z of the S subset draws IS the (S, B, D) latent stack: one decoder call, one likelihood launch
+            z_all = torch.cat([res[a]["z"] for a in range(len(subsets))], 0)
+            loc = _first(vae.dec({"latents": z_all, "masks": None}))
+            S, rows = self.obj_fn.lpx_weighted_sum(loc, mods[name], vae.llik_scaling, w_const=-1.0, ltype=_ltype(vae),
+                                                   family=_family(vae), defer=True)
+            terms.append(S)
+            if i < len(subsets):  # logging quirk: modality m is paired with subset m (:179-180)
+                rec_log[i] = ops.reduce_sum(rows[i * B:(i + 1) * B], -1.0 / vae.llik_scaling)
         for a, sub in enumerate(subsets):
             z = res[a]["z"]
             for i, name in enumerate(names):
+                if folded[i]:
+                    continue
                 vae = self.vaes[name]
                 self.obj_fn.set_ltype(vae.ltype)
                 masks = mods[name]["masks"] if i in sub else None
@@ -500,8 +527,17 @@ class DMVAE(TorchMMVAE):
                 return self.obj_fn.lpx_weighted_sum(loc, mods[name], lam, w_const=-1.0, ltype=_ltype(vae), unmasked=_unmasked(vae), family=fam,
                                                     defer=True)
 
-            S1, rows1 = term(z_sh)
-            terms += [S1, term(z_joint)[0]] + [term(res[di]["z"])[0] for di in index["cross"][i].values()]
+            if _fold_ok(vae, masks):  # own shared, joint and cross latents as ONE (terms, B, Dz) stack
+                zs = [z_sh, z_joint] + [res[di]["z"] for di in index["cross"][i].values()]
+                z_all = torch.cat([torch.cat([z_a, z_pr], -1) for z_a in zs], 0)
+                loc = _first(vae.dec({"latents": z_all, "masks": None}))
+                S_all, rows_all = self.obj_fn.lpx_weighted_sum(loc, mods[name], lam, w_const=-1.0, ltype=_ltype(vae),
+                                                               family=fam, defer=True)
+                terms.append(S_all)
+                rows1 = rows_all[:z_sh.shape[1]]
+            else:
+                S1, rows1 = term(z_sh)
+                terms += [S1, term(z_joint)[0]] + [term(res[di]["z"])[0] for di in index["cross"][i].values()]
             # -(lpx - beta KL_shared) - (lpx_joint - beta KL_joint) - sum_cross (lpx_cross - beta KL_private)  (:455-463)
             kc += [beta, beta * len(index["cross"][i])]
             kg += [1.0 / M, 0.0]  # "kld" = sum_b mean_i KL_shared_i[b]

@@ -59,6 +59,10 @@ class LinearDecoder(nn.Module):
         self.squash = squash
         # True: hand the pre-sigmoid logits to the likelihood kernel, which applies the tail itself (bce_logits)
         self.returns_logits = bool(returns_logits and squash)
+        # rows of the (K, B, Dz) latents are decoded independently and come back k-major (the reference's CNN / FNN
+        # decoders do the same, decoders.py:96-98, :400): the plugins may stack the latents of several likelihood terms
+        # of this modality along K and decode them in ONE call (mmvae_models._fold_ok)
+        self.folds_K = True
         # the likelihood scale every reference decoder returns (decoders.py:98 builds it from a host scalar on every
         # call -- a pageable H2D copy, which a CUDA-graph capture does not allow): a non-persistent buffer instead
         self.register_buffer("_scale", torch.tensor(0.75), persistent=False)

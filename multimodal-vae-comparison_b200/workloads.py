@@ -109,7 +109,7 @@ class LeafStep:
     """One objective fwd+bwd on device-resident leaves through the CUDA path.  ``run()`` returns the loss tensor;
     gradients land in ``.grad`` of ``self.mu / self.s / self.pz_logits / self.recon[i]``."""
 
-    def __init__(self, cfg, tensors, device="cuda", beta=1.0, group=None, global_batch=None, sync_grads=False):
+    def __init__(self, cfg, tensors, device="cuda", beta=1.0, group=None, global_batch=None, sync_grads=False, fold=False):
         self.cfg, self.beta, self.group = cfg, beta, group
         self.model, self.obj = cfg["model"], cfg["obj"]
         self.M, self.K, self.D, self.pv, self.B = len(cfg["mods"]), cfg["K"], cfg["D"], cfg.get("private") or 0, cfg["B"]
@@ -124,6 +124,19 @@ class LeafStep:
         self.dz = tensors["dz"].to(dev) if tensors.get("dz") is not None else None
         self._z = None
         self.plan = term_plan(self.model, self.M)
+        # fold: the likelihood terms of one target modality as ONE (terms * B, ...) leaf -- what a plugin gets from a
+        # decoder that folds K when it stacks the latents of those terms (mmvae_models._fold_ok): one launch per modality,
+        # same values (row r reads target row r % B).  ELBO models with constant row weights only.
+        self.fold = bool(fold) and self.obj == "elbo" and self.model in ("poe", "dmvae", "mopoe") and \
+            not cfg.get("latent_only") and all(m["ltype"] != "optimal_sigma" for m in cfg["mods"])
+        if self.fold:
+            by_mod = {}
+            for i, (tm, _) in enumerate(self.plan):
+                by_mod.setdefault(tm, []).append(i)
+            self.recon = [torch.cat([tensors["recon"][i] for i in idx], 0).to(dev).requires_grad_(True)
+                          for tm, idx in sorted(by_mod.items())]
+            self.fold_index = {tm: idx for tm, idx in by_mod.items()}  # for tests: which terms a folded leaf holds
+            self.plan = [(tm, "folded") for tm in sorted(by_mod)]
         self.codes = [1 if m["dist"] == "laplace" else 0 for m in cfg["mods"]]
         if self.model == "mopoe":
             subs = mopoe_subsets(range(self.M))

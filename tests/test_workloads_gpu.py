@@ -143,3 +143,22 @@ def test_c2_full_size_properties():
     w_self1 = (g1[2].view(K * B, -1) * unit2.view(K * B, -1)).sum(-1) / (unit2.view(K * B, -1) ** 2).sum(-1)
     tot = (w_self0.view(K, B).sum(0) + w_self1.view(K, B).sum(0))
     assert torch.allclose(tot, -torch.ones_like(tot), rtol=0, atol=2e-4)
+
+
+@pytest.mark.parametrize("name,B", [("c1_poe_elbo_cdsprites_l1", 6), ("c5_dmvae_elbo_cub", 4)])
+def test_folded_leaf_protocol_equals_per_term(name, B):
+    """LeafStep(fold=True): the likelihood terms of a modality as one (terms * B, ...) leaf and one launch -- same loss,
+    same gradients (the folded leaf's gradient is the concatenation of the per-term ones)."""
+    import mmvae_b200.workloads as W
+    cfg, t = W.make_leaves(name, B=B, seed=5)
+    a = W.LeafStep(cfg, t, device="cuda")
+    la = a.run().detach().clone()
+    b = W.LeafStep(cfg, t, device="cuda", fold=True)
+    assert b.fold and len(b.recon) == len(cfg["mods"])
+    lb = b.run().detach().clone()
+    rel = lambda x, y: float((x.double() - y.double()).abs().max() / y.double().abs().max().clamp_min(1e-30))
+    assert rel(lb, la) < 1e-6
+    assert rel(b.mu.grad, a.mu.grad) < 1e-6 and rel(b.s.grad, a.s.grad) < 1e-6
+    for tm, idx in b.fold_index.items():
+        want = torch.cat([a.recon[i].grad for i in idx], 0)
+        assert rel(b.recon[sorted(b.fold_index).index(tm)].grad, want) < 1e-6
