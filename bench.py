@@ -68,6 +68,7 @@ def parse():
                          "(w: the number is the batch per GPU, weak scaling)")
     ap.add_argument("--nccl-only", action="store_true",
                     help="N>1: every collective through NCCL (default: the small ones fused into our kernels over peer memory)")
+    ap.add_argument("--cpu-budget-s", type=float, default=10.0, help="wall-clock budget of the cpu_baseline leg (seconds)")
     ap.add_argument("--cpu-batch", type=int, default=None,
                     help="opt-in: samples per step of the CPU arms (default: the workload batch, bounded by an element budget)")
     return ap.parse_args()
@@ -267,7 +268,7 @@ def cpu_baseline(args, cfg_full, B):
     torch.set_num_threads(cores)
     Bc = cpu_sample_batch(args, cfg_full, B)
     cfg, t = W.make_leaves(args.workload, B=Bc, seed=1234)
-    n, dt = cpu_steps(cfg, t, 1, budget_s=10.0)
+    n, dt = cpu_steps(cfg, t, 1, budget_s=args.cpu_budget_s)
     return {"value": Bc * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
             "sample": "%d of %d samples per step of %s (same shapes, K=%d), %d steps, %.1f s" % (
                 Bc, B, args.workload, cfg["K"], n, dt)}

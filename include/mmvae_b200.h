@@ -134,19 +134,21 @@ MMVAE_API int mmvae_catce_rows_masked(int mode, const void* recon, int64_t ld_re
  * stage 1 and 2:
  *   _sumsq : sumsq[0] += sum_all (t - x)^2, sumsq[1] += rows*P   (TWO doubles, caller zeroes them; a sharded caller
  *            all-reduces both in one collective).  _fwd / _bwd take the element count from n_total, or from sumsq[1]
- *            when n_total <= 0 (device-resident global count: uneven shards).
+ *            when n_total <= 0 (device-resident global count: uneven shards).  row_sumsq (rows floats, may be NULL)
+ *            receives sum_p (t - x)^2 of every row.
  *   _fwd   : log_sigma = -6 + softplus(log sqrt(sumsq/n_total) + 6);
- *            out_rows[r] = -lam * sum_p [ ((t-x)/sigma)^2 + log_sigma + 0.5 log 2pi ]; stats = {log_sigma, dlogsigma/du}
+ *            out_rows[r] = -lam * sum_p [ ((t-x)/sigma)^2 + log_sigma + 0.5 log 2pi ]; stats = {log_sigma, dlogsigma/du}.
+ *            With row_sumsq != NULL (the array stage 1 wrote) the rows follow from it without a pass over recon / target.
  *   _bwd   : only log_sigma carries gradient (the squared term is detached):
  *            grad[i] = -lam * P * (sum_r w_rows[r]) * sigmoid(u+6) * (x_i - t_i) / sumsq
  * ------------------------------------------------------------------------------------------------------- */
 MMVAE_API int mmvae_osigma_sumsq(const void* recon, int64_t ld_recon, int dtype_recon,
                        const void* target, int64_t ld_target, int dtype_target,
-                       int64_t rows, int64_t B, int64_t P, double* sumsq, void* stream);
+                       int64_t rows, int64_t B, int64_t P, double* sumsq, float* row_sumsq, void* stream);
 MMVAE_API int mmvae_osigma_fwd(const void* recon, int64_t ld_recon, int dtype_recon,
                      const void* target, int64_t ld_target, int dtype_target,
                      int64_t rows, int64_t B, int64_t P, float lam, const double* sumsq, double n_total,
-                     float* out_rows, float* stats2, void* workspace, void* stream);
+                     float* out_rows, float* stats2, const float* row_sumsq, void* stream);
 MMVAE_API int mmvae_osigma_bwd(const void* recon, int64_t ld_recon, int dtype_recon,
                      const void* target, int64_t ld_target, int dtype_target,
                      int64_t rows, int64_t B, int64_t P, float lam, const double* sumsq, double n_total,

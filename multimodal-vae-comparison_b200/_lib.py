@@ -39,7 +39,7 @@ SIGNATURES = {
     "mmvae_catce_rows": (c_i, [c_i] + _RECON + [c_i64, c_i64, c_i64, c_i64, c_f, c_p, c_f, c_p, c_p, c_i64, c_p, c_p]),
     "mmvae_catce_rows_masked": (c_i, [c_i] + _RECON + [c_i64, c_i64, c_i64, c_i64, c_f, c_p, c_f, c_p, c_p, c_i64, c_p, c_p,
                                              c_i64, c_p]),
-    "mmvae_osigma_sumsq": (c_i, _RECON + [c_i64, c_i64, c_i64, c_p, c_p]),
+    "mmvae_osigma_sumsq": (c_i, _RECON + [c_i64, c_i64, c_i64, c_p, c_p, c_p]),
     "mmvae_osigma_fwd": (c_i, _RECON + [c_i64, c_i64, c_i64, c_f, c_p, c_d, c_p, c_p, c_p, c_p]),
     "mmvae_osigma_bwd": (c_i, _RECON + [c_i64, c_i64, c_i64, c_f, c_p, c_d, c_p, c_p, c_p, c_i64, c_p]),
     "mmvae_latent_draws_fwd": (c_i, [c_p, c_p, c_i, c_i64, c_i, ctypes.POINTER(DrawDesc), c_i, c_p, c_p, c_p, c_p,

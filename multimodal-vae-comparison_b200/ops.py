@@ -360,7 +360,9 @@ class _OsigmaRows(torch.autograd.Function):
         if Pt != P or rows % B != 0:
             raise RuntimeError("mmvae_b200: optimal_sigma shapes %s vs %s" % (tuple(recon.shape), tuple(target.shape)))
         stat = torch.zeros(2, dtype=torch.float64, device=recon.device)  # [sumsq, element count], both device side
-        call("mmvae_osigma_sumsq", _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, P, _ptr(stat), _stream())
+        row_ss = torch.empty(rows, dtype=torch.float32, device=recon.device)  # per-row sums of squares: stage 2 needs no
+        call("mmvae_osigma_sumsq", _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, P, _ptr(stat), _ptr(row_ss),  # 2nd pass
+             _stream())
         n_total = 0.0  # <= 0: the kernels read the count from stat[1]
         peer, pgroup = _peer(group)
         if peer is not None:  # global RMS over every shard: sum AND count through peer memory
@@ -372,7 +374,7 @@ class _OsigmaRows(torch.autograd.Function):
         out = torch.empty(rows, dtype=torch.float32, device=recon.device)
         stats2 = torch.empty(2, dtype=torch.float32, device=recon.device)
         call("mmvae_osigma_fwd", _ptr(x), ldx, _dt(x), _ptr(t), ldt, _dt(t), rows, B, P, lam, _ptr(stat), n_total,
-             _ptr(out), _ptr(stats2), _P(0), _stream())
+             _ptr(out), _ptr(stats2), _ptr(row_ss), _stream())
         ctx.save_for_backward(x, t, stat)
         ctx.meta = (rows, B, P, ldx, ldt, lam, n_total, recon.shape, group, channel)
         return out

@@ -196,3 +196,43 @@ def test_helper_module_matches_reference_semantics(golden):
     import torch.distributions as dist
     p, q = dist.Normal(torch.zeros(4, 3), torch.ones(4, 3) * 0.5), dist.Normal(torch.zeros(1, 3), torch.ones(1, 3))
     assert torch.allclose(U.kl_divergence(p, q), refmath.kl_normal_normal(p.loc, p.scale, q.loc, q.scale))  # CPU: torch registry
+
+
+def test_encoder_tail_plumbing_on_cpu():
+    """Host logic of the fused encoder tail (no kernels involved): encode() keeps reference semantics for every caller
+    except the objectives; _stack_raw hands raw logits to the kernels only when every encoder is raw and of one width."""
+    import torch
+    import mmvae_b200
+    import mmvae_b200.synthetic as syn
+    torch.manual_seed(0)
+    D = 8
+
+    def vaes(raw1, raw2):
+        return {"mod_1": syn.StubVAE(syn.LinearEncoder((3, 4, 4), D, returns_raw_logvar=raw1),
+                                     syn.LinearDecoder(D, (3, 4, 4), squash=True), D, "bce", id_name="mod_1"),
+                "mod_2": syn.StubVAE(syn.LinearEncoder((5, 27), D, returns_raw_logvar=raw2),
+                                     syn.LinearDecoder(D, (5, 27), squash=False), D, "category_ce", id_name="mod_2")}
+
+    batch = {"mod_1": {"data": torch.rand(6, 3, 4, 4), "masks": None, "categorical": False},
+             "mod_2": {"data": torch.rand(6, 5, 27), "masks": None, "categorical": False}}
+    m = mmvae_b200.MODEL_REGISTRY["poe"](vaes(True, True), D, {"obj": "elbo", "beta": 1.0, "K": 1}, None)
+    enc = m.encode(batch)  # reference semantics: (mu, softmax(raw) + 1e-6)
+    s = enc["mod_1"]["shared"][1]
+    assert not enc["mod_1"]["raw"] and torch.allclose(s.sum(-1), torch.full((6,), 1 + D * 1e-6), atol=1e-5) and float(s.min()) > 0
+    enc_raw = m.encode(batch, raw_ok=True)
+    assert enc_raw["mod_1"]["raw"] and enc_raw["mod_1"]["shared"] is None
+    mu, sraw, flag = m._stack_raw(enc_raw, ["mod_1", "mod_2"], "shared")
+    assert flag and sraw.shape == (2, 6, D) and not torch.allclose(sraw.sum(-1), torch.ones(2, 6))
+    assert torch.allclose(torch.softmax(sraw[0], -1) + 1e-6, s, atol=1e-6)
+    # mixed encoders: the tail is applied on the host, the kernels get scales
+    m2 = mmvae_b200.MODEL_REGISTRY["poe"](vaes(True, False), D, {"obj": "elbo", "beta": 1.0, "K": 1}, None)
+    mu2, s2, flag2 = m2._stack_raw(m2.encode(batch, raw_ok=True), ["mod_1", "mod_2"], "shared")
+    assert not flag2 and torch.allclose(s2.sum(-1), torch.full((2, 6), 1 + D * 1e-6), atol=1e-5)
+
+
+def test_bench_sweep_and_fold_flags_parse():
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True).stdout
+    for flag in ("--sweep", "--fold-terms", "--nccl-only", "--cpu-budget-s", "--impl"):
+        assert flag in out
