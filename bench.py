@@ -309,15 +309,38 @@ class PluginStep:
             self.gobj = mmvae_b200.GraphedObjective(
                 self.model, {k: {"data": v.to(dev), "masks": None, "categorical": False} for k, v in self.host.items()})
         self.h2d = sum(v.numel() * v.element_size() for v in self.host.values())
+        # input pipeline: the batch of step i+1 is copied host -> device on a copy stream while step i computes (what a
+        # DataLoader with pinned memory and non_blocking copies gives a training loop); two sets of device buffers.
+        # Every step still copies its own inputs from pinned host memory inside the timed region.
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self._bufs = [{k: torch.empty_like(v, device=dev) for k, v in self.host.items()} for _ in range(2)]
+        self._ready = [None, None]
+        self._slot = 0
+        self._prefetch(0)
         self.api = "mmvae_b200.%s(vaes, ...).objective(batch) + backward, linear stand-in encoders/decoders (torch), %s%s%s" % (
-            cfg["model"], "mmvae_b200.GraphedObjective (one CUDA-graph replay per step)" if graphed else "eager launches",
+            cfg["model"], "mmvae_b200.GraphedObjective (one CUDA-graph replay per step), double-buffered H2D of the next batch behind the "
+            "current step" if graphed else "eager launches, double-buffered H2D",
             ("; decoder tail sigmoid+clamp fused into the likelihood kernel (bce_logits)" if fused_tail else "") +
             ("; encoder tail softmax+1e-6 fused into the latent kernels" if fused_enc else ""),
             "; flat-bucket NCCL all-reduce(SUM) of the parameter gradients" if world > 1 else "")
 
+    def _prefetch(self, slot):
+        torch = self.torch
+        self.copy_stream.wait_stream(torch.cuda.current_stream(self.dev))  # the slot's previous consumer is done
+        with torch.cuda.stream(self.copy_stream):
+            for k, v in self.host.items():
+                self._bufs[slot][k].copy_(v, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self._ready[slot] = ev
+
     def step(self):
-        dev = self.dev
-        batch = {k: {"data": v.to(dev, non_blocking=True), "masks": None, "categorical": False} for k, v in self.host.items()}
+        torch = self.torch
+        slot = self._slot
+        torch.cuda.current_stream(self.dev).wait_event(self._ready[slot])  # this step's inputs have arrived
+        batch = {k: {"data": v, "masks": None, "categorical": False} for k, v in self._bufs[slot].items()}
+        self._slot = 1 - slot
+        self._prefetch(self._slot)  # the next step's inputs travel while this step computes
         if self.gobj is not None:
             loss = self.gobj.step(batch)["loss"]
         else:
