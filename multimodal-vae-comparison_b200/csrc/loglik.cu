@@ -5,6 +5,8 @@
 //
 // Replaces reference objectives.py:30-52 / :103-125 / :389-458 (recon_loss_fn, reshape_for_loss, ReconLoss.bce,
 // lprob, mse, l1) together with the "* llik_scaling).sum(-1)" of every call site in mmvae_models.py.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mmvae {
@@ -78,6 +80,10 @@ __device__ __forceinline__ float rcp_newton2(float v) {
     r = fmaf(r, fmaf(-v, r, 1.0f), r);
     return r;
 }
+
+#ifndef MMVAE_LOGLIK_TILE_MIN_K
+#define MMVAE_LOGLIK_TILE_MIN_K 2
+#endif
 
 template <int LT>
 struct LogP {
@@ -450,7 +456,10 @@ static int launch(LoglikParams p, int dtx, int dtt, int ltype, cudaStream_t st) 
     p.tpr = plan_tpr(p.P, vect ? V : 1, p.cpr);
     {   // L2 tiling of the target: keep a tile of targets (<= 16 MB) resident while its K sample rows stream by
         const int64_t tile_rows = (16LL << 20) / (p.P * stt);
-        p.tile = (p.rows > p.B && tile_rows < p.B) ? (int)(tile_rows < 1 ? 1 : tile_rows) : (int)(p.B > 0x7fffffff ? 0x7fffffff : p.B);
+        // (tuning knob, read per call: the tiled order only pays when the target is re-read often enough)
+        static const int tile_min_k = [] { const char* e = getenv("MMVAE_LOGLIK_TILE_MIN_K"); return e ? atoi(e) : MMVAE_LOGLIK_TILE_MIN_K; }();
+        const bool tiled = p.rows > p.B && tile_rows < p.B && p.rows / p.B >= tile_min_k;
+        p.tile = tiled ? (int)(tile_rows < 1 ? 1 : tile_rows) : (int)(p.B > 0x7fffffff ? 0x7fffffff : p.B);
     }
     if (MODE != MODE_BWD && p.cpr > 1 && !p.ws) return MMVAE_E_ARG;
     if (dtx == MMVAE_F32 && dtt == MMVAE_F32) return launch2<float, float, MODE>(p, ltype, vect, st);
