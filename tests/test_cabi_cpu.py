@@ -236,3 +236,42 @@ def test_bench_sweep_and_fold_flags_parse():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True).stdout
     for flag in ("--sweep", "--fold-terms", "--nccl-only", "--cpu-budget-s", "--impl"):
         assert flag in out
+
+
+def test_round2_entry_points_validate_arguments_without_gpu(lib):
+    """Every check below returns before the first CUDA call: bad arguments are MMVAE_E_ARG (-1) / MMVAE_E_LIMIT (-3)."""
+    import ctypes
+    c_p, c_i, c_i64, c_f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+    P = lambda v=0x1000: c_p(v)  # never dereferenced on these paths
+    lib = ctypes.CDLL(lib.LIB_PATH)  # a private handle: its argtypes do not touch the package's binding
+    # ELBO combine: no terms and no KL segments; too many terms
+    f = lib.mmvae_objective_elbo
+    f.restype = c_i
+    f.argtypes = [c_p, c_p, c_p, c_i, c_p, c_i64, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p]
+    assert f(None, None, None, 0, None, 0, None, None, 0, P(), None, None, None, None, None) == -1
+    assert f(P(), P(), P(), 49, None, 0, None, None, 0, P(), None, None, None, None, None) == -3
+    assert f(None, None, None, 0, None, 8, P(), None, 2, P(), None, None, None, None, None) == -1  # KL segments without rows
+    # masked category_ce: mask rows shorter than the class axis
+    g = lib.mmvae_catce_rows_masked
+    g.restype = c_i
+    g.argtypes = [c_i, c_p, c_i64, c_i, c_p, c_i64, c_i, c_i64, c_i64, c_i64, c_i64, c_f, c_p, c_f, c_p, c_p, c_i64, c_p,
+                  c_p, c_i64, c_p]
+    assert g(0, P(), 45 * 27, 0, P(), 45 * 27, 0, 8, 8, 45, 27, 1.0, None, 0.0, P(), None, 0, None, P(), 44, None) == -1
+    # fused encoder tail: only the flat MoE kernels have it (D % 4 == 0, D <= 128, M <= 3)
+    h = lib.mmvae_moe_logdens_fwd_tail
+    h.restype = c_i
+    h.argtypes = [c_p, c_p, c_i, c_i64, c_i, c_i, ctypes.POINTER(ctypes.c_int32), c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]
+    dists = (ctypes.c_int32 * 2)(0, 0)
+    assert h(P(), P(), 2, 8, 10, 3, dists, P(), P(), P(), P(), P(), P(), None, None) == -3
+    # peer-memory collectives: more values than a 4 KB slot, bad rank
+    k = lib.mmvae_peer_allreduce_f64
+    k.restype = c_i
+    k.argtypes = [c_p, c_i, c_p, c_i, c_i, c_i, c_p]
+    assert k(P(), 513, P(), 0, 2, 0, None) == -3
+    assert k(P(), 4, P(), 2, 2, 0, None) == -1
+    assert k(P(), 4, P(), 0, 2, 8, None) == -3  # channel >= MMVAE_PEER_CHANNELS
+    # DReG packed coefficients need M == 2
+    s1 = lib.mmvae_objective_dreg_stage1_ptrs
+    s1.restype = c_i
+    s1.argtypes = [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i64, c_p, c_p, c_i, c_p]
+    assert s1(P(), P(), P(), None, 3, 1, 4, 8, P(), P(), 1, None) == -1
